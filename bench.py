@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""Headline benchmark: Verlet-build neighbours/second (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one complete VerletList build -- LinkedCellList binning, gather-permute,
+count pass, offsets scan, fill pass, including the allocation-size read-back -- of the
+16 078 716-atom FCC Lennard-Jones configuration (BASELINE.json configs[2]:
+FullNeighborTag, VerletLayoutCSR, cutoff 2.5 sigma + 0.3 sigma skin), which fits one B200.
+At N > 1 the SAME configuration is slab-decomposed along x over N GPUs (strong scaling):
+every step then also selects the ghost layer, builds the Halo plan and gathers ghost
+positions over NCCL before the local build.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is defined.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "verlet_build_neighbors_per_sec"
+UNIT = "neighbors/s"
+FCC_CELLS = 159          # 4 * 159^3 = 16 078 716 atoms
+RADIUS = 2.8             # 2.5 sigma cutoff + 0.3 sigma skin
+CELL_RATIO = 1.0
+CPU_SAMPLE_CELLS = 64    # bounded CPU sample: 4 * 64^3 = 1 048 576 atoms of the same lattice
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def _workload_config(n_gpus):
+    return {
+        "workload": "cfg3: 16 078 716-atom FCC LJ (rho*=0.8442), r = 2.8 sigma, cell_size_ratio 1.0, "
+                    "FullNeighborTag, VerletLayoutCSR" + ("" if n_gpus == 1 else
+                    f", x-slab decomposition over {n_gpus} GPUs with Halo ghost gather each step"),
+        "particles": 4 * FCC_CELLS**3,
+        "radius": RADIUS,
+        "cell_size_ratio": CELL_RATIO,
+        "algorithm": "FullNeighborTag",
+        "layout": "VerletLayoutCSR",
+        "positions": "AoSoA<double[3]> slice, VectorLength 32",
+        "l2_policy": "inputs_exceed_l2 (386 MB of positions + 5 GB of output per step vs 126 MB L2)",
+    }
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(smax)) if smax else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ----------------------------------------------------------------------------------- CPU arm
+def cpu_reference_run(steps: int, warmup: int, cells: int = CPU_SAMPLE_CELLS):
+    """Time the CPU port of the reference path (oracle/) on a bounded FCC sample."""
+    import oracle
+    from cabana_b200 import datasets
+
+    ps = datasets.fcc_lattice(cells)
+    x = oracle.slice_from_xyz(ps.xyz, vlen=16)  # host AoSoA vector length (PerformanceTraits)
+    threads = oracle.num_threads()
+    times, total = [], 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        res = oracle.verlet_build(x, 0, ps.n, ps.radius, CELL_RATIO, ps.grid_min, ps.grid_max,
+                                  algo=oracle.FULL, layout=oracle.CSR)
+        dt = time.perf_counter() - t0
+        total = res.total
+        if it >= warmup:
+            times.append(dt)
+    avg = float(np.mean(times))
+    return {
+        "value": total / avg,
+        "unit": UNIT,
+        "cores": threads,
+        "kind": "port",
+        "sample": f"{ps.n}-atom FCC sub-lattice ({cells}^3 cells) of the same workload, "
+                  f"{len(times)} timed builds, avg {avg*1e3:.1f} ms (min {min(times)*1e3:.1f}, "
+                  f"max {max(times)*1e3:.1f}); C++/OpenMP restatement of the reference "
+                  "(Kokkos is not installable here), -O3 -ffp-contract=off",
+    }, avg, total, ps.n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 2))
+    cpu, avg, total, n = cpu_reference_run(steps, warmup)
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": avg * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": _workload_config(1),
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------- GPU arm
+def _fcc_slab(rank, world):
+    """Owned atoms of this rank: lattice cells [c0,c1) along x; bounds at multiples of a."""
+    from cabana_b200 import datasets
+
+    a = (4.0 / datasets.FCC_DENSITY) ** (1.0 / 3.0)
+    cuts = [round(FCC_CELLS * g / world) for g in range(world + 1)]
+    bounds = [c * a for c in cuts]
+    bounds[-1] = FCC_CELLS * a
+    c0, c1 = cuts[rank], cuts[rank + 1]
+    ps = datasets.fcc_lattice(c1 - c0, radius=RADIUS, cells_yz=FCC_CELLS)
+    xyz = ps.xyz
+    xyz[:, 0] += c0 * a
+    return xyz, bounds, (FCC_CELLS * a,) * 3
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from cabana_b200 import build as cb_build
+    if rank == 0:
+        cb_build.build()
+    if world > 1:
+        dist.barrier()
+    from cabana_b200 import capi, comm
+    from cabana_b200 import core as cb
+    import ctypes as C
+
+    L = capi.lib()
+    xyz, bounds, gmax = _fcc_slab(rank, world)
+    num_local = xyz.shape[0]
+    gmin = (0.0, 0.0, 0.0)
+
+    lst = cb.VerletList(algorithm=cb.FULL, layout=cb.CSR)
+    capi.check(L.cb_verlet_set_profiling(lst._h, 1))
+
+    if world == 1:
+        x = cb.slice_from_array(xyz, vlen=32)
+
+        def step():
+            lst.build(x, 0, num_local, RADIUS, CELL_RATIO, gmin, gmax)
+            return lst.total
+    else:
+        slab = comm.SlabDecomposition(bounds, RADIUS)
+        lgx = slab.local_grid_x()
+        lmin = (lgx[0], 0.0, 0.0)
+        lmax = (lgx[1], gmax[1], gmax[2])
+        # capacity for owned + ghosts: two faces of thickness ~r
+        cap = num_local + int(2.2 * RADIUS / (bounds[rank + 1] - bounds[rank]) * num_local) + 1024
+        store = np.zeros((cap, 3))
+        store[:num_local] = xyz
+        x_all = cb.slice_from_array(store, vlen=32)
+
+        def step():
+            x_own = cb.Slice(x_all.data, num_local, x_all.outer_stride, x_all.vlen, x_all.comp_stride, 3)
+            halo = slab.create_halo(x_own, num_local)
+            n_tot = halo.numLocal() + halo.numGhost()
+            assert n_tot <= cap, "ghost capacity exceeded"
+            x_tot = cb.Slice(x_all.data, n_tot, x_all.outer_stride, x_all.vlen, x_all.comp_stride, 3)
+            comm.gather(halo, x_tot)
+            lst.build(x_tot, 0, num_local, RADIUS, CELL_RATIO, lmin, lmax)
+            return lst.total
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        local_total = step()
+    sync_all()
+
+    # ---- timed region: device events on the launching stream, barrier+sync both sides
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    phase_sum = np.zeros(6)
+    launches0 = L.cb_kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record()
+    for _ in range(args.steps):
+        local_total = step()
+        ph = (C.c_double * 6)()
+        capi.check(L.cb_verlet_get_phase_times(lst._h, ph))
+        phase_sum += np.array(list(ph))
+    ev1.record()
+    sync_all()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = L.cb_kernel_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([elapsed_ms, float(local_total), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        elapsed_ms = float(tmax[0])
+        global_total = float(tsum[1])
+        launches = int(tsum[2])
+    else:
+        global_total = float(local_total)
+    ms_per_step = elapsed_ms / args.steps
+    value = global_total / (ms_per_step * 1e-3)
+
+    # ---- per-kernel roofline for the dominant kernel (fill pass), rank 0's numbers
+    peak, peak_kind = _peaks()
+    phases = phase_sum / args.steps  # ms: bin, gather, count, scan, fill, total
+    n_rows = num_local
+    k_s = local_total / max(n_rows, 1)
+    # fill kernel algorithmic bytes per launch: read positions 24 + ids 4 + row offset 4,
+    # write counts 4 + 4*K_s neighbour ids   (36 + 4 K_s per particle)
+    fill_bytes = n_rows * (36.0 + 4.0 * k_s)
+    fill_gbs = fill_bytes / (phases[4] * 1e-3) / 1e9 if phases[4] > 0 else 0.0
+    # whole step: bin 32 + build 36 + 4 K_s
+    step_bytes = n_rows * (68.0 + 4.0 * k_s)
+    step_gbs = step_bytes / (phases[5] * 1e-3) / 1e9 if phases[5] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get("k_verlet_pass_fill_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "hbm", "kernel": "k_verlet_pass<fill> (dominant kernel of the step)",
+        "achieved": fill_gbs, "peak": peak, "unit": "GB/s", "frac": fill_gbs / peak,
+        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "traffic": traffic,
+        "algorithmic_bytes_per_launch": fill_bytes,
+        "kernel_ms": float(phases[4]),
+        "step": {"achieved": step_gbs, "frac": step_gbs / peak, "algorithmic_bytes": step_bytes,
+                 "note": "whole build (bin+gather+count+scan+fill) against the HBM roof"},
+        "phase_ms": {"binning": float(phases[0]), "gather_permute": float(phases[1]),
+                     "count_pass": float(phases[2]), "offset_scan": float(phases[3]),
+                     "fill_pass": float(phases[4]), "build_total": float(phases[5])},
+    }
+
+    # ---- end-to-end: host buffers in, list back to host, copies inside the timed region
+    e2e = None
+    if world == 1:
+        host_x = torch.from_numpy(np.ascontiguousarray(xyz)).pin_memory()
+        counts_h = torch.empty(num_local, dtype=torch.int32).pin_memory()
+        offsets_h = torch.empty(num_local, dtype=torch.int32).pin_memory()
+        nb_h = torch.empty(int(lst.total), dtype=torch.int32).pin_memory()
+        e_steps = max(1, min(args.steps, 5))
+
+        def e2e_step():
+            lst.build_host(host_x, 0, num_local, RADIUS, CELL_RATIO, gmin, gmax)
+            lst.copy_to_host(counts_h, offsets_h, nb_h)
+
+        e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e_steps
+        assert int(counts_h.to(torch.int64).sum()) == lst.total
+        e2e = {"value": lst.total / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": e_steps,
+               "h2d_bytes_per_step": int(host_x.numel() * 8),
+               "d2h_bytes_per_step": int(4 * (2 * num_local + lst.total)),
+               "api": "cb_verlet_build_host + cb_verlet_copy_to_host (pinned host buffers)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu, _, _, _ = cpu_reference_run(steps=3, warmup=1)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": _workload_config(world),
+        "neighbors_per_step": global_total,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

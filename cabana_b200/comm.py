@@ -1,0 +1,298 @@
+"""Halo / Distributor for the slab decomposition, over torch.distributed (NCCL on NVLink).
+
+Mirrors the reference's communication-plan surface for the hot path:
+  CommunicationPlan   core/src/Cabana_CommunicationPlanBase.hpp (counts, steering,
+                      neighbour order: self first, then ascending ranks, :374-394)
+  Halo / gather / scatter      core/src/Cabana_Halo.hpp:59-268, :392-682;
+                               core/src/impl/Cabana_Halo_Mpi.hpp:41-125, :269-350
+  Distributor / migrate        core/src/Cabana_Distributor.hpp:62-146, :275-337;
+                               core/src/impl/Cabana_Migrate_Mpi.hpp:41-177
+with CommSpaceType = Nccl instead of Mpi: export counts are
+exchanged with ONE all_gather of a world-size vector (replacing a point-to-point per
+neighbour), payloads with grouped send/recv on the current CUDA stream between the pack
+and unpack kernels (no host fence, no barrier).
+
+The device work (count/steer, pack, unpack, scatter-add, slab selection) is the C ABI's
+(include/cabana_b200.h, csrc/cb_comm.cu).  `kernels` is injectable so the host-side plan
+logic can be exercised with world_size-2 gloo tests on a CPU-only box; the package itself
+only ships the CUDA implementation (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import capi
+from .core import Slice, _stream
+
+
+class CudaCommKernels:
+    """The product implementation: csrc/cb_comm.cu through the C ABI."""
+
+    device = "cuda"
+
+    def count_and_steer(self, export_ranks: torch.Tensor, export_ids: torch.Tensor | None, num_ranks: int):
+        n = export_ranks.numel()
+        counts = (C.c_int64 * num_ranks)()
+        offsets = (C.c_int64 * (num_ranks + 1))()
+        steering = torch.empty(max(n, 1), dtype=torch.int32, device="cuda")
+        assert export_ranks.dtype == torch.int32 and export_ranks.is_cuda
+        ids_ptr = C.c_void_p(export_ids.data_ptr()) if export_ids is not None else None
+        capi.check(capi.lib().cb_comm_count_and_steer(
+            C.c_void_p(export_ranks.data_ptr()), C.c_int64(n), C.c_int(num_ranks), counts, offsets,
+            C.c_void_p(steering.data_ptr()), ids_ptr, _stream()))
+        return list(counts), list(offsets), steering
+
+    def tuple_bytes(self, fields) -> int:
+        arr = (capi.Field * len(fields))(*[f.field_desc() for f in fields])
+        return int(capi.lib().cb_comm_tuple_bytes(arr, len(fields)))
+
+    def pack(self, fields, steering: torch.Tensor, count: int, out: torch.Tensor):
+        arr = (capi.Field * len(fields))(*[f.field_desc() for f in fields])
+        capi.check(capi.lib().cb_comm_pack(arr, len(fields), C.c_void_p(steering.data_ptr()),
+                                           C.c_int64(count), C.c_void_p(out.data_ptr()), _stream()))
+
+    def unpack(self, fields, dst_begin: int, count: int, buf: torch.Tensor):
+        arr = (capi.Field * len(fields))(*[f.field_desc() for f in fields])
+        capi.check(capi.lib().cb_comm_unpack(arr, len(fields), C.c_int64(dst_begin), C.c_int64(count),
+                                             C.c_void_p(buf.data_ptr()), _stream()))
+
+    def scatter_add(self, field, steering: torch.Tensor, count: int, buf: torch.Tensor):
+        fd = field.field_desc()
+        capi.check(capi.lib().cb_comm_scatter_add(C.byref(fd), C.c_void_p(steering.data_ptr()),
+                                                  C.c_int64(count), C.c_void_p(buf.data_ptr()), _stream()))
+
+    def slab_halo_select(self, x: Slice, num_local, lo_thresh, hi_thresh, lo_rank, hi_rank):
+        ranks = torch.empty(2 * max(num_local, 1), dtype=torch.int32, device="cuda")
+        ids = torch.empty(2 * max(num_local, 1), dtype=torch.int32, device="cuda")
+        d = x.positions_desc()
+        capi.check(capi.lib().cb_slab_halo_select(
+            C.byref(d), C.c_int64(num_local), C.c_double(lo_thresh), C.c_double(hi_thresh),
+            C.c_int(lo_rank), C.c_int(hi_rank), C.c_void_p(ranks.data_ptr()),
+            C.c_void_p(ids.data_ptr()), _stream()))
+        return ids[: 2 * num_local], ranks[: 2 * num_local]
+
+    def slab_destinations(self, x: Slice, num_local, bounds):
+        out = torch.empty(max(num_local, 1), dtype=torch.int32, device="cuda")
+        d = x.positions_desc()
+        b = (C.c_double * len(bounds))(*[float(v) for v in bounds])
+        capi.check(capi.lib().cb_slab_migrate_destinations(
+            C.byref(d), C.c_int64(num_local), b, C.c_int(len(bounds) - 1),
+            C.c_void_p(out.data_ptr()), _stream()))
+        return out[:num_local]
+
+
+def _world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+class CommunicationPlan:
+    """Export-built plan with the reference's neighbour ordering.
+
+    neighbors: self first, then the other ranks that we export to or import from in
+    ascending order (getUniqueTopology, Cabana_CommunicationPlanBase.hpp:374-394).
+    Export blocks and import blocks are laid out in that neighbour order
+    (:626-637; impl/Cabana_Halo_Mpi.hpp:73-101).
+    """
+
+    def __init__(self, export_ranks: torch.Tensor, export_ids: torch.Tensor | None = None,
+                 group=None, kernels=None):
+        self.kernels = kernels if kernels is not None else CudaCommKernels()
+        self.group = group
+        self.rank, self.world = _world(group)
+        counts, offsets, steering = self.kernels.count_and_steer(export_ranks, export_ids, self.world)
+        # counts exchange: one all_gather of the export-count vector (replaces the
+        # per-neighbour MPI_Send of one unsigned long, impl/Cabana_CommunicationPlan_Mpi.hpp:152-178)
+        mine = torch.tensor(counts, dtype=torch.int64, device=self.kernels.device)
+        if self.world > 1:
+            allc = torch.empty(self.world * self.world, dtype=torch.int64, device=self.kernels.device)
+            dist.all_gather_into_tensor(allc, mine, group=group)
+            allc = allc.view(self.world, self.world).cpu()
+        else:
+            allc = mine.view(1, 1).cpu()
+        self.export_matrix = allc  # [src, dst]
+        imports = [int(allc[s, self.rank]) for s in range(self.world)]
+        others = sorted(r for r in range(self.world)
+                        if r != self.rank and (counts[r] > 0 or imports[r] > 0))
+        self.neighbors = [self.rank] + others
+        self.num_export = [counts[r] for r in self.neighbors]
+        self.num_import = [imports[r] for r in self.neighbors]
+        # steering comes back grouped by ascending rank; re-express as neighbour-ordered blocks
+        self._steer_rank_offsets = offsets
+        self._steering = steering
+        self.export_block = {r: (offsets[r], counts[r]) for r in self.neighbors}
+        self.total_export = sum(self.num_export)
+        self.total_import = sum(self.num_import)
+        off = 0
+        self.import_offset = {}
+        for r, c in zip(self.neighbors, self.num_import):
+            self.import_offset[r] = off
+            off += c
+
+    def numNeighbor(self):
+        return len(self.neighbors)
+
+    def neighborRank(self, n):
+        return self.neighbors[n]
+
+    def numExport(self, n):
+        return self.num_export[n]
+
+    def numImport(self, n):
+        return self.num_import[n]
+
+    def totalNumExport(self):
+        return self.total_export
+
+    def totalNumImport(self):
+        return self.total_import
+
+    def steering_for(self, r) -> torch.Tensor:
+        o, c = self.export_block[r]
+        return self._steering[o : o + c]
+
+    # -- payload exchange: sends[r] / recvs[r] are byte tensors per neighbour rank
+    def exchange(self, sends: dict, recvs: dict):
+        ops = []
+        for r in self.neighbors:
+            if r == self.rank:
+                continue
+            if r in recvs and recvs[r].numel() > 0:
+                ops.append(dist.P2POp(dist.irecv, recvs[r], r, group=self.group))
+        for r in self.neighbors:
+            if r == self.rank:
+                continue
+            if r in sends and sends[r].numel() > 0:
+                ops.append(dist.P2POp(dist.isend, sends[r], r, group=self.group))
+        if self.rank in sends and self.rank in recvs and sends[self.rank].numel() > 0:
+            recvs[self.rank].copy_(sends[self.rank])  # self-send short-circuits to a copy
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+
+class Halo(CommunicationPlan):
+    """Cabana::Halo<MemorySpace, Export, Nccl> (core/src/Cabana_Halo.hpp:59-268)."""
+
+    def __init__(self, num_local: int, export_ids: torch.Tensor, export_ranks: torch.Tensor,
+                 group=None, kernels=None):
+        super().__init__(export_ranks, export_ids, group, kernels)
+        self._num_local = int(num_local)
+
+    def numLocal(self):
+        return self._num_local
+
+    def numGhost(self):
+        return self.total_import
+
+
+def gather(halo: Halo, *fields: Slice):
+    """Cabana::gather(halo, aosoa|slice) (Cabana_Halo.hpp:677-682; impl/Cabana_Halo_Mpi.hpp:41-125).
+
+    Every field must hold numLocal() + numGhost() elements; ghosts land at
+    [numLocal(), numLocal()+numGhost()) grouped by source rank in neighbour order.
+    """
+    k = halo.kernels
+    tb = k.tuple_bytes(fields)
+    sends, recvs = {}, {}
+    for r, ne, ni in zip(halo.neighbors, halo.num_export, halo.num_import):
+        if ne > 0:
+            buf = torch.empty(ne * tb, dtype=torch.uint8, device=k.device)
+            k.pack(fields, halo.steering_for(r), ne, buf)
+            sends[r] = buf
+        if ni > 0:
+            recvs[r] = torch.empty(ni * tb, dtype=torch.uint8, device=k.device)
+    halo.exchange(sends, recvs)
+    for r, ni in zip(halo.neighbors, halo.num_import):
+        if ni > 0:
+            k.unpack(fields, halo.numLocal() + halo.import_offset[r], ni, recvs[r])
+
+
+def scatter(halo: Halo, field: Slice):
+    """Cabana::scatter(halo, slice) (impl/Cabana_Halo_Mpi.hpp:236-350): ghost values are sent
+    back to their owners and atomically summed into them."""
+    k = halo.kernels
+    nc = field.num_comp
+    sends, recvs = {}, {}
+    ghost = field.to_array()  # (n, nc) dense copy of the field, ghosts at the tail
+    for r, ne, ni in zip(halo.neighbors, halo.num_export, halo.num_import):
+        if ni > 0:
+            b = halo.numLocal() + halo.import_offset[r]
+            sends[r] = ghost[b : b + ni].contiguous().view(torch.uint8).reshape(-1)
+        if ne > 0:
+            recvs[r] = torch.empty(ne * nc * 8, dtype=torch.uint8, device=k.device)
+    halo.exchange(sends, recvs)
+    for r, ne in zip(halo.neighbors, halo.num_export):
+        if ne > 0:
+            k.scatter_add(field, halo.steering_for(r), ne, recvs[r])
+
+
+class Distributor(CommunicationPlan):
+    """Cabana::Distributor<MemorySpace, Nccl> (core/src/Cabana_Distributor.hpp:62-146).
+
+    export_ranks[i] = destination rank of element i, -1 to drop it.
+    """
+
+    def __init__(self, export_ranks: torch.Tensor, group=None, kernels=None):
+        super().__init__(export_ranks, None, group, kernels)
+
+
+def migrate(distributor: Distributor, src_fields, dst_fields):
+    """Cabana::migrate(distributor, src, dst) (Cabana_Distributor.hpp:330-337;
+    impl/Cabana_Migrate_Mpi.hpp:41-177): dst holds totalNumImport() elements, staying
+    elements first (self is neighbour 0), then one block per source rank."""
+    k = distributor.kernels
+    tb = k.tuple_bytes(src_fields)
+    sends, recvs = {}, {}
+    for r, ne, ni in zip(distributor.neighbors, distributor.num_export, distributor.num_import):
+        if ne > 0:
+            buf = torch.empty(ne * tb, dtype=torch.uint8, device=k.device)
+            k.pack(src_fields, distributor.steering_for(r), ne, buf)
+            sends[r] = buf
+        if ni > 0:
+            recvs[r] = torch.empty(ni * tb, dtype=torch.uint8, device=k.device)
+    distributor.exchange(sends, recvs)
+    for r, ni in zip(distributor.neighbors, distributor.num_import):
+        if ni > 0:
+            k.unpack(dst_fields, distributor.import_offset[r], ni, recvs[r])
+
+
+# --------------------------------------------------------------------------------- slab domain
+class SlabDecomposition:
+    """1-D slab partition along x over the ranks of `group`.
+
+    Rank g owns x in [bounds[g], bounds[g+1]) (the last rank owns its upper face).
+    """
+
+    def __init__(self, bounds, halo_width: float, group=None, kernels=None):
+        self.kernels = kernels if kernels is not None else CudaCommKernels()
+        self.group = group
+        self.rank, self.world = _world(group)
+        assert len(bounds) == self.world + 1
+        self.bounds = [float(b) for b in bounds]
+        # a hair wider than r so that rounding of lo + r can never lose a neighbour
+        self.halo_width = float(halo_width) * (1.0 + 2.0**-40)
+        self.lo = self.bounds[self.rank]
+        self.hi = self.bounds[self.rank + 1]
+        self.lo_rank = self.rank - 1 if self.rank > 0 else -1
+        self.hi_rank = self.rank + 1 if self.rank < self.world - 1 else -1
+
+    def local_grid_x(self):
+        """x-extent of the local Verlet grid: the slab widened by the halo on interior faces."""
+        gmin = self.lo - self.halo_width if self.lo_rank >= 0 else self.lo
+        gmax = self.hi + self.halo_width if self.hi_rank >= 0 else self.hi
+        return gmin, gmax
+
+    def create_halo(self, x: Slice, num_local: int) -> Halo:
+        ids, ranks = self.kernels.slab_halo_select(
+            x, num_local, self.lo + self.halo_width, self.hi - self.halo_width,
+            self.lo_rank, self.hi_rank)
+        return Halo(num_local, ids, ranks, self.group, self.kernels)
+
+    def create_distributor(self, x: Slice, num_local: int) -> Distributor:
+        dest = self.kernels.slab_destinations(x, num_local, self.bounds)
+        return Distributor(dest, self.group, self.kernels)

@@ -1,0 +1,391 @@
+// Slab Halo / Distributor device kernels for sm_100a.
+//
+// Replaces the device work of
+//   countSendsAndCreateSteering   core/src/Cabana_CommunicationPlanBase.hpp:96-224
+//   createExportSteering          :596-657
+//   gather pack / unpack          core/src/impl/Cabana_Halo_Mpi.hpp:58-65, :113-121
+//   scatter (atomic add unpack)   :269-282, :334-347
+//   migrate pack / unpack         core/src/impl/Cabana_Migrate_Mpi.hpp:92-103, :164-172
+//   destination-from-position     grid/src/Cabana_Grid_ParticleDistributor.hpp:119-158
+//
+// The reference claims steering slots with atomics, so the order inside a destination
+// block is not deterministic there (core/unit_test/tstDistributor.hpp:242-244).  Here a
+// stable partition (flag -> decoupled look-back scan -> scatter, one pass per non-empty
+// destination) makes it deterministic: ascending destination rank, ascending export index.
+#include "cb_common.cuh"
+#include "cb_internal.h"
+
+namespace cb
+{
+namespace
+{
+
+constexpr int kBlock = 256;
+constexpr int kMaxRanks = 1024;
+constexpr int kMaxFields = 8;
+constexpr int kMaxBounds = 65;
+
+struct Bounds
+{
+    double b[kMaxBounds];
+    int num_ranks;
+};
+
+__global__ void __launch_bounds__( kBlock )
+    k_slab_halo_select( PosAccess x, long long num_local, double lo_thresh,
+                        double hi_thresh, int lo_rank, int hi_rank,
+                        int* __restrict__ export_ranks, unsigned* __restrict__ export_ids )
+{
+    for ( long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < num_local;
+          i += (long long)gridDim.x * kBlock )
+    {
+        const double px = x.base[x.offset( i )];
+        export_ranks[2 * i] = ( lo_rank >= 0 && px < lo_thresh ) ? lo_rank : -1;
+        export_ranks[2 * i + 1] = ( hi_rank >= 0 && px >= hi_thresh ) ? hi_rank : -1;
+        export_ids[2 * i] = (unsigned)i;
+        export_ids[2 * i + 1] = (unsigned)i;
+    }
+}
+
+__global__ void __launch_bounds__( kBlock )
+    k_slab_destinations( PosAccess x, long long num_local, Bounds bd,
+                         int* __restrict__ export_ranks )
+{
+    for ( long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < num_local;
+          i += (long long)gridDim.x * kBlock )
+    {
+        const double px = x.base[x.offset( i )];
+        int dest = -1;
+        if ( px >= bd.b[0] && px <= bd.b[bd.num_ranks] )
+        {
+            dest = bd.num_ranks - 1; // the last slab owns its upper face
+            for ( int g = 0; g < bd.num_ranks - 1; ++g )
+                if ( px < bd.b[g + 1] )
+                {
+                    dest = g;
+                    break;
+                }
+        }
+        export_ranks[i] = dest;
+    }
+}
+
+__global__ void __launch_bounds__( kBlock )
+    k_rank_histogram( const int* __restrict__ export_ranks, long long n, int num_ranks,
+                      unsigned long long* __restrict__ counts )
+{
+    extern __shared__ unsigned s_hist[];
+    for ( int r = threadIdx.x; r < num_ranks; r += kBlock )
+        s_hist[r] = 0;
+    __syncthreads();
+    for ( long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n;
+          i += (long long)gridDim.x * kBlock )
+    {
+        const int r = export_ranks[i];
+        if ( r >= 0 && r < num_ranks )
+            atomicAdd( &s_hist[r], 1u );
+    }
+    __syncthreads();
+    for ( int r = threadIdx.x; r < num_ranks; r += kBlock )
+        if ( s_hist[r] )
+            atomicAdd( &counts[r], (unsigned long long)s_hist[r] );
+}
+
+__global__ void __launch_bounds__( kBlock )
+    k_flag_rank( const int* __restrict__ export_ranks, long long n, int rank,
+                 int* __restrict__ flags )
+{
+    for ( long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n;
+          i += (long long)gridDim.x * kBlock )
+        flags[i] = export_ranks[i] == rank ? 1 : 0;
+}
+
+__global__ void __launch_bounds__( kBlock )
+    k_steer_scatter( const int* __restrict__ export_ranks, long long n, int rank,
+                     const int* __restrict__ slot, const unsigned* __restrict__ export_ids,
+                     unsigned* __restrict__ steering_block )
+{
+    for ( long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n;
+          i += (long long)gridDim.x * kBlock )
+        if ( export_ranks[i] == rank )
+            steering_block[slot[i]] = export_ids ? export_ids[i] : (unsigned)i;
+}
+
+struct FieldSet
+{
+    FieldAccess f[kMaxFields];
+    int byte_off[kMaxFields];
+    int num;
+    int tuple_bytes;
+};
+
+template <int DIR> // 0 = pack (field -> buffer), 1 = unpack (buffer -> field)
+__global__ void __launch_bounds__( kBlock )
+    k_pack_unpack( FieldSet fs, const unsigned* __restrict__ steering,
+                   long long dst_begin, long long count, char* buffer )
+{
+    for ( long long j = (long long)blockIdx.x * kBlock + threadIdx.x; j < count;
+          j += (long long)gridDim.x * kBlock )
+    {
+        const long long elem = DIR == 0 ? (long long)steering[j] : dst_begin + j;
+        char* tuple = buffer + j * fs.tuple_bytes;
+        for ( int k = 0; k < fs.num; ++k )
+        {
+            const FieldAccess& f = fs.f[k];
+            const long long off = f.offset( elem );
+            if ( f.elem_bytes == 8 )
+            {
+                unsigned long long* fb = reinterpret_cast<unsigned long long*>( f.base );
+                unsigned long long* tb =
+                    reinterpret_cast<unsigned long long*>( tuple + fs.byte_off[k] );
+                for ( int c = 0; c < f.num_comp; ++c )
+                {
+                    if ( DIR == 0 )
+                        tb[c] = fb[off + f.comp_stride * c];
+                    else
+                        fb[off + f.comp_stride * c] = tb[c];
+                }
+            }
+            else
+            {
+                unsigned* fb = reinterpret_cast<unsigned*>( f.base );
+                unsigned* tb = reinterpret_cast<unsigned*>( tuple + fs.byte_off[k] );
+                for ( int c = 0; c < f.num_comp; ++c )
+                {
+                    if ( DIR == 0 )
+                        tb[c] = fb[off + f.comp_stride * c];
+                    else
+                        fb[off + f.comp_stride * c] = tb[c];
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__( kBlock )
+    k_scatter_add( FieldAccess f, const unsigned* __restrict__ steering, long long count,
+                   const double* __restrict__ recv )
+{
+    double* fb = reinterpret_cast<double*>( f.base );
+    for ( long long j = (long long)blockIdx.x * kBlock + threadIdx.x; j < count;
+          j += (long long)gridDim.x * kBlock )
+    {
+        const long long off = f.offset( (long long)steering[j] );
+        for ( int c = 0; c < f.num_comp; ++c )
+            atomicAdd( fb + off + f.comp_stride * c, recv[j * f.num_comp + c] );
+    }
+}
+
+int make_field_set( const cb_field* fields, int num_fields, FieldSet& fs )
+{
+    if ( !fields || num_fields < 1 || num_fields > kMaxFields )
+        return fail( CB_ERR_INVALID, "comm: need 1..8 fields" );
+    // 8-byte members first would be the natural alignment rule; Cabana tuples keep the
+    // declared member order, so do we -- and require each member to stay aligned.
+    int off = 0;
+    for ( int k = 0; k < num_fields; ++k )
+    {
+        const cb_field& f = fields[k];
+        if ( !f.base || f.vlen < 1 || f.num_comp < 1 ||
+             ( f.elem_bytes != 4 && f.elem_bytes != 8 ) )
+            return fail( CB_ERR_INVALID, "comm: bad field descriptor" );
+        if ( off % f.elem_bytes )
+            off += f.elem_bytes - off % f.elem_bytes;
+        fs.f[k] = make_access( f );
+        fs.byte_off[k] = off;
+        off += f.num_comp * f.elem_bytes;
+    }
+    if ( off % 8 )
+        off += 8 - off % 8;
+    fs.num = num_fields;
+    fs.tuple_bytes = off;
+    return CB_OK;
+}
+
+// Scratch shared by the plan kernels (one caller thread per process, cabana_b200.h).
+struct CommScratch
+{
+    DeviceBuffer counts, flags, slots, scan;
+    PinnedScalars pinned;
+};
+CommScratch& scratch()
+{
+    static thread_local CommScratch s;
+    return s;
+}
+
+} // namespace
+} // namespace cb
+
+using namespace cb;
+
+extern "C" int cb_slab_halo_select( const cb_positions* x, int64_t num_local,
+                                    double lo_thresh, double hi_thresh, int lo_rank,
+                                    int hi_rank, int32_t* export_ranks,
+                                    uint32_t* export_ids, cb_stream_t stream_ )
+{
+    if ( !x || !export_ranks || !export_ids || num_local < 0 || num_local > x->n ||
+         x->vlen < 1 )
+        return fail( CB_ERR_INVALID, "cb_slab_halo_select: bad argument" );
+    if ( num_local == 0 )
+        return CB_OK;
+    k_slab_halo_select<<<launch_grid_for( num_local, kBlock ), kBlock, 0,
+                         (cudaStream_t)stream_>>>( make_access( *x ), num_local,
+                                                   lo_thresh, hi_thresh, lo_rank,
+                                                   hi_rank, export_ranks, export_ids );
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
+extern "C" int cb_slab_migrate_destinations( const cb_positions* x, int64_t num_local,
+                                             const double* bounds_h, int num_ranks,
+                                             int32_t* export_ranks, cb_stream_t stream_ )
+{
+    if ( !x || !bounds_h || !export_ranks || num_local < 0 || num_local > x->n ||
+         x->vlen < 1 || num_ranks < 1 || num_ranks >= kMaxBounds )
+        return fail( CB_ERR_INVALID, "cb_slab_migrate_destinations: bad argument" );
+    if ( num_local == 0 )
+        return CB_OK;
+    Bounds bd;
+    bd.num_ranks = num_ranks;
+    for ( int g = 0; g <= num_ranks; ++g )
+        bd.b[g] = bounds_h[g];
+    k_slab_destinations<<<launch_grid_for( num_local, kBlock ), kBlock, 0,
+                          (cudaStream_t)stream_>>>( make_access( *x ), num_local, bd,
+                                                    export_ranks );
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
+extern "C" int cb_comm_count_and_steer( const int32_t* export_ranks, int64_t num_export,
+                                        int num_ranks, int64_t* counts_h,
+                                        int64_t* offsets_h, uint32_t* steering,
+                                        const uint32_t* export_ids, cb_stream_t stream_ )
+{
+    if ( !counts_h || !offsets_h || num_export < 0 || num_ranks < 1 ||
+         num_ranks > kMaxRanks || ( num_export > 0 && ( !export_ranks || !steering ) ) )
+        return fail( CB_ERR_INVALID, "cb_comm_count_and_steer: bad argument" );
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CommScratch& s = scratch();
+    CB_TRY( s.pinned.ensure() );
+    CB_TRY( s.counts.ensure( sizeof( unsigned long long ) * kMaxRanks ) );
+    CB_CUDA( cudaMemsetAsync( s.counts.ptr, 0, sizeof( unsigned long long ) * num_ranks,
+                              stream ) );
+    std::string keep;
+    unsigned long long* host_counts = nullptr;
+    CB_CUDA( cudaMallocHost( (void**)&host_counts,
+                             sizeof( unsigned long long ) * num_ranks ) );
+    if ( num_export > 0 )
+    {
+        k_rank_histogram<<<launch_grid_for( num_export, kBlock * 4 ), kBlock,
+                           sizeof( unsigned ) * num_ranks, stream>>>(
+            export_ranks, num_export, num_ranks, s.counts.as<unsigned long long>() );
+        cudaError_t le = cudaGetLastError();
+        if ( le != cudaSuccess )
+        {
+            cudaFreeHost( host_counts );
+            return cuda_fail( le, "k_rank_histogram", __FILE__, __LINE__ );
+        }
+    }
+    cudaError_t e1 = cudaMemcpyAsync( host_counts, s.counts.ptr,
+                                      sizeof( unsigned long long ) * num_ranks,
+                                      cudaMemcpyDeviceToHost, stream );
+    cudaError_t e2 = e1 == cudaSuccess ? cudaStreamSynchronize( stream ) : e1;
+    if ( e2 != cudaSuccess )
+    {
+        cudaFreeHost( host_counts );
+        return cuda_fail( e2, "count readback", __FILE__, __LINE__ );
+    }
+    int64_t run = 0;
+    for ( int r = 0; r < num_ranks; ++r )
+    {
+        counts_h[r] = (int64_t)host_counts[r];
+        offsets_h[r] = run;
+        run += counts_h[r];
+    }
+    offsets_h[num_ranks] = run;
+    cudaFreeHost( host_counts );
+
+    if ( num_export > 0 && run > 0 )
+    {
+        CB_TRY( s.flags.ensure( sizeof( int ) * (size_t)num_export, 1.1 ) );
+        CB_TRY( s.slots.ensure( sizeof( int ) * (size_t)( num_export + 1 ), 1.1 ) );
+        const int grid = launch_grid_for( num_export, kBlock );
+        for ( int r = 0; r < num_ranks; ++r )
+        {
+            if ( counts_h[r] == 0 )
+                continue;
+            k_flag_rank<<<grid, kBlock, 0, stream>>>( export_ranks, num_export, r,
+                                                      s.flags.as<int>() );
+            CB_CHECK_LAUNCH();
+            CB_TRY( exclusive_scan_i32( s.flags.as<int>(), s.slots.as<int>(), num_export,
+                                        false, nullptr, s.scan, stream ) );
+            k_steer_scatter<<<grid, kBlock, 0, stream>>>(
+                export_ranks, num_export, r, s.slots.as<int>(), export_ids,
+                steering + offsets_h[r] );
+            CB_CHECK_LAUNCH();
+        }
+    }
+    return CB_OK;
+}
+
+extern "C" int64_t cb_comm_tuple_bytes( const cb_field* fields, int num_fields )
+{
+    FieldSet fs;
+    if ( make_field_set( fields, num_fields, fs ) != CB_OK )
+        return -1;
+    return fs.tuple_bytes;
+}
+
+extern "C" int cb_comm_pack( const cb_field* fields, int num_fields,
+                             const uint32_t* steering, int64_t count, void* send_buffer,
+                             cb_stream_t stream_ )
+{
+    FieldSet fs;
+    CB_TRY( make_field_set( fields, num_fields, fs ) );
+    if ( count < 0 || ( count > 0 && ( !steering || !send_buffer ) ) )
+        return fail( CB_ERR_INVALID, "cb_comm_pack: bad argument" );
+    if ( count == 0 )
+        return CB_OK;
+    k_pack_unpack<0><<<launch_grid_for( count, kBlock ), kBlock, 0,
+                       (cudaStream_t)stream_>>>( fs, steering, 0, count,
+                                                 (char*)send_buffer );
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
+extern "C" int cb_comm_unpack( const cb_field* fields, int num_fields, int64_t dst_begin,
+                               int64_t count, const void* recv_buffer,
+                               cb_stream_t stream_ )
+{
+    FieldSet fs;
+    CB_TRY( make_field_set( fields, num_fields, fs ) );
+    if ( count < 0 || dst_begin < 0 || ( count > 0 && !recv_buffer ) )
+        return fail( CB_ERR_INVALID, "cb_comm_unpack: bad argument" );
+    for ( int k = 0; k < num_fields; ++k )
+        if ( fields[k].n < dst_begin + count )
+            return fail( CB_ERR_INVALID, "cb_comm_unpack: field too small for ghosts" );
+    if ( count == 0 )
+        return CB_OK;
+    k_pack_unpack<1><<<launch_grid_for( count, kBlock ), kBlock, 0,
+                       (cudaStream_t)stream_>>>( fs, nullptr, dst_begin, count,
+                                                 (char*)recv_buffer );
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
+extern "C" int cb_comm_scatter_add( const cb_field* field, const uint32_t* steering,
+                                    int64_t count, const void* recv_buffer,
+                                    cb_stream_t stream_ )
+{
+    if ( !field || field->elem_bytes != 8 || field->vlen < 1 || field->num_comp < 1 ||
+         count < 0 || ( count > 0 && ( !steering || !recv_buffer ) ) )
+        return fail( CB_ERR_INVALID, "cb_comm_scatter_add: doubles only" );
+    if ( count == 0 )
+        return CB_OK;
+    k_scatter_add<<<launch_grid_for( count, kBlock ), kBlock, 0,
+                    (cudaStream_t)stream_>>>( make_access( *field ), steering, count,
+                                              (const double*)recv_buffer );
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}

@@ -1,0 +1,415 @@
+// neighbor_parallel_for / neighbor_parallel_reduce over a VerletList (FirstNeighborsTag).
+//
+// Replaces the device loops of core/src/Cabana_Parallel.hpp:
+//   :280-288  Serial  -- RangePolicy over i, thread-local loop over neighbours
+//   :416-430  Team    -- TeamPolicy league = particles, TeamThreadRange over neighbours
+//   :670-684 / :820-843  the same with a scalar reduction
+// through the NeighborList<VerletList<..CSR|2D..>> accessors
+// (core/src/Cabana_VerletList.hpp:1633-1648, :1683-1697).
+//
+// Serial = one thread per particle; Team = one warp per particle with lanes striding the
+// row (coalesced id loads) and a shuffle reduction.  The consumers compiled here are the
+// Lennard-Jones functor (north_star) and the reference unit tests' id-sum functor; generic
+// user functors are instantiated by the header-only C++ shim with the same loop shapes.
+#include "cb_common.cuh"
+#include "cb_internal.h"
+
+namespace cb
+{
+namespace
+{
+
+constexpr int kBlock = 256;
+
+struct ListAccess
+{
+    const int* counts;
+    const int* offsets; // null for 2D
+    const int* neighbors;
+    long long row_stride;
+    long long col_stride;
+
+    CB_D int num( long long i ) const { return counts[i]; }
+    CB_D long long row( long long i ) const
+    {
+        return offsets ? (long long)offsets[i] : i * row_stride;
+    }
+    CB_D long long step() const { return offsets ? 1 : col_stride; }
+};
+
+ListAccess make_list( const cb_verlet_view& v )
+{
+    ListAccess l;
+    l.counts = v.counts;
+    l.offsets = v.layout == CB_LAYOUT_CSR ? v.offsets : nullptr;
+    l.neighbors = v.neighbors;
+    l.row_stride = v.row_stride;
+    l.col_stride = v.col_stride;
+    return l;
+}
+
+struct LJ
+{
+    double rc2;
+    double s2;
+    double eps24;
+    double eps4;
+};
+
+CB_D void lj_pair( const LJ& p, double dx, double dy, double dz, double& fx, double& fy,
+                   double& fz, bool& within )
+{
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    within = r2 < p.rc2;
+    if ( within )
+    {
+        const double sr2 = p.s2 / r2;
+        const double sr6 = sr2 * sr2 * sr2;
+        const double fpair = p.eps24 * sr6 * ( 2.0 * sr6 - 1.0 ) / r2;
+        fx = fpair * dx;
+        fy = fpair * dy;
+        fz = fpair * dz;
+    }
+}
+
+CB_D void add3( double* base, long long off, long long cs, double fx, double fy,
+                double fz, bool atomic )
+{
+    if ( atomic )
+    {
+        atomicAdd( base + off, fx );
+        atomicAdd( base + off + cs, fy );
+        atomicAdd( base + off + 2 * cs, fz );
+    }
+    else
+    {
+        base[off] += fx;
+        base[off + cs] += fy;
+        base[off + 2 * cs] += fz;
+    }
+}
+
+// Serial: Cabana_Parallel.hpp:280-288
+template <bool NEWTON>
+__global__ void __launch_bounds__( kBlock )
+    k_lj_serial( ListAccess l, PosAccess x, FieldAccess f, LJ p, long long begin,
+                 long long end )
+{
+    double* fb = reinterpret_cast<double*>( f.base );
+    for ( long long i = begin + (long long)blockIdx.x * kBlock + threadIdx.x; i < end;
+          i += (long long)gridDim.x * kBlock )
+    {
+        const long long xo = x.offset( i );
+        const double xi = x.base[xo];
+        const double yi = x.base[xo + x.comp_stride];
+        const double zi = x.base[xo + 2 * x.comp_stride];
+        const int nn = l.num( i );
+        const long long row = l.row( i );
+        const long long step = l.step();
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        for ( int n = 0; n < nn; ++n )
+        {
+            const long long j = l.neighbors[row + n * step];
+            const long long jo = x.offset( j );
+            double fx, fy, fz;
+            bool within;
+            lj_pair( p, xi - x.base[jo], yi - x.base[jo + x.comp_stride],
+                     zi - x.base[jo + 2 * x.comp_stride], fx, fy, fz, within );
+            if ( within )
+            {
+                ax += fx;
+                ay += fy;
+                az += fz;
+                if ( NEWTON )
+                    add3( fb, f.offset( j ), f.comp_stride, -fx, -fy, -fz, true );
+            }
+        }
+        add3( fb, f.offset( i ), f.comp_stride, ax, ay, az, NEWTON );
+    }
+}
+
+// Team: Cabana_Parallel.hpp:416-430 -- one warp per particle.
+template <bool NEWTON>
+__global__ void __launch_bounds__( kBlock )
+    k_lj_team( ListAccess l, PosAccess x, FieldAccess f, LJ p, long long begin,
+               long long end )
+{
+    double* fb = reinterpret_cast<double*>( f.base );
+    const unsigned lane = lane_id();
+    const long long warp = ( (long long)blockIdx.x * kBlock + threadIdx.x ) >> 5;
+    const long long nwarps = ( (long long)gridDim.x * kBlock ) >> 5;
+    for ( long long i = begin + warp; i < end; i += nwarps )
+    {
+        const long long xo = x.offset( i );
+        const double xi = x.base[xo];
+        const double yi = x.base[xo + x.comp_stride];
+        const double zi = x.base[xo + 2 * x.comp_stride];
+        const int nn = l.num( i );
+        const long long row = l.row( i );
+        const long long step = l.step();
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        for ( int n = (int)lane; n < nn; n += 32 )
+        {
+            const long long j = l.neighbors[row + n * step];
+            const long long jo = x.offset( j );
+            double fx, fy, fz;
+            bool within;
+            lj_pair( p, xi - x.base[jo], yi - x.base[jo + x.comp_stride],
+                     zi - x.base[jo + 2 * x.comp_stride], fx, fy, fz, within );
+            if ( within )
+            {
+                ax += fx;
+                ay += fy;
+                az += fz;
+                if ( NEWTON )
+                    add3( fb, f.offset( j ), f.comp_stride, -fx, -fy, -fz, true );
+            }
+        }
+        ax = warp_reduce_sum( ax );
+        ay = warp_reduce_sum( ay );
+        az = warp_reduce_sum( az );
+        if ( lane == 0 )
+            add3( fb, f.offset( i ), f.comp_stride, ax, ay, az, NEWTON );
+    }
+}
+
+// neighbor_parallel_reduce with the LJ pair energy.  TEAM selects warp-per-particle.
+template <bool TEAM>
+__global__ void __launch_bounds__( kBlock )
+    k_lj_energy( ListAccess l, PosAccess x, LJ p, double scale, long long begin,
+                 long long end, double* energy )
+{
+    __shared__ double s_part[kBlock / 32];
+    const unsigned lane = lane_id();
+    double e = 0.0;
+    if ( TEAM )
+    {
+        const long long warp = ( (long long)blockIdx.x * kBlock + threadIdx.x ) >> 5;
+        const long long nwarps = ( (long long)gridDim.x * kBlock ) >> 5;
+        for ( long long i = begin + warp; i < end; i += nwarps )
+        {
+            const long long xo = x.offset( i );
+            const double xi = x.base[xo], yi = x.base[xo + x.comp_stride],
+                         zi = x.base[xo + 2 * x.comp_stride];
+            const int nn = l.num( i );
+            const long long row = l.row( i ), step = l.step();
+            for ( int n = (int)lane; n < nn; n += 32 )
+            {
+                const long long jo = x.offset( l.neighbors[row + n * step] );
+                const double dx = xi - x.base[jo], dy = yi - x.base[jo + x.comp_stride],
+                             dz = zi - x.base[jo + 2 * x.comp_stride];
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                if ( r2 < p.rc2 )
+                {
+                    const double sr2 = p.s2 / r2;
+                    const double sr6 = sr2 * sr2 * sr2;
+                    e += p.eps4 * ( sr6 * sr6 - sr6 );
+                }
+            }
+        }
+    }
+    else
+    {
+        for ( long long i = begin + (long long)blockIdx.x * kBlock + threadIdx.x;
+              i < end; i += (long long)gridDim.x * kBlock )
+        {
+            const long long xo = x.offset( i );
+            const double xi = x.base[xo], yi = x.base[xo + x.comp_stride],
+                         zi = x.base[xo + 2 * x.comp_stride];
+            const int nn = l.num( i );
+            const long long row = l.row( i ), step = l.step();
+            for ( int n = 0; n < nn; ++n )
+            {
+                const long long jo = x.offset( l.neighbors[row + n * step] );
+                const double dx = xi - x.base[jo], dy = yi - x.base[jo + x.comp_stride],
+                             dz = zi - x.base[jo + 2 * x.comp_stride];
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                if ( r2 < p.rc2 )
+                {
+                    const double sr2 = p.s2 / r2;
+                    const double sr6 = sr2 * sr2 * sr2;
+                    e += p.eps4 * ( sr6 * sr6 - sr6 );
+                }
+            }
+        }
+    }
+    e = warp_reduce_sum( e );
+    if ( lane == 0 )
+        s_part[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if ( threadIdx.x < 32 )
+    {
+        e = ( lane < kBlock / 32 ) ? s_part[lane] : 0.0;
+        e = warp_reduce_sum( e );
+        if ( lane == 0 )
+            atomicAdd( energy, scale * e );
+    }
+}
+
+// Reference unit-test functor: result[i] += j (neighbor_unit_test.hpp:291-348).
+template <bool TEAM>
+__global__ void __launch_bounds__( kBlock )
+    k_id_sum( ListAccess l, long long begin, long long end, long long* result )
+{
+    if ( TEAM )
+    {
+        const unsigned lane = lane_id();
+        const long long warp = ( (long long)blockIdx.x * kBlock + threadIdx.x ) >> 5;
+        const long long nwarps = ( (long long)gridDim.x * kBlock ) >> 5;
+        for ( long long i = begin + warp; i < end; i += nwarps )
+        {
+            const int nn = l.num( i );
+            const long long row = l.row( i ), step = l.step();
+            long long acc = 0;
+            for ( int n = (int)lane; n < nn; n += 32 )
+                acc += l.neighbors[row + n * step];
+            acc = warp_reduce_sum( acc );
+            if ( lane == 0 )
+                result[i] += acc;
+        }
+    }
+    else
+    {
+        for ( long long i = begin + (long long)blockIdx.x * kBlock + threadIdx.x;
+              i < end; i += (long long)gridDim.x * kBlock )
+        {
+            const int nn = l.num( i );
+            const long long row = l.row( i ), step = l.step();
+            long long acc = 0;
+            for ( int n = 0; n < nn; ++n )
+                acc += l.neighbors[row + n * step];
+            result[i] += acc;
+        }
+    }
+}
+
+int check_list( const cb_verlet_view* v, int64_t begin, int64_t end, const char* who )
+{
+    if ( !v || !v->counts || ( v->total > 0 && !v->neighbors ) )
+        return fail( CB_ERR_INVALID, who );
+    if ( v->layout == CB_LAYOUT_CSR && !v->offsets )
+        return fail( CB_ERR_INVALID, who );
+    if ( begin < 0 || end < begin || end > v->n )
+        return fail( CB_ERR_INVALID, who );
+    return CB_OK;
+}
+
+int team_grid( long long items )
+{
+    long long blocks = ( items * 32 + kBlock - 1 ) / kBlock;
+    const long long cap = (long long)kNumSMs * 64;
+    if ( blocks > cap )
+        blocks = cap;
+    return (int)( blocks < 1 ? 1 : blocks );
+}
+
+} // namespace
+} // namespace cb
+
+using namespace cb;
+
+extern "C" int cb_neighbor_for_lj( const cb_verlet_view* list, const cb_positions* x,
+                                   const cb_field* f, double eps, double sigma,
+                                   double rc, int newton, int op, int64_t begin,
+                                   int64_t end, cb_stream_t stream_ )
+{
+    CB_TRY( check_list( list, begin, end, "cb_neighbor_for_lj: bad list or range" ) );
+    if ( !x || !f || x->vlen < 1 || f->vlen < 1 )
+        return fail( CB_ERR_INVALID, "cb_neighbor_for_lj: null argument" );
+    if ( f->elem_bytes != 8 || f->num_comp != 3 || f->n < list->n || x->n < list->n )
+        return fail( CB_ERR_INVALID, "cb_neighbor_for_lj: force field must be double[3]" );
+    if ( op != CB_OP_SERIAL && op != CB_OP_TEAM )
+        return fail( CB_ERR_INVALID, "cb_neighbor_for_lj: op must be Serial or Team" );
+    if ( end == begin )
+        return CB_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LJ p;
+    p.rc2 = rc * rc;
+    p.s2 = sigma * sigma;
+    p.eps24 = 24.0 * eps;
+    p.eps4 = 4.0 * eps;
+    const ListAccess l = make_list( *list );
+    const PosAccess xa = make_access( *x );
+    const FieldAccess fa = make_access( *f );
+    const long long items = end - begin;
+    if ( op == CB_OP_SERIAL )
+    {
+        const int grid = launch_grid_for( items, kBlock );
+        if ( newton )
+            k_lj_serial<true><<<grid, kBlock, 0, stream>>>( l, xa, fa, p, begin, end );
+        else
+            k_lj_serial<false><<<grid, kBlock, 0, stream>>>( l, xa, fa, p, begin, end );
+    }
+    else
+    {
+        const int grid = team_grid( items );
+        if ( newton )
+            k_lj_team<true><<<grid, kBlock, 0, stream>>>( l, xa, fa, p, begin, end );
+        else
+            k_lj_team<false><<<grid, kBlock, 0, stream>>>( l, xa, fa, p, begin, end );
+    }
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
+extern "C" int cb_neighbor_reduce_lj( const cb_verlet_view* list, const cb_positions* x,
+                                      double eps, double sigma, double rc, double scale,
+                                      int op, int64_t begin, int64_t end,
+                                      double* energy_h, cb_stream_t stream_ )
+{
+    CB_TRY( check_list( list, begin, end, "cb_neighbor_reduce_lj: bad list or range" ) );
+    if ( !x || !energy_h || x->vlen < 1 || x->n < list->n )
+        return fail( CB_ERR_INVALID, "cb_neighbor_reduce_lj: null argument" );
+    if ( op != CB_OP_SERIAL && op != CB_OP_TEAM )
+        return fail( CB_ERR_INVALID, "cb_neighbor_reduce_lj: op must be Serial or Team" );
+    cudaStream_t stream = (cudaStream_t)stream_;
+    double* energy_dev = nullptr;
+    CB_CUDA( cudaMallocAsync( (void**)&energy_dev, sizeof( double ), stream ) );
+    CB_CUDA( cudaMemsetAsync( energy_dev, 0, sizeof( double ), stream ) );
+    LJ p;
+    p.rc2 = rc * rc;
+    p.s2 = sigma * sigma;
+    p.eps24 = 24.0 * eps;
+    p.eps4 = 4.0 * eps;
+    const long long items = end - begin;
+    if ( items > 0 )
+    {
+        if ( op == CB_OP_SERIAL )
+            k_lj_energy<false><<<launch_grid_for( items, kBlock ), kBlock, 0, stream>>>(
+                make_list( *list ), make_access( *x ), p, scale, begin, end,
+                energy_dev );
+        else
+            k_lj_energy<true><<<team_grid( items ), kBlock, 0, stream>>>(
+                make_list( *list ), make_access( *x ), p, scale, begin, end,
+                energy_dev );
+        CB_CHECK_LAUNCH();
+    }
+    CB_CUDA( cudaMemcpyAsync( energy_h, energy_dev, sizeof( double ),
+                              cudaMemcpyDeviceToHost, stream ) );
+    CB_CUDA( cudaFreeAsync( energy_dev, stream ) );
+    CB_CUDA( cudaStreamSynchronize( stream ) );
+    return CB_OK;
+}
+
+extern "C" int cb_neighbor_for_id_sum( const cb_verlet_view* list, int64_t* result,
+                                       int op, int64_t begin, int64_t end,
+                                       cb_stream_t stream_ )
+{
+    CB_TRY( check_list( list, begin, end, "cb_neighbor_for_id_sum: bad list or range" ) );
+    if ( !result )
+        return fail( CB_ERR_INVALID, "cb_neighbor_for_id_sum: null argument" );
+    if ( op != CB_OP_SERIAL && op != CB_OP_TEAM )
+        return fail( CB_ERR_INVALID, "cb_neighbor_for_id_sum: op must be Serial or Team" );
+    if ( end == begin )
+        return CB_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long items = end - begin;
+    if ( op == CB_OP_SERIAL )
+        k_id_sum<false><<<launch_grid_for( items, kBlock ), kBlock, 0, stream>>>(
+            make_list( *list ), begin, end, reinterpret_cast<long long*>( result ) );
+    else
+        k_id_sum<true><<<team_grid( items ), kBlock, 0, stream>>>(
+            make_list( *list ), begin, end, reinterpret_cast<long long*>( result ) );
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
