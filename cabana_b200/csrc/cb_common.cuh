@@ -153,6 +153,16 @@ CB_HD int locate_1d( const Grid& g, int d, double p )
     return ( c == g.nx[d] ) ? c - 1 : c;
 }
 
+// Sub-cell index on the m-times refined internal grid: user cell `cu` (exact, from
+// locate_1d) times m plus the sub-cell the point falls in.  Monotone non-decreasing in p.
+CB_HD int fine_index_1d( const Grid& g, int d, double p, int cu, int m )
+{
+    const double t = CB_MUL( CB_SUB( p, g.min[d] ), g.rdx[d] );
+    int sub = (int)( ( t - (double)cu ) * (double)m );
+    sub = sub < 0 ? 0 : ( sub > m - 1 ? m - 1 : sub );
+    return cu * m + sub;
+}
+
 // One dimension of minDistanceToPoint (:212-220): returns rx*rx for cell index c.
 CB_HD double min_dist_1d_sq( const Grid& g, int d, double x, int c )
 {

@@ -129,14 +129,15 @@ int max_and_sum_i32( const int* in, long long n, long long* stats_dev,
 struct Grid;
 struct PosAccess;
 
-// Bin particles [begin,end) on `grid`:
+// Bin particles [begin,end) on `grid` (each cell split into refine^3 sub-cells when
+// refine > 1; cell ids are then cardinal indices of the refined grid):
 //   counts[ncell], offsets[ncell+1] (uint32), permute[end-begin] = absolute ids,
 //   cell_of[end-begin] = cardinal cell of particle begin+q (particle_bins, unsorted).
 // `rank_scratch` holds the per-particle slot claimed in its cell.
 int bin_particles( const cb_grid& grid, const cb_positions& x, long long begin,
                    long long end, int* counts, unsigned* offsets, unsigned* permute,
                    int* cell_of, DeviceBuffer& rank_scratch, DeviceBuffer& scan_scratch,
-                   cudaStream_t stream );
+                   cudaStream_t stream, int refine = 1 );
 
 int launch_grid_for( long long work_items, int block );
 

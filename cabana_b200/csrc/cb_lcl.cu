@@ -28,7 +28,7 @@ namespace
 constexpr int kBlock = 256;
 
 __global__ void __launch_bounds__( kBlock )
-    k_cell_count( PosAccess x, Grid g, long long begin, long long np,
+    k_cell_count( PosAccess x, Grid g, int m, long long begin, long long np,
                   int* __restrict__ counts, int* __restrict__ cell_of,
                   unsigned* __restrict__ slot )
 {
@@ -55,7 +55,18 @@ __global__ void __launch_bounds__( kBlock )
             ci = min( max( ci, 0 ), g.nx[0] - 1 );
             cj = min( max( cj, 0 ), g.nx[1] - 1 );
             ck = min( max( ck, 0 ), g.nx[2] - 1 );
-            c = cardinal_index( g, ci, cj, ck );
+            if ( m > 1 )
+            {
+                // Refined internal grid (Verlet build): every user cell is split into
+                // m^3 sub-cells.  The USER cell stays exact (locatePoint above); the
+                // sub-cell only has to be deterministic and monotone in the coordinate.
+                ci = fine_index_1d( g, 0, px, ci, m );
+                cj = fine_index_1d( g, 1, py, cj, m );
+                ck = fine_index_1d( g, 2, pz, ck, m );
+                c = ( ci * ( g.nx[1] * m ) + cj ) * ( g.nx[2] * m ) + ck;
+            }
+            else
+                c = cardinal_index( g, ci, cj, ck );
             cell_of[q] = c;
         }
         // Warp-aggregated atomic: lanes sharing a cell issue ONE atomicAdd.
@@ -128,16 +139,17 @@ __global__ void __launch_bounds__( kBlock )
 int bin_particles( const cb_grid& grid, const cb_positions& x, long long begin,
                    long long end, int* counts, unsigned* offsets, unsigned* permute,
                    int* cell_of, DeviceBuffer& rank_scratch, DeviceBuffer& scan_scratch,
-                   cudaStream_t stream )
+                   cudaStream_t stream, int refine )
 {
     const long long np = end - begin;
-    const long long ncell = (long long)grid.nx[0] * grid.nx[1] * grid.nx[2];
+    const long long m3 = (long long)refine * refine * refine;
+    const long long ncell = (long long)grid.nx[0] * grid.nx[1] * grid.nx[2] * m3;
     CB_CUDA( cudaMemsetAsync( counts, 0, sizeof( int ) * (size_t)ncell, stream ) );
     CB_TRY( rank_scratch.ensure( sizeof( unsigned ) * (size_t)( np > 0 ? np : 1 ), 1.1 ) );
     if ( np > 0 )
     {
         k_cell_count<<<launch_grid_for( np, kBlock ), kBlock, 0, stream>>>(
-            make_access( x ), to_grid( grid ), begin, np, counts, cell_of,
+            make_access( x ), to_grid( grid ), refine, begin, np, counts, cell_of,
             rank_scratch.as<unsigned>() );
         CB_CHECK_LAUNCH();
     }

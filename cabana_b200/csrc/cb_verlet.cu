@@ -20,8 +20,13 @@
 #include <new>
 #include <utility>
 
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "cb_common.cuh"
 #include "cb_internal.h"
+#include "cb_verlet_fine.h"
 
 namespace cb
 {
@@ -52,15 +57,28 @@ struct VerletArgs
 __global__ void __launch_bounds__( kBlock )
     k_gather_sorted( PosAccess x, long long n, const unsigned* __restrict__ permute,
                      double* __restrict__ xs, double* __restrict__ ys,
-                     double* __restrict__ zs )
+                     double* __restrict__ zs, float4* __restrict__ q, double ox, double oy,
+                     double oz )
 {
     for ( long long s = (long long)blockIdx.x * kBlock + threadIdx.x; s < n;
           s += (long long)gridDim.x * kBlock )
     {
-        const long long off = x.offset( (long long)permute[s] );
-        xs[s] = x.base[off];
-        ys[s] = x.base[off + x.comp_stride];
-        zs[s] = x.base[off + 2 * x.comp_stride];
+        const unsigned pid = permute[s];
+        const long long off = x.offset( (long long)pid );
+        const double px = x.base[off];
+        const double py = x.base[off + x.comp_stride];
+        const double pz = x.base[off + 2 * x.comp_stride];
+        xs[s] = px;
+        ys[s] = py;
+        zs[s] = pz;
+        if ( q )
+        {
+            // origin-relative FP32 copy for the tier-1 filter; w carries the particle id
+            q[s] = make_float4( __double2float_rn( px - ox ), __double2float_rn( py - oy ),
+                                __double2float_rn( pz - oz ), __int_as_float( (int)pid ) );
+            if ( s == 0 ) // sentinel used to pad candidate lists: never within any cutoff
+                q[n] = make_float4( 3.0e38f, 3.0e38f, 3.0e38f, __int_as_float( -1 ) );
+        }
     }
 }
 
@@ -241,7 +259,8 @@ struct cb_verlet
     bool built = false;
     DeviceBuffer counts, offsets, neighbors;
     // workspace
-    DeviceBuffer cell_counts, cell_off, permute, cell_of, rank, scan, xs, ys, zs, stats;
+    DeviceBuffer cell_counts, cell_off, permute, cell_of, rank, scan, xs, ys, zs, q, stats;
+    DeviceBuffer worklist;
     DeviceBuffer host_stage; // device copy of host positions (build_host)
     PinnedScalars pinned;
     // optional phase timing
@@ -331,11 +350,56 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
     const int cell_range = cb_stencil_cell_range( cell_size_ratio );
     const double rsqr = radius * radius; // :239
 
+    // Kernel generation: v1 (refined grid + FP32 filter, default) or v0 (CB_VERLET_IMPL=v0).
+    const char* impl_env = getenv( "CB_VERLET_IMPL" );
+    const bool use_v0 = impl_env && strcmp( impl_env, "v0" ) == 0;
+    int refine = 1;
+    if ( !use_v0 )
+    {
+        // refined cells of about r/2; m is a power of two (cheap user-cell arithmetic)
+        const double target = 2.0 * grid.dx[0] / radius;
+        refine = 1;
+        while ( refine < 8 && (double)refine * 1.4142 < target )
+            refine *= 2;
+        const char* m_env = getenv( "CB_VERLET_REFINE" );
+        if ( m_env && ( atoi( m_env ) == 1 || atoi( m_env ) == 2 || atoi( m_env ) == 4 ||
+                        atoi( m_env ) == 8 ) )
+            refine = atoi( m_env );
+        // keep the refined grid a sane size relative to the particle count
+        while ( refine > 1 )
+        {
+            const double nc = (double)ncell * refine * refine * refine;
+            if ( nc < 2.0e9 && nc <= 8.0 * (double)n + 1048576.0 )
+                break;
+            refine /= 2;
+        }
+    }
+    // v1 tabulates the z reach of a stencil row for |da|,|db| <= 8 refined cells; finer
+    // user grids (cell_size_ratio < ~0.13) take the v0 kernels.
+    bool fine_ok = !use_v0;
+    if ( fine_ok )
+        for ( int d = 0; d < 3; ++d )
+        {
+            const double hf = grid.dx[d] / refine;
+            if ( floor( radius * ( 1.0 + 1.0e-9 ) / hf ) + 1.0 > 8.0 )
+                fine_ok = false;
+        }
+    const bool use_fine = fine_ok;
+    if ( !use_fine )
+        refine = 1;
+    const long long ncell_f = ncell * refine * refine * refine;
+
     CB_TRY( v->pinned.ensure() );
     CB_TRY( v->stats.ensure( 4 * sizeof( long long ) ) );
     CB_TRY( v->counts.ensure( sizeof( int ) * na, 1.1 ) );
-    CB_TRY( v->cell_counts.ensure( sizeof( int ) * (size_t)ncell ) );
-    CB_TRY( v->cell_off.ensure( sizeof( unsigned ) * (size_t)( ncell + 1 ) ) );
+    CB_TRY( v->cell_counts.ensure( sizeof( int ) * (size_t)ncell_f ) );
+    CB_TRY( v->cell_off.ensure( sizeof( unsigned ) * (size_t)( ncell_f + 1 ) ) );
+    const char* col_env = getenv( "CB_VERLET_COLUMNS" );
+    const bool use_columns = use_fine && !( col_env && strcmp( col_env, "0" ) == 0 );
+    if ( use_fine )
+        CB_TRY( v->q.ensure( sizeof( float4 ) * ( na + 1 ), 1.1 ) );
+    if ( use_columns )
+        CB_TRY( v->worklist.ensure( sizeof( unsigned ) * (size_t)( ncell_f + 4 ) ) );
     CB_TRY( v->permute.ensure( sizeof( unsigned ) * na, 1.1 ) );
     CB_TRY( v->cell_of.ensure( sizeof( int ) * na, 1.1 ) );
     CB_TRY( v->xs.ensure( sizeof( double ) * na, 1.1 ) );
@@ -361,13 +425,14 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
     // LCL over ALL particles, not just [begin,end) (:229-235).
     CB_TRY( bin_particles( grid, *x, 0, n, v->cell_counts.as<int>(),
                            v->cell_off.as<unsigned>(), v->permute.as<unsigned>(),
-                           v->cell_of.as<int>(), v->rank, v->scan, stream ) );
+                           v->cell_of.as<int>(), v->rank, v->scan, stream, refine ) );
     v->mark( 1, stream );
     if ( n > 0 )
     {
         k_gather_sorted<<<launch_grid_for( n, kBlock ), kBlock, 0, stream>>>(
             make_access( *x ), n, v->permute.as<unsigned>(), v->xs.as<double>(),
-            v->ys.as<double>(), v->zs.as<double>() );
+            v->ys.as<double>(), v->zs.as<double>(), use_fine ? v->q.as<float4>() : nullptr,
+            grid.min[0], grid.min[1], grid.min[2] );
         CB_CHECK_LAUNCH();
     }
     v->mark( 2, stream );
@@ -389,13 +454,101 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
     a.neighbors = nullptr;
     a.width = 0;
 
+    FineArgs fa;
+    memset( &fa, 0, sizeof( fa ) );
+    if ( use_fine )
+    {
+        fa.q = v->q.as<float4>();
+        fa.xs = a.xs;
+        fa.ys = a.ys;
+        fa.zs = a.zs;
+        fa.cell_off = a.cell_off;
+        fa.ug = a.g;
+        fa.lgm = refine == 8 ? 3 : ( refine == 4 ? 2 : ( refine == 2 ? 1 : 0 ) );
+        fa.R = cell_range;
+        double extent = 0.0, cmax = 0.0, hmax = 0.0;
+        for ( int d = 0; d < 3; ++d )
+        {
+            fa.nf[d] = grid.nx[d] * refine;
+            fa.hf[d] = grid.dx[d] / refine;
+            extent = fmax( extent, grid.max[d] - grid.min[d] );
+            cmax = fmax( cmax, fmax( fabs( grid.min[d] ), fabs( grid.max[d] ) ) );
+            hmax = fmax( hmax, fa.hf[d] );
+        }
+        // Conservative reach for cell-level pruning: a point's refined cell is known to
+        // ~1e-12 h, so two points |k| cells apart are at least (|k|-1) h - eps apart.
+        const double reach = radius * ( 1.0 + 1.0e-9 ) + 4.0e-9 * hmax;
+        const double reach2 = reach * reach;
+        for ( int d = 0; d < 3; ++d )
+        {
+            fa.K[d] = (int)floor( reach / fa.hf[d] ) + 1;
+            const int kmax = ( cell_range + 1 ) * refine; // never beyond the user stencil
+            if ( fa.K[d] > kmax )
+                fa.K[d] = kmax;
+            if ( fa.K[d] > 8 )
+                fa.K[d] = 8; // cannot bind: use_fine guarantees floor(reach/hf)+1 <= 8
+        }
+        for ( int da = 0; da <= 8; ++da )
+            for ( int db = 0; db <= 8; ++db )
+            {
+                const double ga = ( da > 1 ? da - 1 : 0 ) * fa.hf[0];
+                const double gb = ( db > 1 ? db - 1 : 0 ) * fa.hf[1];
+                const double rem = reach2 - ( ga * ga + gb * gb );
+                int kz = -1;
+                if ( rem >= 0.0 && da <= fa.K[0] && db <= fa.K[1] )
+                {
+                    kz = fa.K[2];
+                    while ( kz > 1 )
+                    {
+                        const double gz = ( kz - 1 ) * fa.hf[2];
+                        if ( gz * gz <= rem )
+                            break;
+                        --kz;
+                    }
+                }
+                fa.kz[da * 9 + db] = (signed char)kz;
+            }
+        fa.rsqr = rsqr;
+        // Tier-1 filter: |s32 - s| <= E for s <= 1.1 r^2 with origin-relative floats
+        // (DESIGN.md "Exactness"); tau = 4 E + 2^-22 r^2.
+        const double u = ldexp( 1.0, -24 );
+        const double E = u * ( 6.5 * 1.1 * rsqr + 7.3 * 1.05 * extent * radius );
+        const double tau = 4.0 * E + ldexp( rsqr, -22 );
+        fa.t_hi = nextafterf( (float)( rsqr + tau ), INFINITY );
+        fa.t_lo = rsqr - tau > 0.0 ? nextafterf( (float)( rsqr - tau ), -INFINITY ) : -1.0f;
+        // Band in which the reference's cell prune can reject an in-range pair: its min
+        // distance is computed with O(ulp(coordinate)) error.
+        const double eta = ldexp( cmax + extent + radius, -46 );
+        fa.band = 8.0 * radius * eta + 4.0 * eta * eta + ldexp( rsqr, -44 );
+        fa.n = n;
+        fa.begin = begin;
+        fa.end = end;
+        fa.ncell = ncell_f;
+        fa.counts = a.counts;
+        fa.offsets = nullptr;
+        fa.neighbors = nullptr;
+        fa.width = 0;
+        fa.worklist = use_columns ? v->worklist.as<unsigned>() + 4 : nullptr;
+        fa.work_count = use_columns ? v->worklist.as<unsigned>() : nullptr;
+    }
+    auto run_pass = [&]( bool fill ) -> int
+    {
+        if ( !use_fine )
+            return fill ? launch_pass<kFill>( a, algorithm, layout, stream )
+                        : launch_pass<kCount>( a, algorithm, layout, stream );
+        fa.offsets = a.offsets;
+        fa.neighbors = a.neighbors;
+        fa.width = a.width;
+        return launch_fine_pass( fa, fill, algorithm, layout, stream );
+    };
+
     long long* stats_dev = v->stats.as<long long>();
     long long* stats_h = v->pinned.ptr;
 
     if ( layout == CB_LAYOUT_CSR )
     {
         // count -> processCounts(CSR) -> fill  (:1454-1480, :507-532)
-        CB_TRY( launch_pass<kCount>( a, algorithm, layout, stream ) );
+        CB_TRY( run_pass( false ) );
         v->mark( 3, stream );
         CB_TRY( v->offsets.ensure( sizeof( int ) * ( na + 1 ), 1.1 ) );
         CB_TRY( max_and_sum_i32( v->counts.as<int>(), n, stats_dev, stream ) );
@@ -414,7 +567,7 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
                                      1.05 ) );
         a.offsets = v->offsets.as<int>();
         a.neighbors = v->neighbors.as<int>();
-        CB_TRY( launch_pass<kFill>( a, algorithm, layout, stream ) );
+        CB_TRY( run_pass( true ) );
         v->mark( 5, stream );
     }
     else
@@ -427,11 +580,11 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
             CB_TRY( v->neighbors.ensure( sizeof( int ) * na * (size_t)v->width ) );
             a.neighbors = v->neighbors.as<int>();
             a.width = v->width;
-            CB_TRY( launch_pass<kFill>( a, algorithm, layout, stream ) );
+            CB_TRY( run_pass( true ) );
         }
         else
         {
-            CB_TRY( launch_pass<kCount>( a, algorithm, layout, stream ) );
+            CB_TRY( run_pass( false ) );
         }
         v->mark( 3, stream );
         // processCounts(2D) :536-562
@@ -451,7 +604,7 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
                 sizeof( int ) * na * (size_t)( v->width > 0 ? v->width : 1 ) ) );
             a.neighbors = v->neighbors.as<int>();
             a.width = v->width;
-            CB_TRY( launch_pass<kFill>( a, algorithm, layout, stream ) );
+            CB_TRY( run_pass( true ) );
             if ( !count )
                 v->refilled = 1;
         }
