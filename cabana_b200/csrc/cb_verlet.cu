@@ -260,7 +260,7 @@ struct cb_verlet
     DeviceBuffer counts, offsets, neighbors;
     // workspace
     DeviceBuffer cell_counts, cell_off, permute, cell_of, rank, scan, xs, ys, zs, q, stats;
-    DeviceBuffer worklist;
+    DeviceBuffer worklist, tmp, tmp_off, ctrl;
     DeviceBuffer host_stage; // device copy of host positions (build_host)
     PinnedScalars pinned;
     // optional phase timing
@@ -459,6 +459,7 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
     if ( use_fine )
     {
         fa.q = v->q.as<float4>();
+        fa.ids = a.ids;
         fa.xs = a.xs;
         fa.ys = a.ys;
         fa.zs = a.zs;
@@ -523,6 +524,7 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
         fa.n = n;
         fa.begin = begin;
         fa.end = end;
+        fa.full_range = ( begin == 0 && end == n ) ? 1 : 0;
         fa.ncell = ncell_f;
         fa.counts = a.counts;
         fa.offsets = nullptr;
@@ -533,17 +535,96 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
     }
     auto run_pass = [&]( bool fill ) -> int
     {
-        if ( !use_fine )
-            return fill ? launch_pass<kFill>( a, algorithm, layout, stream )
-                        : launch_pass<kCount>( a, algorithm, layout, stream );
-        fa.offsets = a.offsets;
-        fa.neighbors = a.neighbors;
-        fa.width = a.width;
-        return launch_fine_pass( fa, fill, algorithm, layout, stream );
+        return fill ? launch_pass<kFill>( a, algorithm, layout, stream )
+                    : launch_pass<kCount>( a, algorithm, layout, stream );
     };
 
     long long* stats_dev = v->stats.as<long long>();
     long long* stats_h = v->pinned.ptr;
+
+    if ( use_fine )
+    {
+        // ---- v1: ONE test pass into a binned-order temporary, then reorder ----------
+        CB_TRY( v->tmp_off.ensure( sizeof( unsigned ) * na, 1.1 ) );
+        CB_TRY( v->ctrl.ensure( 64 ) );
+        if ( layout == CB_LAYOUT_CSR )
+            CB_TRY( v->offsets.ensure( sizeof( int ) * ( na + 1 ), 1.1 ) );
+        // first guess of the temporary's size: uniform-density estimate plus the slack
+        // of the per-warp reservations; a rebuild reuses the previous capacity
+        if ( v->tmp.capacity == 0 )
+        {
+            double vol = 1.0;
+            for ( int d = 0; d < 3; ++d )
+                vol *= grid.max[d] - grid.min[d];
+            const double k_est = 4.18879 * radius * radius * radius * (double)n / vol *
+                                 ( algorithm == CB_NEIGHBOR_HALF ? 0.5 : 1.0 );
+            const double est = 1.15 * k_est * (double)n + 16.0 * (double)n + 6.0e7;
+            CB_TRY( v->tmp.ensure( sizeof( int ) * (size_t)est ) );
+        }
+        fa.tmp_off = v->tmp_off.as<unsigned>();
+        fa.cursor = reinterpret_cast<unsigned long long*>( v->ctrl.as<char>() );
+        fa.overflow = reinterpret_cast<int*>( v->ctrl.as<char>() + 8 );
+        for ( int attempt = 0;; ++attempt )
+        {
+            fa.tmp = v->tmp.as<int>();
+            fa.tmp_capacity = (long long)( v->tmp.capacity / sizeof( int ) );
+            CB_CUDA( cudaMemsetAsync( v->ctrl.ptr, 0, 64, stream ) );
+            CB_TRY( launch_fine_single( fa, algorithm, stream ) );
+            v->mark( 3, stream );
+            CB_TRY( max_and_sum_i32( v->counts.as<int>(), n, stats_dev, stream ) );
+            if ( layout == CB_LAYOUT_CSR )
+                CB_TRY( exclusive_scan_i32( v->counts.as<int>(), v->offsets.as<int>(), n,
+                                            false, nullptr, v->scan, stream ) );
+            CB_CUDA( cudaMemcpyAsync( stats_h, stats_dev, 2 * sizeof( long long ),
+                                      cudaMemcpyDeviceToHost, stream ) );
+            CB_CUDA( cudaMemcpyAsync( stats_h + 2, v->ctrl.ptr, 2 * sizeof( long long ),
+                                      cudaMemcpyDeviceToHost, stream ) );
+            v->mark( 4, stream );
+            CB_CUDA( cudaStreamSynchronize( stream ) ); // sizes the allocation (:518-528)
+            const int overflowed = (int)( stats_h[3] & 0xffffffffll );
+            if ( !overflowed )
+                break;
+            if ( attempt >= 2 )
+                return fail( CB_ERR_NOMEM, "cb_verlet_build: temporary buffer kept overflowing" );
+            CB_TRY( v->tmp.ensure( sizeof( int ) * (size_t)( (double)stats_h[2] * 1.05 + 1.0e6 ) ) );
+        }
+        v->max_n = stats_h[0];
+        v->total = stats_h[1];
+        if ( layout == CB_LAYOUT_CSR )
+        {
+            if ( v->total > 2147483647ll )
+                return fail( CB_ERR_OVERFLOW,
+                             "cb_verlet_build: total neighbours exceed INT_MAX" );
+            CB_TRY( v->neighbors.ensure(
+                sizeof( int ) * (size_t)( v->total > 0 ? v->total : 1 ), 1.05 ) );
+            fa.offsets = v->offsets.as<int>();
+            fa.width = 0;
+        }
+        else
+        {
+            // initCounts / processCounts(2D) (:495-505, :536-562): keep max_neigh when it is
+            // enough, otherwise reallocate to exactly max_n ("refill")
+            if ( max_neigh > 0 && v->max_n <= max_neigh )
+                v->width = max_neigh;
+            else
+            {
+                v->width = v->max_n;
+                if ( max_neigh > 0 )
+                    v->refilled = 1;
+            }
+            if ( (double)na * (double)v->width > 9.0e18 )
+                return fail( CB_ERR_OVERFLOW, "cb_verlet_build: 2D list too large" );
+            CB_TRY( v->neighbors.ensure(
+                sizeof( int ) * na * (size_t)( v->width > 0 ? v->width : 1 ) ) );
+            fa.offsets = nullptr;
+            fa.width = v->width;
+        }
+        fa.neighbors = v->neighbors.as<int>();
+        CB_TRY( launch_fine_reorder( fa, layout, stream ) );
+        v->mark( 5, stream );
+        v->built = true;
+        return CB_OK;
+    }
 
     if ( layout == CB_LAYOUT_CSR )
     {

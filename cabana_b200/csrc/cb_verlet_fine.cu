@@ -1,8 +1,9 @@
-// VerletList count / fill passes, v1: refined cell grid + FP32 filter + exact FP64 resolve.
+// VerletList construction kernels, v1: refined cell grid + FP32 filter + exact FP64
+// resolve + ONE test pass.
 //
 // Same reference semantics as cb_verlet.cu (core/src/Cabana_VerletList.hpp:316-474 count,
-// :572-713 fill) but organised for the B200's issue and L1 bandwidth limits (ncu on v0:
-// ~870-1200 warp instructions per particle, issue-bound, DRAM < 6 %):
+// :507-562 processCounts, :572-713 fill) but organised for what ncu showed on v0 (two
+// passes of ~870-1200 warp instructions per particle, issue-bound, DRAM < 6 %):
 //
 //  * Internal grid.  Every user cell (delta = cell_size_ratio * r) is split into m^3
 //    sub-cells of ~r/2 (m a power of two), so a home cell sees ~290 candidates instead of
@@ -10,11 +11,12 @@
 //    sub), so the reference's stencil range (+-R user cells,
 //    Cabana_LinkedCellList.hpp:105-119) is enforced exactly, and cell-level pruning here
 //    is only ever conservative (host-built table kz[|da|][|db|]).
-//  * One warp owns one home cell.  Lanes first build the cell's candidate list (one lane
-//    per stencil row = one contiguous span of the cell-sorted arrays, warp scan, indices
-//    materialised in shared memory and padded with a far-away sentinel), then every lane
-//    loads ONE candidate as a float4 and tests it against up to 4 home particles held in
-//    registers: list set-up and candidate load are shared by all particles of the cell.
+//  * Column kernel.  One warp owns a run of consecutive cells of one (a,b) column and
+//    builds ONE candidate index list for the run in shared memory, ordered layer-major
+//    (z cell, then stencil row): the candidates of home cell c are the contiguous layers
+//    [c-K, c+K].  Every lane loads ONE candidate (float4, L1-resident because the warps of
+//    a block take adjacent columns) and tests it against up to 4 home particles held in
+//    registers.
 //  * Two-tier decision.  Tier 1 is r^2 in FP32 on origin-relative coordinates with a
 //    rigorous error bound tau: s32 <= r^2 - tau is a certain hit, s32 > r^2 + tau a certain
 //    miss.  Only candidates inside the band (~0.02 per particle) go to tier 2: the exact
@@ -22,8 +24,13 @@
 //    exact half-list criterion, and -- when r^2 - band < s <= r^2 -- the reference's own
 //    cell prune (minDistanceToPoint on the user grid, :401-403).  Every in/out decision is
 //    therefore bit-identical to the reference's; DESIGN.md "Exactness" has the bounds.
-//  * Hits are recorded as per-lane bit masks (no ballot/popc in the hot loop) and written
-//    once per window with a warp scan, giving runs of consecutive stores per row.
+//  * Hits are recorded as per-lane bit masks (no ballot/popc in the hot loop).
+//  * ONE test pass.  The reference counts, scans, then repeats every distance test to fill
+//    (:1454-1480).  Here each row is compacted through shared memory straight after its
+//    tests and appended to a temporary buffer in binned order (space reserved per warp
+//    with one atomic per 4096 ids); counts[] come out of the same pass.  After the offsets
+//    scan a streaming kernel (k_reorder_rows) moves every row to its reference position
+//    (offsets = exclusive scan of counts in particle order, or row-major 2D).
 #include "cb_common.cuh"
 #include "cb_internal.h"
 #include "cb_verlet_fine.h"
@@ -33,17 +40,9 @@ namespace cb
 namespace
 {
 
-constexpr int kWarps = 8;
-constexpr int kBlock = kWarps * 32;
-constexpr int kListCap = 512; // candidates per window: 16 iterations of 32 lanes
-constexpr int kCellsPerWarp = 8;
-constexpr int kGroup = 4; // home particles per register group
-
-enum
-{
-    kCount = 0,
-    kFill = 1
-};
+constexpr int kGroup = 4;      // home particles per register group
+constexpr int kReserve = 4096; // ids a warp reserves in the temporary buffer per atomic
+constexpr int kRowBuf = 256;   // ids compacted through shared memory per row
 
 CB_D int warp_inclusive_scan( int v, unsigned lane )
 {
@@ -78,7 +77,7 @@ __device__ __noinline__ bool reference_prune_passes( const FineArgs& a, double x
     return min_distance_sq( a.ug, xp, yp, zp, cn[0], cn[1], cn[2] ) <= a.rsqr;
 }
 
-// Tier 2: exact arithmetic for the lanes' ambiguous candidates of home slot `ps`.
+// Tier 2: exact arithmetic for this lane's ambiguous candidates of home slot `ps`.
 template <bool HALF>
 __device__ __noinline__ unsigned resolve_exact( const FineArgs& a, const unsigned* list,
                                                 unsigned lane, unsigned ps, unsigned hit,
@@ -108,353 +107,132 @@ __device__ __noinline__ unsigned resolve_exact( const FineArgs& a, const unsigne
     return hit;
 }
 
-// Write this lane's hits of one home particle; `wr` is the lane's first slot in the row.
-template <bool CSR>
-__device__ __noinline__ void emit_hits( const FineArgs& a, const unsigned* list,
-                                        unsigned lane, unsigned hm, long long row_base,
-                                        int wr )
+// Warp-private bump allocation in the temporary id buffer.
+struct Reservation
 {
-    while ( hm )
+    long long cur = 0;
+    int left = 0;
+};
+
+CB_D long long reserve_ids( const FineArgs& a, Reservation& rs, int need, unsigned lane )
+{
+    if ( need > rs.left )
     {
-        const int it = __ffs( hm ) - 1;
-        hm &= hm - 1;
-        const unsigned idx = list[it * 32 + (int)lane];
-        const int id = __float_as_int( a.q[idx].w );
-        // 2D: writes past extent(1) are dropped but still counted (:99-105)
-        if ( CSR || wr < a.width )
-            a.neighbors[row_base + wr] = id;
-        ++wr;
+        const int take = max( kReserve, need );
+        unsigned long long got = 0ull;
+        if ( lane == 0 )
+            got = atomicAdd( a.cursor, (unsigned long long)take );
+        rs.cur = (long long)__shfl_sync( kFullMask, got, 0 );
+        rs.left = take;
     }
+    const long long at = rs.cur;
+    rs.cur += need;
+    rs.left -= need;
+    return at;
 }
 
-// Tier 1 hot loop: every lane tests ONE candidate per iteration against NP home particles.
-// Branch-free; the list is padded to a multiple of 32 with a sentinel at infinity.
-template <int NP, bool HALF>
-CB_D void test_window( const float4* __restrict__ q, const unsigned* list, int nit,
-                       int same, unsigned lane, float t_lo, float t_hi,
-                       const float ( &xi )[kGroup], const float ( &yi )[kGroup],
-                       const float ( &zi )[kGroup], unsigned ( &hit )[kGroup],
-                       unsigned ( &amb )[kGroup] )
+// Append one home particle's hits (per-lane masks over `list`) to the temporary buffer:
+// lanes scatter their ids into a shared-memory row at their scanned positions, then the
+// warp streams the row out with coalesced stores.  All lanes must call this.
+CB_D void emit_row( const FineArgs& a, Reservation& rs, const unsigned* list, int* rowbuf,
+                    unsigned lane, unsigned hm, int pid, unsigned slot )
 {
-    unsigned bit = 1u;
-    int t = (int)lane;
-#pragma unroll 2
-    for ( int it = 0; it < nit; ++it )
-    {
-        const float4 c = q[list[t]];
-        const bool in_slab = HALF && ( t < same );
-#pragma unroll
-        for ( int p = 0; p < NP; ++p )
-        {
-            const float dx = xi[p] - c.x;
-            const float dy = yi[p] - c.y;
-            const float dz = zi[p] - c.z;
-            const float s = fmaf( dz, dz, fmaf( dy, dy, dx * dx ) );
-            bool in = s <= t_hi;
-            bool am = s > t_lo;
-            if ( HALF )
-            {
-                // Rows beyond the home x-slab hold only larger x (the refined cell index
-                // is monotone in x): always valid.  Inside the slab float rounding is
-                // monotone too: c.x > xi certainly valid, c.x < xi certainly invalid, a
-                // tie goes to the exact criterion.
-                in = in && ( !in_slab || c.x >= xi[p] );
-                am = am || ( in_slab && c.x == xi[p] );
-            }
-            hit[p] |= in ? bit : 0u;
-            amb[p] |= ( in && am ) ? bit : 0u;
-        }
-        bit <<= 1;
-        t += 32;
-    }
-}
-
-// General per-cell kernel.  With worklist == nullptr it walks every refined cell; otherwise
-// only the cells the column kernel (below) could not take (too many stencil rows or
-// candidates for its shared-memory list), read from a device-side worklist.
-template <int MODE, bool HALF, bool CSR>
-__global__ void __launch_bounds__( kBlock, 3 )
-    k_verlet_fine( const __grid_constant__ FineArgs a, const unsigned* worklist,
-                   const unsigned* work_count )
-{
-    __shared__ unsigned s_list[kWarps][kListCap];
-    const unsigned lane = lane_id();
-    const int wib = threadIdx.x >> 5;
-    unsigned* list = s_list[wib];
-    const long long warp = (long long)blockIdx.x * kWarps + wib;
-    const long long nwarps = (long long)gridDim.x * kWarps;
-    const int nxf = a.nf[0], nyf = a.nf[1], nzf = a.nf[2];
-    const int lgm = a.lgm, R = a.R;
-    const int mm1 = ( 1 << lgm ) - 1;
-    const unsigned sentinel = (unsigned)a.n; // q[n] sits at +infinity
-
-    const long long nwork = worklist ? (long long)*work_count : a.ncell;
-    const int per_warp = worklist ? 1 : kCellsPerWarp;
-    for ( long long cbase = warp * per_warp; cbase < nwork; cbase += nwarps * per_warp )
-    {
-        const long long first = worklist ? (long long)worklist[cbase] : cbase;
-        int fc = (int)( first % nzf );
-        const long long tq = first / nzf;
-        int fb = (int)( tq % nyf );
-        int fa = (int)( tq / nyf );
-        const long long cend = worklist ? first + 1
-                                        : min( first + (long long)kCellsPerWarp, a.ncell );
-        for ( long long cell = first; cell < cend; ++cell )
-        {
-            const int ca = fa, cb_ = fb, cc = fc; // this cell's indices
-            if ( ++fc == nzf )
-            {
-                fc = 0;
-                if ( ++fb == nyf )
-                {
-                    fb = 0;
-                    ++fa;
-                }
-            }
-            const unsigned h0 = a.cell_off[cell];
-            const unsigned h1 = a.cell_off[cell + 1];
-            if ( h1 == h0 )
-                continue;
-
-            // Stencil ranges in refined cells: reference stencil (+-R user cells) cut down
-            // to what the cutoff can reach (+-K refined cells), clipped to the grid.
-            const int ua0 = ( ( ca >> lgm ) - R ) << lgm;
-            const int ub0 = ( ( cb_ >> lgm ) - R ) << lgm;
-            const int uc0 = ( ( cc >> lgm ) - R ) << lgm;
-            const int ua1 = ( ( ( ca >> lgm ) + R ) << lgm ) + mm1;
-            const int ub1 = ( ( ( cb_ >> lgm ) + R ) << lgm ) + mm1;
-            const int uc1 = ( ( ( cc >> lgm ) + R ) << lgm ) + mm1;
-            int alo = max( max( ua0, ca - a.K[0] ), 0 );
-            const int ahi = min( min( ua1, ca + a.K[0] ), nxf - 1 );
-            const int blo = max( max( ub0, cb_ - a.K[1] ), 0 );
-            const int bhi = min( min( ub1, cb_ + a.K[1] ), nyf - 1 );
-            const int zlo = max( uc0, 0 );
-            const int zhi = min( uc1, nzf - 1 );
-            if ( HALF )
-                alo = ca; // cells with a smaller x index hold only smaller x: never valid
-            const int nB = bhi - blo + 1;
-            const int nrows = ( ahi - alo + 1 ) * nB;
-            const int r_home = ( ca - alo ) * nB + ( cb_ - blo );
-            const unsigned nB_magic = ( 65536u + (unsigned)nB - 1u ) / (unsigned)nB;
-
-            for ( unsigned pg = h0; pg < h1; pg += kGroup )
-            {
-                const int np = (int)min( (unsigned)kGroup, h1 - pg );
-                float xi[kGroup], yi[kGroup], zi[kGroup];
-                int pid[kGroup];
-                int acc[kGroup];
-                unsigned active = 0u;
-#pragma unroll
-                for ( int p = 0; p < kGroup; ++p )
-                {
-                    // unused slots replicate the sentinel: they never hit
-                    const float4 h = a.q[p < np ? pg + p : sentinel];
-                    xi[p] = h.x;
-                    yi[p] = h.y;
-                    zi[p] = h.z;
-                    pid[p] = __float_as_int( h.w );
-                    acc[p] = 0;
-                    // only rows in [begin,end) are built (:340)
-                    if ( p < np && pid[p] >= a.begin && pid[p] < a.end )
-                        active |= 1u << p;
-                }
-                if ( active == 0u )
-                    continue;
-
-                for ( int rb = 0; rb < nrows; rb += 32 )
-                {
-                    // lane r: one stencil row = one contiguous span of sorted slots
-                    const int r = rb + (int)lane;
-                    unsigned start = 0;
-                    int len = 0;
-                    if ( r < nrows )
-                    {
-                        const int ra = (int)( ( (unsigned)r * nB_magic ) >> 16 );
-                        const int ap = alo + ra;
-                        const int bp = blo + ( r - ra * nB );
-                        const int kz = a.kz[min( abs( ap - ca ), 8 ) * 9 + min( abs( bp - cb_ ), 8 )];
-                        const int zl = max( zlo, cc - kz );
-                        const int zh = min( zhi, cc + kz );
-                        if ( kz >= 0 && zh >= zl )
-                        {
-                            const int c0 = ( ap * nyf + bp ) * nzf + zl;
-                            start = a.cell_off[c0];
-                            len = (int)( a.cell_off[c0 + ( zh - zl ) + 1] - start );
-                        }
-                    }
-                    const int incl = warp_inclusive_scan( len, lane );
-                    const int excl = incl - len;
-                    const int total = __shfl_sync( kFullMask, incl, 31 );
-                    int same_total = 0;
-                    if ( HALF )
-                    {
-                        // rows 0..nB-1 (ap == ca) come first
-                        const int ns = min( max( nB - rb, 0 ), 32 );
-                        if ( ns > 0 )
-                            same_total = __shfl_sync( kFullMask, incl, ns - 1 );
-                    }
-                    // virtual list position of home particle pg (for j != i)
-                    int self0 = -1;
-                    {
-                        const int hl = r_home - rb;
-                        const unsigned hs = __shfl_sync( kFullMask, start, hl & 31 );
-                        const int he = __shfl_sync( kFullMask, excl, hl & 31 );
-                        if ( hl >= 0 && hl < 32 )
-                            self0 = he + (int)( pg - hs );
-                    }
-
-                    for ( int w0 = 0; w0 < total; w0 += kListCap )
-                    {
-                        const int count = min( kListCap, total - w0 );
-                        const int nit = ( count + 31 ) >> 5;
-                        __syncwarp();
-                        {
-                            // each row lane writes its slice of the window
-                            int v = max( excl, w0 );
-                            const int v1 = min( incl, w0 + count );
-                            unsigned val = start + (unsigned)( v - excl );
-                            unsigned* dst = list + ( v - w0 );
-                            int left = v1 - v;
-                            while ( left >= 4 )
-                            {
-                                dst[0] = val;
-                                dst[1] = val + 1;
-                                dst[2] = val + 2;
-                                dst[3] = val + 3;
-                                dst += 4;
-                                val += 4;
-                                left -= 4;
-                            }
-                            if ( left > 0 )
-                                dst[0] = val;
-                            if ( left > 1 )
-                                dst[1] = val + 1;
-                            if ( left > 2 )
-                                dst[2] = val + 2;
-                            // pad to a multiple of 32 with the sentinel
-                            if ( count + (int)lane < nit * 32 )
-                                list[count + (int)lane] = sentinel;
-                        }
-                        __syncwarp();
-
-                        unsigned hit[kGroup] = { 0u, 0u, 0u, 0u };
-                        unsigned amb[kGroup] = { 0u, 0u, 0u, 0u };
-                        const int same = HALF ? ( same_total - w0 ) : 0;
-                        switch ( np )
-                        {
-                        case 1:
-                            test_window<1, HALF>( a.q, list, nit, same, lane, a.t_lo, a.t_hi,
-                                                  xi, yi, zi, hit, amb );
-                            break;
-                        case 2:
-                            test_window<2, HALF>( a.q, list, nit, same, lane, a.t_lo, a.t_hi,
-                                                  xi, yi, zi, hit, amb );
-                            break;
-                        case 3:
-                            test_window<3, HALF>( a.q, list, nit, same, lane, a.t_lo, a.t_hi,
-                                                  xi, yi, zi, hit, amb );
-                            break;
-                        default:
-                            test_window<4, HALF>( a.q, list, nit, same, lane, a.t_lo, a.t_hi,
-                                                  xi, yi, zi, hit, amb );
-                            break;
-                        }
-
-                        // j != i: each home particle is in its own list exactly once
-                        const int sp0 = self0 - w0;
-                        if ( self0 >= 0 && sp0 + kGroup > 0 && sp0 < kListCap )
-                        {
-#pragma unroll
-                            for ( int p = 0; p < kGroup; ++p )
-                            {
-                                const int sp = sp0 + p;
-                                if ( sp >= 0 && sp < kListCap && ( sp & 31 ) == (int)lane )
-                                {
-                                    hit[p] &= ~( 1u << ( sp >> 5 ) );
-                                    amb[p] &= ~( 1u << ( sp >> 5 ) );
-                                }
-                            }
-                        }
-                        // tier 2 (rare): exact arithmetic for the ambiguous band
-                        if ( __any_sync( kFullMask,
-                                         ( amb[0] | amb[1] | amb[2] | amb[3] ) != 0u ) )
-                        {
-#pragma unroll
-                            for ( int p = 0; p < kGroup; ++p )
-                                if ( amb[p] )
-                                    hit[p] = resolve_exact<HALF>( a, list, lane, pg + p,
-                                                                  hit[p], amb[p] );
-                        }
-
-                        if ( MODE == kCount )
-                        {
-#pragma unroll
-                            for ( int p = 0; p < kGroup; ++p )
-                                acc[p] += __popc( hit[p] );
-                        }
-                        else
-                        {
-#pragma unroll
-                            for ( int p = 0; p < kGroup; ++p )
-                            {
-                                if ( p < np )
-                                {
-                                    const int c = __popc( hit[p] );
-                                    const int inc = warp_inclusive_scan( c, lane );
-                                    const int tot = __shfl_sync( kFullMask, inc, 31 );
-                                    if ( ( active >> p ) & 1u )
-                                    {
-                                        const long long row_base =
-                                            CSR ? (long long)a.offsets[pid[p]]
-                                                : (long long)pid[p] * a.width;
-                                        emit_hits<CSR>( a, list, lane, hit[p], row_base,
-                                                        acc[p] + inc - c );
-                                    }
-                                    acc[p] += tot;
-                                }
-                            }
-                        }
-                    }
-                }
-
-#pragma unroll
-                for ( int p = 0; p < kGroup; ++p )
-                {
-                    if ( ( active >> p ) & 1u )
-                    {
-                        const int total =
-                            MODE == kCount ? warp_reduce_sum( acc[p] ) : acc[p];
-                        if ( lane == 0 )
-                            a.counts[pid[p]] = total;
-                    }
-                }
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// Column kernel (the fast path).  One warp owns a run of kChunk consecutive cells of one
-// (a,b) column.  The stencil rows (a',b') are the same for the whole run, so the warp builds
-// ONE candidate list for it, ordered LAYER-major (z cell k, then row): the candidates of
-// home cell c are then the contiguous range of layers [c-K, c+K] -- no per-cell list, no
-// per-cell row geometry; each new home cell costs one extra layer (one load and one scan).
-// Cells it cannot take (more than 64 stencil rows, more than 1024 candidates, or a run
-// whose layers overflow the shared-memory list) go to a worklist for k_verlet_fine.
-// ---------------------------------------------------------------------------------------
-constexpr int kColWarps = 8;
-constexpr int kColBlock = kColWarps * 32;
-constexpr int kColCap = 1024;  // list entries per warp
-constexpr int kChunk = 8;      // home cells per work item
-constexpr int kMaxLayers = kChunk + 2 * 8 + 1;
-
-CB_D void push_overflow( const FineArgs& a, unsigned cell, unsigned lane )
-{
+    const int c = __popc( hm );
+    const int inc = warp_inclusive_scan( c, lane );
+    const int tot = __shfl_sync( kFullMask, inc, 31 );
+    const long long at = reserve_ids( a, rs, tot, lane );
     if ( lane == 0 )
-        a.worklist[atomicAdd( a.work_count, 1u )] = cell;
+    {
+        a.counts[pid] = tot;
+        a.tmp_off[slot] = (unsigned)at;
+    }
+    if ( at + tot > a.tmp_capacity )
+    {
+        if ( lane == 0 )
+            *a.overflow = 1; // the host grows the buffer to *cursor and reruns the pass
+        return;
+    }
+    int wr = inc - c;
+    if ( tot <= kRowBuf )
+    {
+        __syncwarp();
+        // four hits per trip: the four list reads and id gathers are independent, so
+        // their latencies overlap instead of chaining
+        const unsigned* mine = list + lane;
+        while ( hm )
+        {
+            const int i0 = __ffs( hm ) - 1;
+            hm &= hm - 1;
+            const int i1 = hm ? __ffs( hm ) - 1 : i0;
+            const bool h1 = hm != 0u;
+            hm &= hm - 1;
+            const int i2 = hm ? __ffs( hm ) - 1 : i0;
+            const bool h2 = hm != 0u;
+            hm &= hm - 1;
+            const int i3 = hm ? __ffs( hm ) - 1 : i0;
+            const bool h3 = hm != 0u;
+            hm &= hm - 1;
+            const unsigned s0 = mine[i0 * 32], s1 = mine[i1 * 32], s2 = mine[i2 * 32],
+                           s3 = mine[i3 * 32];
+            const int d0 = (int)a.ids[s0], d1 = (int)a.ids[s1], d2 = (int)a.ids[s2],
+                      d3 = (int)a.ids[s3];
+            rowbuf[wr] = d0;
+            if ( h1 )
+                rowbuf[wr + 1] = d1;
+            if ( h2 )
+                rowbuf[wr + 2] = d2;
+            if ( h3 )
+                rowbuf[wr + 3] = d3;
+            wr += 4;
+        }
+        __syncwarp();
+        for ( int i = (int)lane; i < tot; i += 32 )
+            a.tmp[at + i] = rowbuf[i];
+    }
+    else
+    {
+        while ( hm )
+        {
+            const int it = __ffs( hm ) - 1;
+            hm &= hm - 1;
+            a.tmp[at + wr++] = (int)a.ids[list[it * 32 + (int)lane]];
+        }
+    }
 }
 
-// Tier 1 hot loop over list positions [t0, t1).
+// Tier 1 test of one candidate (c) against home particle (xi,yi,zi): sets `bit` in hit/amb.
+template <bool HALF>
+CB_D void test_one( const float4& c, float xi, float yi, float zi, float t_lo, float t_hi,
+                    unsigned bit, unsigned& hit, unsigned& amb )
+{
+    const float dx = xi - c.x;
+    const float dy = yi - c.y;
+    const float dz = zi - c.z;
+    const float s = fmaf( dz, dz, fmaf( dy, dy, dx * dx ) );
+    if ( HALF )
+    {
+        // x-major half criterion (Cabana_NeighborList.hpp:139-149) in FP32: float rounding
+        // is monotone, so c.x > xi is certainly valid, c.x < xi certainly invalid, and a
+        // tie goes to the exact criterion in tier 2.
+        const bool in = ( s <= t_hi ) && ( c.x >= xi );
+        const bool am = in && ( ( s > t_lo ) || ( c.x == xi ) );
+        hit |= in ? bit : 0u;
+        amb |= am ? bit : 0u;
+    }
+    else
+    {
+        asm( "{\n\t.reg .pred p, q;\n\t"
+             "setp.le.f32 p, %2, %3;\n\t"
+             "setp.gt.and.f32 q, %2, %4, p;\n\t"
+             "@p or.b32 %0, %0, %5;\n\t"
+             "@q or.b32 %1, %1, %5;\n\t}"
+             : "+r"( hit ), "+r"( amb )
+             : "f"( s ), "f"( t_hi ), "f"( t_lo ), "r"( bit ) );
+    }
+}
+
+// Hot loop over list positions [t0, t1): every lane tests ONE candidate per iteration
+// against NP home particles.  Lanes past t1 read the sentinel at infinity.
 template <int NP, bool HALF>
 CB_D void test_range( const float4* __restrict__ q, const unsigned* list, int t0, int t1,
                       unsigned lane, unsigned sentinel, float t_lo, float t_hi,
@@ -466,53 +244,101 @@ CB_D void test_range( const float4* __restrict__ q, const unsigned* list, int t0
 #pragma unroll 2
     for ( int tb = t0; tb < t1; tb += 32 )
     {
-        // lanes past the end read the sentinel at infinity instead of the next layer
         const int t = tb + (int)lane;
         const unsigned idx = t < t1 ? list[t] : sentinel;
         const float4 c = q[idx];
 #pragma unroll
         for ( int p = 0; p < NP; ++p )
-        {
-            const float dx = xi[p] - c.x;
-            const float dy = yi[p] - c.y;
-            const float dz = zi[p] - c.z;
-            const float s = fmaf( dz, dz, fmaf( dy, dy, dx * dx ) );
-            if ( HALF )
-            {
-                // x-major half criterion in FP32: float rounding is monotone, so c.x > xi
-                // is certainly valid, c.x < xi certainly invalid, a tie goes to tier 2.
-                const bool in = ( s <= t_hi ) && ( c.x >= xi[p] );
-                const bool am = in && ( ( s > t_lo ) || ( c.x == xi[p] ) );
-                hit[p] |= in ? bit : 0u;
-                amb[p] |= am ? bit : 0u;
-            }
-            else
-            {
-                asm( "{\n\t.reg .pred p, q;\n\t"
-                     "setp.le.f32 p, %2, %3;\n\t"
-                     "setp.gt.and.f32 q, %2, %4, p;\n\t"
-                     "@p or.b32 %0, %0, %5;\n\t"
-                     "@q or.b32 %1, %1, %5;\n\t}"
-                     : "+r"( hit[p] ), "+r"( amb[p] )
-                     : "f"( s ), "f"( t_hi ), "f"( t_lo ), "r"( bit ) );
-            }
-        }
+            test_one<HALF>( c, xi[p], yi[p], zi[p], t_lo, t_hi, bit, hit[p], amb[p] );
         bit <<= 1;
     }
 }
 
-template <int MODE, bool HALF, bool CSR>
+template <bool HALF>
+CB_D void test_group( int np, const float4* __restrict__ q, const unsigned* list, int t0,
+                      int t1, unsigned lane, unsigned sentinel, float t_lo, float t_hi,
+                      const float ( &xi )[kGroup], const float ( &yi )[kGroup],
+                      const float ( &zi )[kGroup], unsigned ( &hit )[kGroup],
+                      unsigned ( &amb )[kGroup] )
+{
+    switch ( np )
+    {
+    case 1:
+        test_range<1, HALF>( q, list, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
+                             amb );
+        break;
+    case 2:
+        test_range<2, HALF>( q, list, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
+                             amb );
+        break;
+    case 3:
+        test_range<3, HALF>( q, list, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
+                             amb );
+        break;
+    default:
+        test_range<4, HALF>( q, list, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
+                             amb );
+        break;
+    }
+}
+
+// Load a group of home particles; unused slots replicate the sentinel (id -1, never hits).
+CB_D unsigned load_group( const FineArgs& a, unsigned pg, int np, unsigned sentinel,
+                          float ( &xi )[kGroup], float ( &yi )[kGroup],
+                          float ( &zi )[kGroup], int ( &pid )[kGroup] )
+{
+    unsigned active = 0u;
+#pragma unroll
+    for ( int p = 0; p < kGroup; ++p )
+    {
+        const float4 h = a.q[p < np ? pg + p : sentinel];
+        xi[p] = h.x;
+        yi[p] = h.y;
+        zi[p] = h.z;
+        pid[p] = __float_as_int( h.w );
+    }
+    if ( a.full_range )
+        return ( 1u << np ) - 1u;
+    // only rows in [begin,end) are built (:340); the sentinel has id -1
+#pragma unroll
+    for ( int p = 0; p < kGroup; ++p )
+        if ( pid[p] >= a.begin && pid[p] < a.end )
+            active |= 1u << p;
+    return active;
+}
+
+// ---------------------------------------------------------------------------------------
+// Column kernel (the fast path).  Cells it cannot take (more than 64 stencil rows, more
+// than 1024 candidates, or a run whose layers overflow the shared-memory list) go to a
+// worklist for k_verlet_cells.
+// ---------------------------------------------------------------------------------------
+constexpr int kColWarps = 8;
+constexpr int kColBlock = kColWarps * 32;
+constexpr int kColCap = 1024; // list entries per warp
+constexpr int kChunk = 8;     // home cells per work item
+constexpr int kMaxLayers = kChunk + 2 * 8 + 1;
+
+CB_D void push_overflow( const FineArgs& a, unsigned cell, unsigned lane )
+{
+    if ( lane == 0 )
+        a.worklist[atomicAdd( a.work_count, 1u )] = cell;
+}
+
+template <bool HALF>
 __global__ void __launch_bounds__( kColBlock, 3 )
     k_verlet_column( const __grid_constant__ FineArgs a )
 {
     __shared__ unsigned s_list[kColWarps][kColCap];
+    __shared__ int s_row[kColWarps][kRowBuf];
     __shared__ int s_layer[kColWarps][kMaxLayers + 1];
     __shared__ int s_home[kColWarps][kMaxLayers];
     const unsigned lane = threadIdx.x & 31u;
     const int wib = threadIdx.x >> 5;
     unsigned* list = s_list[wib];
+    int* rowbuf = s_row[wib];
     int* layer = s_layer[wib];
     int* homepos = s_home[wib];
+    Reservation rs;
     const int nxf = a.nf[0], nyf = a.nf[1], nzf = a.nf[2];
     const int lgm = a.lgm, R = a.R;
     const int mm1 = ( 1 << lgm ) - 1;
@@ -535,7 +361,8 @@ __global__ void __launch_bounds__( kColBlock, 3 )
         const int cz1 = min( cz0 + kChunk, nzf );
         const int homebase = ( ca * nyf + cb_ ) * nzf;
 
-        // stencil rows of this column (same arithmetic as k_verlet_fine)
+        // Stencil rows of this column: reference stencil (+-R user cells) cut down to
+        // what the cutoff can reach (+-K refined cells), clipped to the grid.
         const int ua0 = ( ( ca >> lgm ) - R ) << lgm;
         const int ub0 = ( ( cb_ >> lgm ) - R ) << lgm;
         const int ua1 = ( ( ( ca >> lgm ) + R ) << lgm ) + mm1;
@@ -545,7 +372,7 @@ __global__ void __launch_bounds__( kColBlock, 3 )
         const int blo = max( max( ub0, cb_ - a.K[1] ), 0 );
         const int bhi = min( min( ub1, cb_ + a.K[1] ), nyf - 1 );
         if ( HALF )
-            alo = ca;
+            alo = ca; // cells with a smaller x index hold only smaller x: never valid
         const int nB = bhi - blo + 1;
         const int nrows = ( ahi - alo + 1 ) * nB;
         const int r_home = ( ca - alo ) * nB + ( cb_ - blo );
@@ -556,7 +383,7 @@ __global__ void __launch_bounds__( kColBlock, 3 )
         const int kL1 = min( cz1 - 1 + Kz, nzf - 1 );
         if ( nrows <= 64 )
         {
-            // lane owns rows `lane` and `lane + 32`
+            // lane owns stencil rows `lane` and `lane + 32`
             int rowbase[2];
             bool rowok[2];
             unsigned e_prev[2];
@@ -624,8 +451,7 @@ __global__ void __launch_bounds__( kColBlock, 3 )
                 if ( lane == 0 )
                     layer[k - kL0] = base;
                 if ( (int)lane == ( r_home & 31 ) )
-                    homepos[k - kL0] =
-                        base + ( r_home < 32 ? incl0 - len[0] : excl1 );
+                    homepos[k - kL0] = base + ( r_home < 32 ? incl0 - len[0] : excl1 );
                 base += tot;
                 ++nbuilt;
             }
@@ -664,43 +490,14 @@ __global__ void __launch_bounds__( kColBlock, 3 )
                 const int np = (int)min( (unsigned)kGroup, h1 - pg );
                 float xi[kGroup], yi[kGroup], zi[kGroup];
                 int pid[kGroup];
-                unsigned active = 0u;
-#pragma unroll
-                for ( int p = 0; p < kGroup; ++p )
-                {
-                    const float4 h = a.q[p < np ? pg + p : sentinel];
-                    xi[p] = h.x;
-                    yi[p] = h.y;
-                    zi[p] = h.z;
-                    pid[p] = __float_as_int( h.w );
-                    // only rows in [begin,end) are built (:340); the sentinel has id -1
-                    if ( pid[p] >= a.begin && pid[p] < a.end )
-                        active |= 1u << p;
-                }
+                const unsigned active = load_group( a, pg, np, sentinel, xi, yi, zi, pid );
                 if ( active == 0u )
                     continue;
 
                 unsigned hit[kGroup] = { 0u, 0u, 0u, 0u };
                 unsigned amb[kGroup] = { 0u, 0u, 0u, 0u };
-                switch ( np )
-                {
-                case 1:
-                    test_range<1, HALF>( a.q, list, t0, t1, lane, sentinel, a.t_lo, a.t_hi, xi,
-                                         yi, zi, hit, amb );
-                    break;
-                case 2:
-                    test_range<2, HALF>( a.q, list, t0, t1, lane, sentinel, a.t_lo, a.t_hi, xi,
-                                         yi, zi, hit, amb );
-                    break;
-                case 3:
-                    test_range<3, HALF>( a.q, list, t0, t1, lane, sentinel, a.t_lo, a.t_hi, xi,
-                                         yi, zi, hit, amb );
-                    break;
-                default:
-                    test_range<4, HALF>( a.q, list, t0, t1, lane, sentinel, a.t_lo, a.t_hi, xi,
-                                         yi, zi, hit, amb );
-                    break;
-                }
+                test_group<HALF>( np, a.q, list, t0, t1, lane, sentinel, a.t_lo, a.t_hi, xi,
+                                  yi, zi, hit, amb );
 
                 // j != i: home particle pg+p sits at list position selfbase + (pg-h0) + p
                 {
@@ -725,32 +522,216 @@ __global__ void __launch_bounds__( kColBlock, 3 )
                             hit[p] = resolve_exact<HALF>( a, list + t0, lane, pg + p, hit[p],
                                                           amb[p] );
                 }
-
 #pragma unroll
                 for ( int p = 0; p < kGroup; ++p )
+                    if ( ( active >> p ) & 1u )
+                        emit_row( a, rs, list + t0, rowbuf, lane, hit[p], pid[p], pg + p );
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// General per-cell kernel: any number of stencil rows and candidates (processed in
+// windows of kListCap).  It takes the column kernel's leftovers from the worklist, or
+// every cell when worklist == nullptr.  A row can span several windows here, so each group
+// of home particles is swept twice: once to size its rows, once to write them.
+// ---------------------------------------------------------------------------------------
+constexpr int kWarps = 8;
+constexpr int kBlock = kWarps * 32;
+constexpr int kListCap = 512;
+
+template <bool HALF>
+__global__ void __launch_bounds__( kBlock, 3 )
+    k_verlet_cells( const __grid_constant__ FineArgs a, const unsigned* worklist,
+                    const unsigned* work_count )
+{
+    __shared__ unsigned s_list[kWarps][kListCap];
+    Reservation rs;
+    const unsigned lane = threadIdx.x & 31u;
+    const int wib = threadIdx.x >> 5;
+    unsigned* list = s_list[wib];
+    const long long warp = (long long)blockIdx.x * kWarps + wib;
+    const long long nwarps = (long long)gridDim.x * kWarps;
+    const int nxf = a.nf[0], nyf = a.nf[1], nzf = a.nf[2];
+    const int lgm = a.lgm, R = a.R;
+    const int mm1 = ( 1 << lgm ) - 1;
+    const unsigned sentinel = (unsigned)a.n; // q[n] sits at +infinity
+    const long long nwork = worklist ? (long long)*work_count : a.ncell;
+
+    for ( long long w = warp; w < nwork; w += nwarps )
+    {
+        const long long cell = worklist ? (long long)worklist[w] : w;
+        const unsigned h0 = a.cell_off[cell];
+        const unsigned h1 = a.cell_off[cell + 1];
+        if ( h1 == h0 )
+            continue;
+        const int cc = (int)( cell % nzf );
+        const long long tq = cell / nzf;
+        const int cb_ = (int)( tq % nyf );
+        const int ca = (int)( tq / nyf );
+
+        const int ua0 = ( ( ca >> lgm ) - R ) << lgm;
+        const int ub0 = ( ( cb_ >> lgm ) - R ) << lgm;
+        const int uc0 = ( ( cc >> lgm ) - R ) << lgm;
+        const int ua1 = ( ( ( ca >> lgm ) + R ) << lgm ) + mm1;
+        const int ub1 = ( ( ( cb_ >> lgm ) + R ) << lgm ) + mm1;
+        const int uc1 = ( ( ( cc >> lgm ) + R ) << lgm ) + mm1;
+        int alo = max( max( ua0, ca - a.K[0] ), 0 );
+        const int ahi = min( min( ua1, ca + a.K[0] ), nxf - 1 );
+        const int blo = max( max( ub0, cb_ - a.K[1] ), 0 );
+        const int bhi = min( min( ub1, cb_ + a.K[1] ), nyf - 1 );
+        const int zlo = max( uc0, 0 );
+        const int zhi = min( uc1, nzf - 1 );
+        if ( HALF )
+            alo = ca;
+        const int nB = bhi - blo + 1;
+        const int nrows = ( ahi - alo + 1 ) * nB;
+        const int r_home = ( ca - alo ) * nB + ( cb_ - blo );
+
+        for ( unsigned pg = h0; pg < h1; pg += kGroup )
+        {
+            const int np = (int)min( (unsigned)kGroup, h1 - pg );
+            float xi[kGroup], yi[kGroup], zi[kGroup];
+            int pid[kGroup];
+            const unsigned active = load_group( a, pg, np, sentinel, xi, yi, zi, pid );
+            if ( active == 0u )
+                continue;
+            int acc[kGroup] = { 0, 0, 0, 0 }; // phase 0: row sizes; phase 1: ids written
+            long long at[kGroup] = { 0, 0, 0, 0 };
+            bool fits = true;
+
+            for ( int phase = 0; phase < 2; ++phase )
+            {
+                if ( phase == 1 )
                 {
-                    if ( p < np )
+#pragma unroll
+                    for ( int p = 0; p < kGroup; ++p )
                     {
-                        const int c = __popc( hit[p] );
-                        if ( MODE == kCount )
+                        if ( ( active >> p ) & 1u )
                         {
-                            const int total = warp_reduce_sum( c );
-                            if ( lane == 0 && ( ( active >> p ) & 1u ) )
-                                a.counts[pid[p]] = total;
+                            const int tot = warp_reduce_sum( acc[p] );
+                            at[p] = reserve_ids( a, rs, tot, lane );
+                            if ( lane == 0 )
+                            {
+                                a.counts[pid[p]] = tot;
+                                a.tmp_off[pg + p] = (unsigned)at[p];
+                            }
+                            if ( at[p] + tot > a.tmp_capacity )
+                                fits = false;
+                        }
+                        acc[p] = 0;
+                    }
+                    if ( !fits )
+                    {
+                        if ( lane == 0 )
+                            *a.overflow = 1;
+                        break;
+                    }
+                }
+                for ( int rb = 0; rb < nrows; rb += 32 )
+                {
+                    // lane r: one stencil row = one contiguous span of sorted slots
+                    const int r = rb + (int)lane;
+                    unsigned start = 0;
+                    int len = 0;
+                    if ( r < nrows )
+                    {
+                        const int ra = r / nB;
+                        const int ap = alo + ra;
+                        const int bp = blo + ( r - ra * nB );
+                        const int kz =
+                            a.kz[min( abs( ap - ca ), 8 ) * 9 + min( abs( bp - cb_ ), 8 )];
+                        const int zl = max( zlo, cc - kz );
+                        const int zh = min( zhi, cc + kz );
+                        if ( kz >= 0 && zh >= zl )
+                        {
+                            const int c0 = ( ap * nyf + bp ) * nzf + zl;
+                            start = a.cell_off[c0];
+                            len = (int)( a.cell_off[c0 + ( zh - zl ) + 1] - start );
+                        }
+                    }
+                    const int incl = warp_inclusive_scan( len, lane );
+                    const int excl = incl - len;
+                    const int total = __shfl_sync( kFullMask, incl, 31 );
+                    // virtual list position of home particle pg (for j != i)
+                    int self0 = -1;
+                    {
+                        const int hl = r_home - rb;
+                        const unsigned hs = __shfl_sync( kFullMask, start, hl & 31 );
+                        const int he = __shfl_sync( kFullMask, excl, hl & 31 );
+                        if ( hl >= 0 && hl < 32 )
+                            self0 = he + (int)( pg - hs );
+                    }
+
+                    for ( int w0 = 0; w0 < total; w0 += kListCap )
+                    {
+                        const int count = min( kListCap, total - w0 );
+                        __syncwarp();
+                        {
+                            // each row lane writes its slice of the window
+                            const int v0 = max( excl, w0 );
+                            const int v1 = min( incl, w0 + count );
+                            for ( int v = v0; v < v1; ++v )
+                                list[v - w0] = start + (unsigned)( v - excl );
+                        }
+                        __syncwarp();
+
+                        unsigned hit[kGroup] = { 0u, 0u, 0u, 0u };
+                        unsigned amb[kGroup] = { 0u, 0u, 0u, 0u };
+                        test_group<HALF>( np, a.q, list, 0, count, lane, sentinel, a.t_lo,
+                                          a.t_hi, xi, yi, zi, hit, amb );
+
+                        const int sp0 = self0 - w0;
+                        if ( self0 >= 0 && sp0 + kGroup > 0 && sp0 < kListCap )
+                        {
+#pragma unroll
+                            for ( int p = 0; p < kGroup; ++p )
+                            {
+                                const int sp = sp0 + p;
+                                if ( sp >= 0 && sp < kListCap && ( sp & 31 ) == (int)lane )
+                                {
+                                    hit[p] &= ~( 1u << ( sp >> 5 ) );
+                                    amb[p] &= ~( 1u << ( sp >> 5 ) );
+                                }
+                            }
+                        }
+                        if ( __any_sync( kFullMask,
+                                         ( amb[0] | amb[1] | amb[2] | amb[3] ) != 0u ) )
+                        {
+#pragma unroll
+                            for ( int p = 0; p < kGroup; ++p )
+                                if ( amb[p] )
+                                    hit[p] = resolve_exact<HALF>( a, list, lane, pg + p,
+                                                                  hit[p], amb[p] );
+                        }
+
+                        if ( phase == 0 )
+                        {
+#pragma unroll
+                            for ( int p = 0; p < kGroup; ++p )
+                                acc[p] += __popc( hit[p] );
                         }
                         else
                         {
-                            const int inc = warp_inclusive_scan( c, lane );
-                            const int tot = __shfl_sync( kFullMask, inc, 31 );
-                            if ( ( active >> p ) & 1u )
+#pragma unroll
+                            for ( int p = 0; p < kGroup; ++p )
                             {
-                                const long long row_base =
-                                    CSR ? (long long)a.offsets[pid[p]]
-                                        : (long long)pid[p] * a.width;
-                                emit_hits<CSR>( a, list + t0, lane, hit[p], row_base,
-                                                inc - c );
-                                if ( lane == 0 )
-                                    a.counts[pid[p]] = tot;
+                                if ( ( active >> p ) & 1u )
+                                {
+                                    const int c = __popc( hit[p] );
+                                    const int inc = warp_inclusive_scan( c, lane );
+                                    const int tot = __shfl_sync( kFullMask, inc, 31 );
+                                    long long wr = at[p] + acc[p] + inc - c;
+                                    unsigned hm = hit[p];
+                                    while ( hm )
+                                    {
+                                        const int it = __ffs( hm ) - 1;
+                                        hm &= hm - 1;
+                                        a.tmp[wr++] = (int)a.ids[list[it * 32 + (int)lane]];
+                                    }
+                                    acc[p] += tot;
+                                }
                             }
                         }
                     }
@@ -760,63 +741,109 @@ __global__ void __launch_bounds__( kColBlock, 3 )
     }
 }
 
-template <int MODE>
-int launch_mode( const FineArgs& a, int algorithm, int layout, cudaStream_t stream )
+// ---------------------------------------------------------------------------------------
+// Move every row from the binned-order temporary buffer to its reference position:
+//   CSR  neighbors[offsets[pid] + k]       (offsets = exclusive scan of counts in particle
+//                                            order, Cabana_VerletList.hpp:478-491, :507-523)
+//   2D   neighbors[pid*width + k], k < width (writes past extent(1) dropped, :99-105)
+// One warp per row, coalesced both ways: this is the only kernel of the build that is
+// HBM-bound (reads and writes 4 B per stored neighbour).
+// ---------------------------------------------------------------------------------------
+template <bool CSR>
+__global__ void __launch_bounds__( 256 )
+    k_reorder_rows( const unsigned* __restrict__ ids, const int* __restrict__ counts,
+                    const unsigned* __restrict__ tmp_off, const int* __restrict__ tmp,
+                    const int* __restrict__ offsets, int* __restrict__ neighbors,
+                    long long width, long long n, long long begin, long long end )
+{
+    // a quarter-warp per row, four rows in flight per warp: short rows (~78 ids) would
+    // otherwise leave each warp with only three loads outstanding
+    const unsigned sub = threadIdx.x & 7u;
+    const long long group = ( (long long)blockIdx.x * 256 + threadIdx.x ) >> 3;
+    const long long ngroups = ( (long long)gridDim.x * 256 ) >> 3;
+    for ( long long s = group; s < n; s += ngroups )
+    {
+        const int pid = (int)ids[s];
+        if ( pid < begin || pid >= end )
+            continue;
+        int c = counts[pid];
+        if ( !CSR && c > width )
+            c = (int)width;
+        const int* src = tmp + tmp_off[s];
+        int* dst = neighbors + ( CSR ? (long long)offsets[pid] : (long long)pid * width );
+        int i = (int)sub;
+        for ( ; i + 24 < c; i += 32 )
+        {
+            const int v0 = src[i], v1 = src[i + 8], v2 = src[i + 16], v3 = src[i + 24];
+            dst[i] = v0;
+            dst[i + 8] = v1;
+            dst[i + 16] = v2;
+            dst[i + 24] = v3;
+        }
+        for ( ; i < c; i += 8 )
+            dst[i] = src[i];
+    }
+}
+
+} // namespace
+
+int launch_fine_single( const FineArgs& a, int algorithm, cudaStream_t stream )
 {
     if ( a.n == 0 || a.ncell == 0 )
         return CB_OK;
     const bool half = algorithm == CB_NEIGHBOR_HALF;
-    const bool csr = layout == CB_LAYOUT_CSR;
     const bool columns = a.worklist != nullptr;
     if ( columns )
     {
         CB_CUDA( cudaMemsetAsync( a.work_count, 0, sizeof( unsigned ), stream ) );
         const int nchunk = ( a.nf[2] + kChunk - 1 ) / kChunk;
-        long long items = (long long)a.nf[0] * a.nf[1] * nchunk;
+        const long long items = (long long)a.nf[0] * a.nf[1] * nchunk;
         long long blocks = ( items + kColWarps - 1 ) / kColWarps;
-        const long long cap = (long long)kNumSMs * 3 * 16;
+        // persistent grid: 3 CTAs per SM (keeps the reservation slack of the temporary
+        // buffer at warps * kReserve ids ~ 58 MB)
+        const long long cap = (long long)kNumSMs * 3;
         if ( blocks > cap )
             blocks = cap;
-        const int grid = (int)blocks;
-        if ( half && csr )
-            k_verlet_column<MODE, true, true><<<grid, kColBlock, 0, stream>>>( a );
-        else if ( half )
-            k_verlet_column<MODE, true, false><<<grid, kColBlock, 0, stream>>>( a );
-        else if ( csr )
-            k_verlet_column<MODE, false, true><<<grid, kColBlock, 0, stream>>>( a );
+        if ( half )
+            k_verlet_column<true><<<(int)blocks, kColBlock, 0, stream>>>( a );
         else
-            k_verlet_column<MODE, false, false><<<grid, kColBlock, 0, stream>>>( a );
+            k_verlet_column<false><<<(int)blocks, kColBlock, 0, stream>>>( a );
         CB_CHECK_LAUNCH();
     }
     // General kernel: everything (no worklist) or the column kernel's leftovers.  The
     // leftover count lives on the device; an empty worklist costs one tiny launch.
-    long long blocks =
-        ( a.ncell + (long long)kWarps * kCellsPerWarp - 1 ) / ( (long long)kWarps * kCellsPerWarp );
-    const long long cap = columns ? (long long)kNumSMs * 3 : (long long)kNumSMs * 96;
+    long long blocks = ( a.ncell + kWarps - 1 ) / kWarps;
+    const long long cap = (long long)kNumSMs * 3;
     if ( blocks > cap )
         blocks = cap;
-    const int grid = (int)blocks;
     const unsigned* wl = columns ? a.worklist : nullptr;
     const unsigned* wc = columns ? a.work_count : nullptr;
-    if ( half && csr )
-        k_verlet_fine<MODE, true, true><<<grid, kBlock, 0, stream>>>( a, wl, wc );
-    else if ( half )
-        k_verlet_fine<MODE, true, false><<<grid, kBlock, 0, stream>>>( a, wl, wc );
-    else if ( csr )
-        k_verlet_fine<MODE, false, true><<<grid, kBlock, 0, stream>>>( a, wl, wc );
+    if ( half )
+        k_verlet_cells<true><<<(int)blocks, kBlock, 0, stream>>>( a, wl, wc );
     else
-        k_verlet_fine<MODE, false, false><<<grid, kBlock, 0, stream>>>( a, wl, wc );
+        k_verlet_cells<false><<<(int)blocks, kBlock, 0, stream>>>( a, wl, wc );
     CB_CHECK_LAUNCH();
     return CB_OK;
 }
 
-} // namespace
-
-int launch_fine_pass( const FineArgs& a, bool fill, int algorithm, int layout,
-                      cudaStream_t stream )
+int launch_fine_reorder( const FineArgs& a, int layout, cudaStream_t stream )
 {
-    return fill ? launch_mode<kFill>( a, algorithm, layout, stream )
-                : launch_mode<kCount>( a, algorithm, layout, stream );
+    if ( a.n == 0 )
+        return CB_OK;
+    long long blocks = ( a.n * 8 + 255 ) / 256;
+    const long long cap = (long long)kNumSMs * 64;
+    if ( blocks > cap )
+        blocks = cap;
+    if ( layout == CB_LAYOUT_CSR )
+        k_reorder_rows<true><<<(int)blocks, 256, 0, stream>>>(
+            a.ids, a.counts, a.tmp_off, a.tmp, a.offsets, a.neighbors, a.width, a.n, a.begin,
+            a.end );
+    else
+        k_reorder_rows<false><<<(int)blocks, 256, 0, stream>>>(
+            a.ids, a.counts, a.tmp_off, a.tmp, a.offsets, a.neighbors, a.width, a.n, a.begin,
+            a.end );
+    CB_CHECK_LAUNCH();
+    return CB_OK;
 }
 
 } // namespace cb

@@ -12,6 +12,7 @@ struct FineArgs
 {
     const float4* q;      // sorted slots: (x-ox, y-oy, z-oz) as float, w = particle id bits;
                           // q[n] is a sentinel at +infinity (list padding)
+    const unsigned* ids;  // sorted slot -> particle id (the LCL permutation)
     const double* xs;     // sorted exact coordinates
     const double* ys;
     const double* zs;
@@ -29,6 +30,7 @@ struct FineArgs
     double band;              // s > rsqr - band: evaluate the reference's cell prune
     float t_lo, t_hi;         // FP32 filter thresholds r^2 -+ tau
     long long n, begin, end;
+    int full_range;           // begin == 0 && end == n
     long long ncell;
     int* counts;
     const int* offsets;
@@ -36,9 +38,17 @@ struct FineArgs
     long long width;
     unsigned* worklist;   // [ncell] cells handed from the column kernel to the general one
     unsigned* work_count; // device counter; nullptr worklist = general kernel only
+    // single test pass: rows are appended here in binned order, then reordered
+    int* tmp;                   // [tmp_capacity] neighbour ids
+    unsigned* tmp_off;          // [n] row start in tmp, per SORTED slot
+    unsigned long long* cursor; // bump allocator of tmp (ids reserved so far)
+    int* overflow;              // set when tmp_capacity was too small
+    long long tmp_capacity;
 };
 
-int launch_fine_pass( const FineArgs& a, bool fill, int algorithm, int layout,
-                      cudaStream_t stream );
+// Test every pair once: counts[pid], tmp rows, tmp_off[slot].
+int launch_fine_single( const FineArgs& a, int algorithm, cudaStream_t stream );
+// Move the rows to neighbors[offsets[pid]..] (CSR) or neighbors[pid*width..] (2D).
+int launch_fine_reorder( const FineArgs& a, int layout, cudaStream_t stream );
 
 } // namespace cb
