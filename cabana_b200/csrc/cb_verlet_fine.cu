@@ -42,7 +42,8 @@ namespace
 
 constexpr int kGroup = 4;      // home particles per register group
 constexpr int kReserve = 4096; // ids a warp reserves in the temporary buffer per atomic
-constexpr int kRowBuf = 256;   // ids compacted through shared memory per row
+constexpr int kRowBuf = 128;   // ids compacted through shared memory per row
+constexpr int kIdBuf = 384;    // candidate ids of the current home cell kept in shared memory
 
 CB_D int warp_inclusive_scan( int v, unsigned lane )
 {
@@ -134,8 +135,9 @@ CB_D long long reserve_ids( const FineArgs& a, Reservation& rs, int need, unsign
 // Append one home particle's hits (per-lane masks over `list`) to the temporary buffer:
 // lanes scatter their ids into a shared-memory row at their scanned positions, then the
 // warp streams the row out with coalesced stores.  All lanes must call this.
-CB_D void emit_row( const FineArgs& a, Reservation& rs, const unsigned* list, int* rowbuf,
-                    unsigned lane, unsigned hm, int pid, unsigned slot )
+CB_D void emit_row( const FineArgs& a, Reservation& rs, const unsigned* list,
+                    const int* idbuf, int* rowbuf, unsigned lane, unsigned hm, int pid,
+                    unsigned slot )
 {
     const int c = __popc( hm );
     const int inc = warp_inclusive_scan( c, lane );
@@ -143,8 +145,8 @@ CB_D void emit_row( const FineArgs& a, Reservation& rs, const unsigned* list, in
     const long long at = reserve_ids( a, rs, tot, lane );
     if ( lane == 0 )
     {
-        a.counts[pid] = tot;
-        a.tmp_off[slot] = (unsigned)at;
+        __stcs( &a.counts[pid], tot );
+        __stcs( &a.tmp_off[slot], (unsigned)at );
     }
     if ( at + tot > a.tmp_capacity )
     {
@@ -156,38 +158,20 @@ CB_D void emit_row( const FineArgs& a, Reservation& rs, const unsigned* list, in
     if ( tot <= kRowBuf )
     {
         __syncwarp();
-        // four hits per trip: the four list reads and id gathers are independent, so
-        // their latencies overlap instead of chaining
-        const unsigned* mine = list + lane;
+        // the candidates' ids were parked in shared memory by the test loop (they arrive
+        // in the float4's w): no global gather, no dependent-load chain
+        const int* mine = idbuf + lane;
         while ( hm )
         {
-            const int i0 = __ffs( hm ) - 1;
+            const int it = __ffs( hm ) - 1;
             hm &= hm - 1;
-            const int i1 = hm ? __ffs( hm ) - 1 : i0;
-            const bool h1 = hm != 0u;
-            hm &= hm - 1;
-            const int i2 = hm ? __ffs( hm ) - 1 : i0;
-            const bool h2 = hm != 0u;
-            hm &= hm - 1;
-            const int i3 = hm ? __ffs( hm ) - 1 : i0;
-            const bool h3 = hm != 0u;
-            hm &= hm - 1;
-            const unsigned s0 = mine[i0 * 32], s1 = mine[i1 * 32], s2 = mine[i2 * 32],
-                           s3 = mine[i3 * 32];
-            const int d0 = (int)a.ids[s0], d1 = (int)a.ids[s1], d2 = (int)a.ids[s2],
-                      d3 = (int)a.ids[s3];
-            rowbuf[wr] = d0;
-            if ( h1 )
-                rowbuf[wr + 1] = d1;
-            if ( h2 )
-                rowbuf[wr + 2] = d2;
-            if ( h3 )
-                rowbuf[wr + 3] = d3;
-            wr += 4;
+            rowbuf[wr++] = mine[it * 32];
         }
         __syncwarp();
+        // streaming stores: the rows are not read again by this kernel and must not evict
+        // the candidate positions from L1
         for ( int i = (int)lane; i < tot; i += 32 )
-            a.tmp[at + i] = rowbuf[i];
+            __stcs( &a.tmp[at + i], rowbuf[i] );
     }
     else
     {
@@ -195,7 +179,7 @@ CB_D void emit_row( const FineArgs& a, Reservation& rs, const unsigned* list, in
         {
             const int it = __ffs( hm ) - 1;
             hm &= hm - 1;
-            a.tmp[at + wr++] = (int)a.ids[list[it * 32 + (int)lane]];
+            a.tmp[at + wr++] = idbuf[it * 32 + (int)lane];
         }
     }
 }
@@ -234,8 +218,9 @@ CB_D void test_one( const float4& c, float xi, float yi, float zi, float t_lo, f
 // Hot loop over list positions [t0, t1): every lane tests ONE candidate per iteration
 // against NP home particles.  Lanes past t1 read the sentinel at infinity.
 template <int NP, bool HALF>
-CB_D void test_range( const float4* __restrict__ q, const unsigned* list, int t0, int t1,
-                      unsigned lane, unsigned sentinel, float t_lo, float t_hi,
+CB_D void test_range( const float4* __restrict__ q, const unsigned* list, int* idbuf,
+                      int t0, int t1, unsigned lane, unsigned sentinel, float t_lo,
+                      float t_hi,
                       const float ( &xi )[kGroup], const float ( &yi )[kGroup],
                       const float ( &zi )[kGroup], unsigned ( &hit )[kGroup],
                       unsigned ( &amb )[kGroup] )
@@ -247,6 +232,8 @@ CB_D void test_range( const float4* __restrict__ q, const unsigned* list, int t0
         const int t = tb + (int)lane;
         const unsigned idx = t < t1 ? list[t] : sentinel;
         const float4 c = q[idx];
+        if ( idbuf )
+            idbuf[t - t0] = __float_as_int( c.w );
 #pragma unroll
         for ( int p = 0; p < NP; ++p )
             test_one<HALF>( c, xi[p], yi[p], zi[p], t_lo, t_hi, bit, hit[p], amb[p] );
@@ -255,8 +242,9 @@ CB_D void test_range( const float4* __restrict__ q, const unsigned* list, int t0
 }
 
 template <bool HALF>
-CB_D void test_group( int np, const float4* __restrict__ q, const unsigned* list, int t0,
-                      int t1, unsigned lane, unsigned sentinel, float t_lo, float t_hi,
+CB_D void test_group( int np, const float4* __restrict__ q, const unsigned* list,
+                      int* idbuf, int t0, int t1, unsigned lane, unsigned sentinel,
+                      float t_lo, float t_hi,
                       const float ( &xi )[kGroup], const float ( &yi )[kGroup],
                       const float ( &zi )[kGroup], unsigned ( &hit )[kGroup],
                       unsigned ( &amb )[kGroup] )
@@ -264,19 +252,19 @@ CB_D void test_group( int np, const float4* __restrict__ q, const unsigned* list
     switch ( np )
     {
     case 1:
-        test_range<1, HALF>( q, list, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
+        test_range<1, HALF>( q, list, idbuf, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
                              amb );
         break;
     case 2:
-        test_range<2, HALF>( q, list, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
+        test_range<2, HALF>( q, list, idbuf, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
                              amb );
         break;
     case 3:
-        test_range<3, HALF>( q, list, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
+        test_range<3, HALF>( q, list, idbuf, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
                              amb );
         break;
     default:
-        test_range<4, HALF>( q, list, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
+        test_range<4, HALF>( q, list, idbuf, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
                              amb );
         break;
     }
@@ -314,7 +302,7 @@ CB_D unsigned load_group( const FineArgs& a, unsigned pg, int np, unsigned senti
 // ---------------------------------------------------------------------------------------
 constexpr int kColWarps = 8;
 constexpr int kColBlock = kColWarps * 32;
-constexpr int kColCap = 1024; // list entries per warp
+constexpr int kColCap = 896;  // list entries per warp (static shared memory <= 48 KB)
 constexpr int kChunk = 8;     // home cells per work item
 constexpr int kMaxLayers = kChunk + 2 * 8 + 1;
 
@@ -330,12 +318,14 @@ __global__ void __launch_bounds__( kColBlock, 3 )
 {
     __shared__ unsigned s_list[kColWarps][kColCap];
     __shared__ int s_row[kColWarps][kRowBuf];
+    __shared__ int s_id[kColWarps][kIdBuf];
     __shared__ int s_layer[kColWarps][kMaxLayers + 1];
     __shared__ int s_home[kColWarps][kMaxLayers];
     const unsigned lane = threadIdx.x & 31u;
     const int wib = threadIdx.x >> 5;
     unsigned* list = s_list[wib];
     int* rowbuf = s_row[wib];
+    int* idbuf = s_id[wib];
     int* layer = s_layer[wib];
     int* homepos = s_home[wib];
     Reservation rs;
@@ -478,7 +468,7 @@ __global__ void __launch_bounds__( kColBlock, 3 )
             }
             const int t0 = layer[lo - kL0];
             const int t1 = layer[hi + 1 - kL0];
-            if ( t1 - t0 > 1024 )
+            if ( t1 - t0 > kIdBuf )
             {
                 push_overflow( a, (unsigned)( homebase + cc ), lane );
                 continue;
@@ -496,8 +486,10 @@ __global__ void __launch_bounds__( kColBlock, 3 )
 
                 unsigned hit[kGroup] = { 0u, 0u, 0u, 0u };
                 unsigned amb[kGroup] = { 0u, 0u, 0u, 0u };
-                test_group<HALF>( np, a.q, list, t0, t1, lane, sentinel, a.t_lo, a.t_hi, xi,
-                                  yi, zi, hit, amb );
+                __syncwarp();
+                test_group<HALF>( np, a.q, list, idbuf, t0, t1, lane, sentinel, a.t_lo,
+                                  a.t_hi, xi, yi, zi, hit, amb );
+                __syncwarp();
 
                 // j != i: home particle pg+p sits at list position selfbase + (pg-h0) + p
                 {
@@ -525,7 +517,8 @@ __global__ void __launch_bounds__( kColBlock, 3 )
 #pragma unroll
                 for ( int p = 0; p < kGroup; ++p )
                     if ( ( active >> p ) & 1u )
-                        emit_row( a, rs, list + t0, rowbuf, lane, hit[p], pid[p], pg + p );
+                        emit_row( a, rs, list + t0, idbuf, rowbuf, lane, hit[p], pid[p],
+                                  pg + p );
             }
         }
     }
@@ -679,8 +672,8 @@ __global__ void __launch_bounds__( kBlock, 3 )
 
                         unsigned hit[kGroup] = { 0u, 0u, 0u, 0u };
                         unsigned amb[kGroup] = { 0u, 0u, 0u, 0u };
-                        test_group<HALF>( np, a.q, list, 0, count, lane, sentinel, a.t_lo,
-                                          a.t_hi, xi, yi, zi, hit, amb );
+                        test_group<HALF>( np, a.q, list, nullptr, 0, count, lane, sentinel,
+                                          a.t_lo, a.t_hi, xi, yi, zi, hit, amb );
 
                         const int sp0 = self0 - w0;
                         if ( self0 >= 0 && sp0 + kGroup > 0 && sp0 < kListCap )
@@ -774,14 +767,15 @@ __global__ void __launch_bounds__( 256 )
         int i = (int)sub;
         for ( ; i + 24 < c; i += 32 )
         {
-            const int v0 = src[i], v1 = src[i + 8], v2 = src[i + 16], v3 = src[i + 24];
-            dst[i] = v0;
-            dst[i + 8] = v1;
-            dst[i + 16] = v2;
-            dst[i + 24] = v3;
+            const int v0 = __ldcs( src + i ), v1 = __ldcs( src + i + 8 ),
+                      v2 = __ldcs( src + i + 16 ), v3 = __ldcs( src + i + 24 );
+            __stcs( dst + i, v0 );
+            __stcs( dst + i + 8, v1 );
+            __stcs( dst + i + 16, v2 );
+            __stcs( dst + i + 24, v3 );
         }
         for ( ; i < c; i += 8 )
-            dst[i] = src[i];
+            __stcs( dst + i, __ldcs( src + i ) );
     }
 }
 
