@@ -1,0 +1,215 @@
+"""GPU tests of the slab Halo / Distributor path.
+
+Single-GPU part: the csrc/cb_comm.cu kernels through the C ABI against numpy restatements of
+the reference semantics (countSendsAndCreateSteering, gather pack/unpack, scatter).
+Multi-GPU part (skipped with fewer than 2 devices): a 2-rank NCCL run in which the union of
+the owner-local Verlet lists, mapped to global ids, must equal the single-GPU list exactly
+(SURVEY.md section 8e "parity under sharding").
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from cabana_b200 import datasets
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    assert torch.cuda.is_available()
+    from cabana_b200 import comm
+    from cabana_b200 import core as cb
+
+    return cb, comm
+
+
+def test_count_and_steer_matches_reference_semantics(mods):
+    cb, comm = mods
+    k = comm.CudaCommKernels()
+    rng = np.random.default_rng(3)
+    n, nr = 100_000, 8
+    ranks = rng.integers(-1, nr, n).astype(np.int32)  # -1 = not exported
+    ids = rng.integers(0, 1 << 20, n).astype(np.int32)
+    counts, offsets, steering = k.count_and_steer(torch.from_numpy(ranks).cuda(),
+                                                  torch.from_numpy(ids).cuda(), nr)
+    steering = steering.cpu().numpy()
+    assert counts == [int((ranks == r).sum()) for r in range(nr)]
+    assert offsets[0] == 0 and offsets[-1] == sum(counts)
+    for r in range(nr):
+        # ascending rank blocks, ascending export index inside a block (deterministic)
+        assert np.array_equal(steering[offsets[r]:offsets[r + 1]], ids[ranks == r])
+    # identity ids
+    counts2, offsets2, steer2 = k.count_and_steer(torch.from_numpy(ranks).cuda(), None, nr)
+    assert counts2 == counts
+    assert np.array_equal(steer2.cpu().numpy()[:offsets2[-1]],
+                          np.concatenate([np.nonzero(ranks == r)[0] for r in range(nr)]))
+
+
+@pytest.mark.parametrize("layout", ["view", "slice"])
+def test_pack_unpack_scatter(mods, layout):
+    cb, comm = mods
+    k = comm.CudaCommKernels()
+    rng = np.random.default_rng(4)
+    n = 5000
+    x = rng.random((n, 3))
+    v = rng.random((n, 2))
+    ident = np.arange(n, dtype=np.int32).reshape(-1, 1)
+    mk = (lambda a: cb.view_from_array(a)) if layout == "view" else (lambda a: cb.slice_from_array(a, vlen=32, extra=1))
+    fx, fv, fi = mk(x), mk(v), mk(ident)
+    steering = torch.from_numpy(rng.integers(0, n, 777).astype(np.int32)).cuda()
+    tb = k.tuple_bytes([fx, fi, fv])
+    assert tb == 48  # 24 + 4 (+4 pad) + 16
+    buf = torch.zeros(777 * tb, dtype=torch.uint8, device="cuda")
+    k.pack([fx, fi, fv], steering, 777, buf)
+    raw = buf.cpu().numpy().reshape(777, tb)
+    st = steering.cpu().numpy()
+    assert np.array_equal(raw[:, :24].copy().view(np.float64).reshape(777, 3), x[st])
+    assert np.array_equal(raw[:, 24:28].copy().view(np.int32)[:, 0], ident[st, 0])
+    assert np.array_equal(raw[:, 32:48].copy().view(np.float64).reshape(777, 2), v[st])
+    # unpack into the ghost region [n, n+777)
+    gx, gv, gi = mk(np.zeros((n + 777, 3))), mk(np.zeros((n + 777, 2))), mk(np.zeros((n + 777, 1), dtype=np.int32))
+    k.unpack([gx, gi, gv], n, 777, buf)
+    assert np.array_equal(gx.to_array().cpu().numpy()[n:], x[st])
+    assert np.array_equal(gi.to_array().cpu().numpy()[n:, 0], ident[st, 0])
+    assert np.array_equal(gv.to_array().cpu().numpy()[n:], v[st])
+    assert not gx.to_array().cpu().numpy()[:n].any()
+    # scatter: atomic add with collisions (tstHalo.hpp:146-185)
+    f = mk(np.zeros((n, 3)))
+    contrib = rng.random((777, 3))
+    k.scatter_add(f, steering, 777, torch.from_numpy(contrib).cuda().view(torch.uint8).reshape(-1))
+    exp = np.zeros((n, 3))
+    np.add.at(exp, st, contrib)
+    assert np.allclose(f.to_array().cpu().numpy(), exp, rtol=1e-13, atol=1e-13)
+
+
+def test_slab_select_and_destinations(mods):
+    cb, comm = mods
+    k = comm.CudaCommKernels()
+    rng = np.random.default_rng(5)
+    n = 20000
+    x = rng.random((n, 3)) * np.array([10.0, 3.0, 3.0]) + np.array([20.0, 0, 0])
+    fx = cb.slice_from_array(x, vlen=32)
+    ids, ranks = k.slab_halo_select(fx, n, 21.5, 28.5, 4, 6)
+    ranks = ranks.cpu().numpy().reshape(n, 2)
+    assert np.array_equal(ids.cpu().numpy().reshape(n, 2), np.repeat(np.arange(n), 2).reshape(n, 2))
+    assert np.array_equal(ranks[:, 0], np.where(x[:, 0] < 21.5, 4, -1))
+    assert np.array_equal(ranks[:, 1], np.where(x[:, 0] >= 28.5, 6, -1))
+    # no neighbour on the low side
+    _, r2 = k.slab_halo_select(fx, n, 21.5, 28.5, -1, 6)
+    assert np.all(r2.cpu().numpy().reshape(n, 2)[:, 0] == -1)
+    bounds = [20.0, 22.5, 25.0, 27.5, 29.0]  # last slab ends before some particles
+    dest = k.slab_destinations(fx, n, bounds).cpu().numpy()
+    exp = np.full(n, -1)
+    for g in range(4):
+        exp[(x[:, 0] >= bounds[g]) & (x[:, 0] < bounds[g + 1])] = g
+    exp[x[:, 0] == bounds[4]] = 3
+    assert np.array_equal(dest, exp)
+
+
+# ------------------------------------------------------------------------------------ 2 GPUs
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _rank_main(rank, world, port, ret):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from cabana_b200 import comm
+        from cabana_b200 import core as cb
+
+        ps = datasets.fcc_lattice(24, jitter=0.03)  # 55 296 atoms
+        r = ps.radius
+        L = ps.grid_max[0]
+        bounds = [L * g / world for g in range(world + 1)]
+        owner = np.minimum((ps.xyz[:, 0] / (L / world)).astype(int), world - 1)
+        mine = np.nonzero(owner == rank)[0]
+        nl = len(mine)
+        slab = comm.SlabDecomposition(bounds, r)
+        cap = nl + 30000
+        store = np.zeros((cap, 3))
+        store[:nl] = ps.xyz[mine]
+        gid = np.full((cap, 1), -1, dtype=np.int32)
+        gid[:nl, 0] = mine
+        x_all = cb.slice_from_array(store, vlen=32)
+        g_all = cb.view_from_array(gid)
+        x_own = cb.Slice(x_all.data, nl, x_all.outer_stride, x_all.vlen, x_all.comp_stride, 3)
+        halo = slab.create_halo(x_own, nl)
+        nt = halo.numLocal() + halo.numGhost()
+        x_tot = cb.Slice(x_all.data, nt, x_all.outer_stride, x_all.vlen, x_all.comp_stride, 3)
+        g_tot = cb.Slice(g_all.data, nt, 1, 1, 1, 1)
+        comm.gather(halo, x_tot, g_tot)
+        lgx = slab.local_grid_x()
+        out = {}
+        for algo in (cb.FULL, cb.HALF):
+            lst = cb.VerletList(x_tot, 0, nl, r, 1.0, (lgx[0], 0.0, 0.0), (lgx[1], ps.grid_max[1], ps.grid_max[2]),
+                                algorithm=algo, layout=cb.CSR)
+            counts = lst._data.counts.cpu().numpy()[:nl]
+            offs = lst._data.offsets.cpu().numpy()[:nl]
+            nb = lst._data.neighbors.cpu().numpy()
+            g = g_tot.to_array().cpu().numpy()[:, 0]
+            rows = {int(mine[i]): sorted(int(v) for v in g[nb[offs[i]:offs[i] + counts[i]]]) for i in range(nl)}
+            out[algo] = rows
+            if algo == cb.HALF:
+                # forces on ghosts go home through scatter and match the full-list forces
+                f = cb.view_from_array(np.zeros((cap, 3)))
+                f_tot = cb.Slice(f.data, nt, 3, 1, 1, 3)
+                cb.neighbor_parallel_for_lj(0, nl, lst, x_tot, f_tot, 1.0, 1.0, 2.5, cb.OP_TEAM)
+                comm.scatter(halo, f_tot)
+                out["f_half"] = (mine, f.to_array().cpu().numpy()[:nl])
+            else:
+                f = cb.view_from_array(np.zeros((cap, 3)))
+                f_tot = cb.Slice(f.data, nt, 3, 1, 1, 3)
+                cb.neighbor_parallel_for_lj(0, nl, lst, x_tot, f_tot, 1.0, 1.0, 2.5, cb.OP_SERIAL)
+                out["f_full"] = (mine, f.to_array().cpu().numpy()[:nl])
+        ret[rank] = out
+    except Exception:
+        import traceback
+
+        ret[rank] = traceback.format_exc()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_slab_build_equals_single_gpu(orc):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_rank_main, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for r in range(world):
+        assert isinstance(ret[r], dict), ret[r]
+    ps = datasets.fcc_lattice(24, jitter=0.03)
+    ox = orc.view_from_xyz(ps.xyz)
+    for algo, oalgo in ((0, orc.FULL), (1, orc.HALF)):
+        ref = orc.verlet_build(ox, 0, ps.n, ps.radius, 1.0, ps.grid_min, ps.grid_max, algo=oalgo)
+        merged = {}
+        for r in range(world):
+            merged.update(ret[r][algo])
+        assert len(merged) == ps.n
+        for i in range(ps.n):
+            assert merged[i] == sorted(int(v) for v in ref.row(i)), i
+    # forces: sharded half + scatter == sharded full == oracle (1e-12 of sum |pair force|)
+    full = orc.verlet_build(ox, 0, ps.n, ps.radius, 1.0, ps.grid_min, ps.grid_max, algo=orc.FULL)
+    f_ref, fabs = orc.lj_forces(ox, orc.CSR, full.counts, full.offsets, full.neighbors, 0, 0, ps.n, 1.0, 1.0, 2.5)
+    for key in ("f_full", "f_half"):
+        got = np.zeros((ps.n, 3))
+        for r in range(world):
+            mine, f = ret[r][key]
+            got[mine] = f
+        assert np.all(np.abs(got - f_ref) <= 1e-12 * np.maximum(fabs, 1e-300)), key
