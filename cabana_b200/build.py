@@ -84,6 +84,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+CPP_TEST_SRC = os.path.join(ROOT, "tests", "cpp", "test_cabana_api.cu")
+CPP_TEST_BIN = os.path.join(ROOT, "tests", "cpp", "test_cabana_api.bin")
+
+
+def build_cpp_test(force: bool = False) -> str:
+    """Compile the C++ test of include/Cabana_B200.hpp against the in-tree library."""
+    build()
+    deps = [CPP_TEST_SRC, os.path.join(ROOT, "include", "Cabana_B200.hpp"),
+            os.path.join(ROOT, "include", "cabana_b200.h"), LIB_PATH]
+    if (not force and os.path.exists(CPP_TEST_BIN)
+            and all(os.path.getmtime(CPP_TEST_BIN) >= os.path.getmtime(d) for d in deps)):
+        return CPP_TEST_BIN
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
+           "-ccbin", HOST_CXX, "--extended-lambda", "-I", os.path.join(ROOT, "include"),
+           CPP_TEST_SRC, "-o", CPP_TEST_BIN, "-L", LIB_DIR, "-lcabana_b200",
+           "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../cabana_b200/lib", "-cudart", "shared"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("C++ shim test failed to compile")
+    return CPP_TEST_BIN
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(path)

@@ -1,0 +1,472 @@
+// C++ test of include/Cabana_B200.hpp, written the way the reference's own unit tests are
+// (core/unit_test/tstNeighborList.hpp, neighbor_unit_test.hpp, tstLinkedCellList.hpp):
+// build lists through the Cabana-named classes, compare with a brute-force N^2 list
+// computed in the test, exercise neighbor_parallel_for / reduce with user functors.
+//
+// Compiled with nvcc and linked against libcabana_b200.so by tests/test_gpu_cpp_shim.py.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "Cabana_B200.hpp"
+
+static int g_fail = 0;
+#define EXPECT_TRUE( c )                                                       \
+    do                                                                         \
+    {                                                                          \
+        if ( !( c ) )                                                          \
+        {                                                                      \
+            std::printf( "FAIL %s:%d  %s\n", __FILE__, __LINE__, #c );         \
+            ++g_fail;                                                          \
+        }                                                                      \
+    } while ( 0 )
+#define EXPECT_EQ( a, b ) EXPECT_TRUE( ( a ) == ( b ) )
+
+// ---- test data: NeighborListTestData<3> (neighbor_unit_test.hpp:995-1045) ------------------
+struct TestData
+{
+    std::size_t num_particle = 300;
+    std::size_t begin = 75, end = 225;
+    double test_radius = 2.32;
+    double box_min = -5.3 * 2.32, box_max = 4.7 * 2.32;
+    double cell_size_ratio = 0.5;
+    std::array<double, 3> grid_min, grid_max;
+    std::vector<double> xyz; // (n,3)
+    int vlen = 32;
+    std::size_t stride = 3 * 32;
+    double* d_aosoa = nullptr; // AoSoA<MemberTypes<double[3]>> layout on the device
+
+    TestData()
+    {
+        grid_min = { box_min, box_min, box_min };
+        grid_max = { box_max, box_max, box_max };
+        xyz.resize( 3 * num_particle );
+        std::uint64_t s = 88172645463325252ull; // xorshift64, any fixed seed
+        for ( auto& v : xyz )
+        {
+            s ^= s << 13;
+            s ^= s >> 7;
+            s ^= s << 17;
+            v = box_min + ( box_max - box_min ) * ( ( s >> 11 ) * ( 1.0 / 9007199254740992.0 ) );
+        }
+        const std::size_t nsoa = ( num_particle + vlen - 1 ) / vlen;
+        std::vector<double> host( nsoa * stride, 0.0 );
+        for ( std::size_t i = 0; i < num_particle; ++i )
+            for ( int d = 0; d < 3; ++d )
+                host[stride * ( i / vlen ) + ( i % vlen ) + vlen * d] = xyz[3 * i + d];
+        cudaMalloc( &d_aosoa, host.size() * sizeof( double ) );
+        cudaMemcpy( d_aosoa, host.data(), host.size() * sizeof( double ),
+                    cudaMemcpyHostToDevice );
+    }
+    ~TestData() { cudaFree( d_aosoa ); }
+    Cabana::Slice<double, 3> positions() const
+    {
+        return Cabana::Slice<double, 3>( d_aosoa, num_particle, stride, vlen );
+    }
+};
+
+// computeFullNeighborList (neighbor_unit_test.hpp:86-158)
+static std::vector<std::vector<int>> bruteForce( const TestData& t )
+{
+    std::vector<std::vector<int>> nl( t.num_particle );
+    const double rsqr = t.test_radius * t.test_radius;
+    for ( std::size_t i = 0; i < t.num_particle; ++i )
+        for ( std::size_t j = 0; j < t.num_particle; ++j )
+            if ( i != j )
+            {
+                double dsqr = 0.0;
+                for ( int d = 0; d < 3; ++d )
+                    dsqr += ( t.xyz[3 * i + d] - t.xyz[3 * j + d] ) *
+                            ( t.xyz[3 * i + d] - t.xyz[3 * j + d] );
+                if ( dsqr <= rsqr )
+                    nl[i].push_back( (int)j );
+            }
+    return nl;
+}
+
+template <class ListType>
+static std::vector<std::vector<int>> copyListToHost( const ListType& list, std::size_t n )
+{
+    const cb_verlet_view& v = list.view();
+    std::vector<int> counts( n );
+    cudaMemcpy( counts.data(), v.counts, n * sizeof( int ), cudaMemcpyDeviceToHost );
+    std::vector<std::vector<int>> out( n );
+    if ( v.layout == CB_LAYOUT_CSR )
+    {
+        std::vector<int> offsets( n ), nb( std::max<std::size_t>( v.total, 1 ) );
+        cudaMemcpy( offsets.data(), v.offsets, n * sizeof( int ), cudaMemcpyDeviceToHost );
+        cudaMemcpy( nb.data(), v.neighbors, v.total * sizeof( int ), cudaMemcpyDeviceToHost );
+        for ( std::size_t i = 0; i < n; ++i )
+            out[i].assign( nb.begin() + offsets[i], nb.begin() + offsets[i] + counts[i] );
+    }
+    else
+    {
+        std::vector<int> nb( std::max<std::size_t>( n * v.width, 1 ) );
+        cudaMemcpy( nb.data(), v.neighbors, n * v.width * sizeof( int ), cudaMemcpyDeviceToHost );
+        for ( std::size_t i = 0; i < n; ++i )
+            out[i].assign( nb.begin() + i * v.width, nb.begin() + i * v.width + counts[i] );
+    }
+    for ( auto& r : out )
+        std::sort( r.begin(), r.end() );
+    return out;
+}
+
+// checkFullNeighborList (neighbor_unit_test.hpp:161-198)
+template <class ListType>
+static void checkFullNeighborList( const ListType& list, const TestData& t,
+                                   const std::vector<std::vector<int>>& n2, std::size_t b,
+                                   std::size_t e )
+{
+    auto got = copyListToHost( list, t.num_particle );
+    std::size_t total = 0, mx = 0;
+    for ( std::size_t i = 0; i < t.num_particle; ++i )
+    {
+        if ( i >= b && i < e )
+        {
+            EXPECT_TRUE( got[i] == n2[i] );
+            total += n2[i].size();
+            mx = std::max( mx, n2[i].size() );
+        }
+        else
+            EXPECT_EQ( got[i].size(), 0u );
+    }
+    EXPECT_EQ( Cabana::NeighborList<ListType>::totalNeighbor( list ), total );
+    EXPECT_EQ( Cabana::NeighborList<ListType>::maxNeighbor( list ), mx );
+}
+
+// checkHalfNeighborList (neighbor_unit_test.hpp:201-243)
+template <class ListType>
+static void checkHalfNeighborList( const ListType& list, const TestData& t,
+                                   const std::vector<std::vector<int>>& n2 )
+{
+    auto got = copyListToHost( list, t.num_particle );
+    std::size_t full = 0, half = 0;
+    for ( std::size_t i = 0; i < t.num_particle; ++i )
+    {
+        full += n2[i].size();
+        half += got[i].size();
+        for ( int j : got[i] )
+        {
+            EXPECT_TRUE( std::binary_search( n2[i].begin(), n2[i].end(), j ) );
+            EXPECT_TRUE( !std::binary_search( got[j].begin(), got[j].end(), (int)i ) );
+        }
+    }
+    EXPECT_EQ( full, 2 * half );
+    EXPECT_EQ( Cabana::NeighborList<ListType>::totalNeighbor( list ), full / 2 );
+}
+
+// ---- user functors (neighbor_unit_test.hpp:291-419) ----------------------------------------
+struct IdSumFunctor
+{
+    long long* result;
+    __device__ void operator()( const int i, const int j ) const
+    {
+        atomicAdd( reinterpret_cast<unsigned long long*>( result + i ), (unsigned long long)j );
+    }
+};
+struct TaggedIdSumFunctor
+{
+    struct Tag
+    {
+    };
+    long long* result;
+    __device__ void operator()( const Tag&, const int i, const int j ) const
+    {
+        atomicAdd( reinterpret_cast<unsigned long long*>( result + i ),
+                   (unsigned long long)( 2 * j ) );
+    }
+};
+struct SumPositionsFunctor
+{
+    Cabana::Slice<double, 3> x;
+    __device__ void operator()( const int i, const int j, double& sum ) const
+    {
+        sum += x( i, 0 ) + x( j, 0 );
+    }
+};
+
+template <class LayoutTag>
+static void testVerletListFull()
+{
+    TestData t;
+    auto n2 = bruteForce( t );
+    auto x = t.positions();
+    {
+        Cabana::VerletList<Cabana::DeviceSpace, Cabana::FullNeighborTag, LayoutTag,
+                           Cabana::TeamOpTag>
+            nlist( x, 0, x.size(), t.test_radius, t.cell_size_ratio, t.grid_min, t.grid_max );
+        checkFullNeighborList( nlist, t, n2, 0, t.num_particle );
+        // default construct then assign (tstNeighborList.hpp:42-46)
+        Cabana::VerletList<Cabana::DeviceSpace, Cabana::FullNeighborTag, LayoutTag,
+                           Cabana::TeamOpTag>
+            nlist2;
+        nlist2 = nlist;
+        checkFullNeighborList( nlist2, t, n2, 0, t.num_particle );
+    }
+    for ( std::size_t max_neigh : { std::size_t( 100 ), std::size_t( 2 ) } )
+    {
+        // max_neigh large (no recount) and too small (refill), tstNeighborList.hpp:58-77
+        auto nlist = Cabana::createVerletList<Cabana::FullNeighborTag, LayoutTag,
+                                              Cabana::TeamVectorOpTag>(
+            x, 0, x.size(), t.test_radius, t.cell_size_ratio, t.grid_min, t.grid_max,
+            max_neigh );
+        checkFullNeighborList( nlist, t, n2, 0, t.num_particle );
+    }
+    {
+        // partial range (tstNeighborList.hpp:112-141)
+        Cabana::VerletList<Cabana::DeviceSpace, Cabana::FullNeighborTag, LayoutTag> nlist(
+            x, t.begin, t.end, t.test_radius, t.cell_size_ratio, t.grid_min, t.grid_max );
+        checkFullNeighborList( nlist, t, n2, t.begin, t.end );
+    }
+    {
+        // rank-2 view instead of a slice (testNeighborView, tstNeighborList.hpp:295-325)
+        double* d = nullptr;
+        cudaMalloc( &d, t.xyz.size() * sizeof( double ) );
+        cudaMemcpy( d, t.xyz.data(), t.xyz.size() * sizeof( double ), cudaMemcpyHostToDevice );
+        Cabana::View2D<double, 3> xv( d, t.num_particle );
+        double c_min[3] = { t.box_min, t.box_min, t.box_min };
+        double c_max[3] = { t.box_max, t.box_max, t.box_max };
+        Cabana::VerletList<Cabana::DeviceSpace, Cabana::FullNeighborTag, LayoutTag> nlist(
+            xv, 0, xv.size(), t.test_radius, t.cell_size_ratio, c_min, c_max );
+        checkFullNeighborList( nlist, t, n2, 0, t.num_particle );
+        cudaFree( d );
+    }
+}
+
+template <class LayoutTag>
+static void testVerletListHalf()
+{
+    TestData t;
+    auto n2 = bruteForce( t );
+    auto x = t.positions();
+    Cabana::VerletList<Cabana::DeviceSpace, Cabana::HalfNeighborTag, LayoutTag> nlist(
+        x, 0, x.size(), t.test_radius, t.cell_size_ratio, t.grid_min, t.grid_max );
+    checkHalfNeighborList( nlist, t, n2 );
+}
+
+template <class LayoutTag>
+static void testNeighborParallelFor()
+{
+    TestData t;
+    auto n2 = bruteForce( t );
+    auto x = t.positions();
+    using ListType = Cabana::VerletList<Cabana::DeviceSpace, Cabana::FullNeighborTag, LayoutTag>;
+    ListType nlist( x, 0, x.size(), t.test_radius, t.cell_size_ratio, t.grid_min, t.grid_max );
+    const std::size_t n = t.num_particle;
+    std::vector<long long> expect( n, 0 );
+    double expect_sum = 0.0;
+    for ( std::size_t i = 0; i < n; ++i )
+        for ( int j : n2[i] )
+        {
+            expect[i] += j;
+            expect_sum += t.xyz[3 * i] + t.xyz[3 * j];
+        }
+    long long* d_res = nullptr;
+    cudaMalloc( &d_res, n * sizeof( long long ) );
+    std::vector<long long> res( n );
+    Cabana::RangePolicy<> policy( 0, n );
+
+    // Serial and Team, untagged functor
+    for ( int team = 0; team < 2; ++team )
+    {
+        cudaMemset( d_res, 0, n * sizeof( long long ) );
+        IdSumFunctor f{ d_res };
+        if ( team )
+            Cabana::neighbor_parallel_for( policy, f, nlist, Cabana::FirstNeighborsTag(),
+                                           Cabana::TeamOpTag(), "test_team" );
+        else
+            Cabana::neighbor_parallel_for( policy, f, nlist, Cabana::FirstNeighborsTag(),
+                                           Cabana::SerialOpTag(), "test_serial" );
+        cudaMemcpy( res.data(), d_res, n * sizeof( long long ), cudaMemcpyDeviceToHost );
+        EXPECT_TRUE( res == expect );
+    }
+    // functor with a work tag: multiplier 2 (neighbor_unit_test.hpp:666-742)
+    {
+        cudaMemset( d_res, 0, n * sizeof( long long ) );
+        TaggedIdSumFunctor f{ d_res };
+        Cabana::RangePolicy<TaggedIdSumFunctor::Tag> tagged( 0, n );
+        Cabana::neighbor_parallel_for( tagged, f, nlist, Cabana::FirstNeighborsTag(),
+                                       Cabana::SerialOpTag() );
+        cudaMemcpy( res.data(), d_res, n * sizeof( long long ), cudaMemcpyDeviceToHost );
+        bool ok = true;
+        for ( std::size_t i = 0; i < n; ++i )
+            ok = ok && res[i] == 2 * expect[i];
+        EXPECT_TRUE( ok );
+    }
+    // neighbor_parallel_reduce (checkFirstNeighborParallelReduce, EXPECT_FLOAT_EQ)
+    for ( int team = 0; team < 2; ++team )
+    {
+        double sum = 0.0;
+        SumPositionsFunctor f{ x };
+        if ( team )
+            Cabana::neighbor_parallel_reduce( policy, f, nlist, Cabana::FirstNeighborsTag(),
+                                              Cabana::TeamOpTag(), sum );
+        else
+            Cabana::neighbor_parallel_reduce( policy, f, nlist, Cabana::FirstNeighborsTag(),
+                                              Cabana::SerialOpTag(), sum );
+        EXPECT_TRUE( std::fabs( sum - expect_sum ) <= 1e-6 * std::fabs( expect_sum ) );
+    }
+    // pre-compiled Lennard-Jones consumer: Serial == Team within 1e-12 of sum |pair force|
+    {
+        double *d_f = nullptr, *d_g = nullptr;
+        cudaMalloc( &d_f, 3 * n * sizeof( double ) );
+        cudaMalloc( &d_g, 3 * n * sizeof( double ) );
+        cudaMemset( d_f, 0, 3 * n * sizeof( double ) );
+        cudaMemset( d_g, 0, 3 * n * sizeof( double ) );
+        Cabana::View2D<double, 3> f( d_f, n ), g( d_g, n );
+        Cabana::B200::neighbor_parallel_for_lj( policy, nlist, x, f, 1.0, 1.0, 2.0,
+                                                Cabana::SerialOpTag() );
+        Cabana::B200::neighbor_parallel_for_lj( policy, nlist, x, g, 1.0, 1.0, 2.0,
+                                                Cabana::TeamOpTag() );
+        std::vector<double> hf( 3 * n ), hg( 3 * n );
+        cudaMemcpy( hf.data(), d_f, 3 * n * sizeof( double ), cudaMemcpyDeviceToHost );
+        cudaMemcpy( hg.data(), d_g, 3 * n * sizeof( double ), cudaMemcpyDeviceToHost );
+        // host reference with the same functor definition
+        bool ok = true;
+        for ( std::size_t i = 0; i < n; ++i )
+        {
+            double fr[3] = { 0, 0, 0 }, fa[3] = { 0, 0, 0 };
+            for ( int j : n2[i] )
+            {
+                double d[3], r2 = 0;
+                for ( int c = 0; c < 3; ++c )
+                {
+                    d[c] = t.xyz[3 * i + c] - t.xyz[3 * j + c];
+                    r2 += d[c] * d[c];
+                }
+                if ( r2 < 4.0 )
+                {
+                    const double sr2 = 1.0 / r2, sr6 = sr2 * sr2 * sr2;
+                    const double fp = 24.0 * sr6 * ( 2.0 * sr6 - 1.0 ) / r2;
+                    for ( int c = 0; c < 3; ++c )
+                    {
+                        fr[c] += fp * d[c];
+                        fa[c] += std::fabs( fp * d[c] );
+                    }
+                }
+            }
+            for ( int c = 0; c < 3; ++c )
+            {
+                ok = ok && std::fabs( hf[3 * i + c] - fr[c] ) <= 1e-12 * std::max( fa[c], 1e-300 );
+                ok = ok && std::fabs( hg[3 * i + c] - fr[c] ) <= 1e-12 * std::max( fa[c], 1e-300 );
+            }
+        }
+        EXPECT_TRUE( ok );
+        const double e_s = Cabana::B200::neighbor_parallel_reduce_lj(
+            policy, nlist, x, 1.0, 1.0, 2.0, Cabana::SerialOpTag() );
+        const double e_t = Cabana::B200::neighbor_parallel_reduce_lj(
+            policy, nlist, x, 1.0, 1.0, 2.0, Cabana::TeamOpTag() );
+        EXPECT_TRUE( std::fabs( e_s - e_t ) <= 1e-11 * std::fabs( e_s ) );
+        cudaFree( d_f );
+        cudaFree( d_g );
+    }
+    // setNeighbor (testModifyNeighbors, tstNeighborList.hpp:256-292)
+    {
+        nlist.setNeighbor( 3, 0, -5 );
+        EXPECT_EQ( Cabana::NeighborList<ListType>::getNeighbor( nlist, 3, 0 ), (std::size_t)-5 );
+    }
+    cudaFree( d_res );
+}
+
+// testLinkedList (tstLinkedCellList.hpp:584-620): one particle per unit cell, created
+// x-fastest; after bin + permute the order is i-slowest / k-fastest.
+static void testLinkedList()
+{
+    const int nx = 10;
+    const std::size_t n = nx * nx * nx;
+    std::vector<double> xyz( 3 * n );
+    std::vector<int> ids( 3 * n );
+    for ( int k = 0; k < nx; ++k )
+        for ( int j = 0; j < nx; ++j )
+            for ( int i = 0; i < nx; ++i )
+            {
+                const std::size_t p = i + j * nx + k * nx * nx;
+                xyz[3 * p + 0] = i + 0.5;
+                xyz[3 * p + 1] = j + 0.5;
+                xyz[3 * p + 2] = k + 0.5;
+                ids[3 * p + 0] = i;
+                ids[3 * p + 1] = j;
+                ids[3 * p + 2] = k;
+            }
+    double* d_x = nullptr;
+    int* d_id = nullptr;
+    cudaMalloc( &d_x, xyz.size() * sizeof( double ) );
+    cudaMalloc( &d_id, ids.size() * sizeof( int ) );
+    cudaMemcpy( d_x, xyz.data(), xyz.size() * sizeof( double ), cudaMemcpyHostToDevice );
+    cudaMemcpy( d_id, ids.data(), ids.size() * sizeof( int ), cudaMemcpyHostToDevice );
+    Cabana::View2D<double, 3> pos( d_x, n );
+    Cabana::View2D<int, 3> cell_id( d_id, n );
+    std::array<double, 3> delta = { 1, 1, 1 }, mn = { 0, 0, 0 }, mx = { 10, 10, 10 };
+    for ( int partial = 0; partial < 2; ++partial )
+    {
+        cudaMemcpy( d_x, xyz.data(), xyz.size() * sizeof( double ), cudaMemcpyHostToDevice );
+        cudaMemcpy( d_id, ids.data(), ids.size() * sizeof( int ), cudaMemcpyHostToDevice );
+        const std::size_t b = partial ? 250 : 0, e = partial ? 750 : n;
+        auto lcl = partial ? Cabana::createLinkedCellList( pos, b, e, delta, mn, mx )
+                           : Cabana::createLinkedCellList( pos, delta, mn, mx );
+        EXPECT_EQ( lcl.totalBins(), 1000 );
+        EXPECT_EQ( lcl.numBin( 0 ), 10 );
+        EXPECT_TRUE( !lcl.sorted() );
+        Cabana::permute( lcl, pos, cell_id );
+        EXPECT_TRUE( lcl.sorted() );
+        auto m = lcl.hostMirror();
+        std::vector<int> hid( 3 * n );
+        cudaMemcpy( hid.data(), d_id, hid.size() * sizeof( int ), cudaMemcpyDeviceToHost );
+        // checkLinkedCell (tstLinkedCellList.hpp:281-365)
+        std::size_t particle_id = 0;
+        bool ok = true;
+        for ( int i = 0; i < nx; ++i )
+            for ( int j = 0; j < nx; ++j )
+                for ( int k = 0; k < nx; ++k )
+                {
+                    const std::size_t original = i + j * nx + k * nx * nx;
+                    const auto c = lcl.cardinalBinIndex( i, j, k );
+                    if ( b <= original && original < e )
+                    {
+                        const std::size_t sort_id = b + particle_id;
+                        ok = ok && hid[3 * sort_id] == i && hid[3 * sort_id + 1] == j &&
+                             hid[3 * sort_id + 2] == k;
+                        ok = ok && m.counts[c] == 1 && m.offsets[c] == particle_id;
+                        ++particle_id;
+                    }
+                    else
+                        ok = ok && m.counts[c] == 0;
+                }
+        for ( std::size_t p = 0; p < n; ++p )
+            if ( p < b || p >= e )
+                ok = ok && hid[3 * p] == (int)( p % nx ) && hid[3 * p + 1] == (int)( ( p / nx ) % nx ) &&
+                     hid[3 * p + 2] == (int)( p / ( nx * nx ) );
+        EXPECT_TRUE( ok );
+        int imin, imax, jmin, jmax, kmin, kmax;
+        lcl.getStencilCells( (int)lcl.cardinalBinIndex( 4, 5, 3 ), imin, imax, jmin, jmax, kmin,
+                             kmax );
+        EXPECT_TRUE( imin == 3 && imax == 6 && jmin == 4 && jmax == 7 && kmin == 2 && kmax == 5 );
+    }
+    cudaFree( d_x );
+    cudaFree( d_id );
+}
+
+int main()
+{
+    if ( cb_device_count() < 1 )
+    {
+        std::printf( "no CUDA device\n" );
+        return 2;
+    }
+    testLinkedList();
+    testVerletListFull<Cabana::VerletLayoutCSR>();
+    testVerletListFull<Cabana::VerletLayout2D>();
+    testVerletListHalf<Cabana::VerletLayoutCSR>();
+    testVerletListHalf<Cabana::VerletLayout2D>();
+    testNeighborParallelFor<Cabana::VerletLayoutCSR>();
+    testNeighborParallelFor<Cabana::VerletLayout2D>();
+    cudaDeviceSynchronize();
+    if ( g_fail == 0 )
+        std::printf( "ALL CABANA API TESTS PASSED\n" );
+    return g_fail == 0 ? 0 : 1;
+}
