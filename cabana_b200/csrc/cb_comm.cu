@@ -271,30 +271,35 @@ extern "C" int cb_comm_count_and_steer( const int32_t* export_ranks, int64_t num
     CB_TRY( s.counts.ensure( sizeof( unsigned long long ) * kMaxRanks ) );
     CB_CUDA( cudaMemsetAsync( s.counts.ptr, 0, sizeof( unsigned long long ) * num_ranks,
                               stream ) );
-    std::string keep;
-    unsigned long long* host_counts = nullptr;
-    CB_CUDA( cudaMallocHost( (void**)&host_counts,
-                             sizeof( unsigned long long ) * num_ranks ) );
+    // pinned scratch of the plan (64 slots) for small rank counts, else a temporary
+    unsigned long long* host_counts =
+        reinterpret_cast<unsigned long long*>( s.pinned.ptr );
+    unsigned long long* big_counts = nullptr;
+    if ( num_ranks > 64 )
+    {
+        CB_CUDA( cudaMallocHost( (void**)&big_counts,
+                                 sizeof( unsigned long long ) * num_ranks ) );
+        host_counts = big_counts;
+    }
     if ( num_export > 0 )
     {
         k_rank_histogram<<<launch_grid_for( num_export, kBlock * 4 ), kBlock,
                            sizeof( unsigned ) * num_ranks, stream>>>(
             export_ranks, num_export, num_ranks, s.counts.as<unsigned long long>() );
-        cudaError_t le = cudaGetLastError();
-        if ( le != cudaSuccess )
-        {
-            cudaFreeHost( host_counts );
-            return cuda_fail( le, "k_rank_histogram", __FILE__, __LINE__ );
-        }
+        note_launch();
     }
-    cudaError_t e1 = cudaMemcpyAsync( host_counts, s.counts.ptr,
-                                      sizeof( unsigned long long ) * num_ranks,
-                                      cudaMemcpyDeviceToHost, stream );
-    cudaError_t e2 = e1 == cudaSuccess ? cudaStreamSynchronize( stream ) : e1;
-    if ( e2 != cudaSuccess )
+    cudaError_t e1 = cudaGetLastError();
+    if ( e1 == cudaSuccess )
+        e1 = cudaMemcpyAsync( host_counts, s.counts.ptr,
+                              sizeof( unsigned long long ) * num_ranks,
+                              cudaMemcpyDeviceToHost, stream );
+    if ( e1 == cudaSuccess )
+        e1 = cudaStreamSynchronize( stream );
+    if ( e1 != cudaSuccess )
     {
-        cudaFreeHost( host_counts );
-        return cuda_fail( e2, "count readback", __FILE__, __LINE__ );
+        if ( big_counts )
+            cudaFreeHost( big_counts );
+        return cuda_fail( e1, "count readback", __FILE__, __LINE__ );
     }
     int64_t run = 0;
     for ( int r = 0; r < num_ranks; ++r )
@@ -304,7 +309,8 @@ extern "C" int cb_comm_count_and_steer( const int32_t* export_ranks, int64_t num
         run += counts_h[r];
     }
     offsets_h[num_ranks] = run;
-    cudaFreeHost( host_counts );
+    if ( big_counts )
+        cudaFreeHost( big_counts );
 
     if ( num_export > 0 && run > 0 )
     {
