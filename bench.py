@@ -235,14 +235,31 @@ def run_ours(args):
         store[:num_local] = xyz
         x_all = cb.slice_from_array(store, vlen=32)
 
+        trace = os.environ.get("CB_BENCH_TRACE") == "1"
+        tr = {"plan": 0.0, "gather": 0.0, "build": 0.0, "n": 0}
+
         def step():
+            t0 = time.perf_counter()
             x_own = cb.Slice(x_all.data, num_local, x_all.outer_stride, x_all.vlen, x_all.comp_stride, 3)
             halo = slab.create_halo(x_own, num_local)
             n_tot = halo.numLocal() + halo.numGhost()
             assert n_tot <= cap, "ghost capacity exceeded"
             x_tot = cb.Slice(x_all.data, n_tot, x_all.outer_stride, x_all.vlen, x_all.comp_stride, 3)
+            if trace:
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
             comm.gather(halo, x_tot)
+            if trace:
+                torch.cuda.synchronize()
+                t2 = time.perf_counter()
             lst.build(x_tot, 0, num_local, RADIUS, CELL_RATIO, lmin, lmax)
+            if trace:
+                torch.cuda.synchronize()
+                t3 = time.perf_counter()
+                tr["plan"] += t1 - t0
+                tr["gather"] += t2 - t1
+                tr["build"] += t3 - t2
+                tr["n"] += 1
             return lst.total
 
     def sync_all():
@@ -350,6 +367,10 @@ def run_ours(args):
                "d2h_bytes_per_step": int(4 * (2 * num_local + lst.total)),
                "api": "cb_verlet_build_host + cb_verlet_copy_to_host (pinned host buffers)"}
 
+    if world > 1 and os.environ.get("CB_BENCH_TRACE") == "1":
+        sys.stderr.write("rank %d trace (ms/step): plan %.3f gather %.3f build %.3f\n" % (
+            rank, 1e3 * tr["plan"] / max(tr["n"], 1), 1e3 * tr["gather"] / max(tr["n"], 1),
+            1e3 * tr["build"] / max(tr["n"], 1)))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -74,6 +74,18 @@ class CudaCommKernels:
             C.c_void_p(ids.data_ptr()), _stream()))
         return ids[: 2 * num_local], ranks[: 2 * num_local]
 
+    def slab_halo_plan(self, x: Slice, num_local, lo_thresh, hi_thresh, lo_rank, hi_rank):
+        """Fused selection + stable compaction (one kernel, one read-back)."""
+        steer = torch.empty(2 * max(num_local, 1), dtype=torch.int32, device="cuda")
+        counts = (C.c_int64 * 2)()
+        d = x.positions_desc()
+        capi.check(capi.lib().cb_slab_halo_plan(
+            C.byref(d), C.c_int64(num_local), C.c_double(lo_thresh), C.c_double(hi_thresh),
+            C.c_int(1 if lo_rank >= 0 else 0), C.c_int(1 if hi_rank >= 0 else 0),
+            C.c_void_p(steer.data_ptr()), C.c_void_p(steer.data_ptr() + 4 * max(num_local, 1)),
+            counts, _stream()))
+        return steer, int(counts[0]), int(counts[1])
+
     def slab_destinations(self, x: Slice, num_local, bounds):
         out = torch.empty(max(num_local, 1), dtype=torch.int32, device="cuda")
         d = x.positions_desc()
@@ -99,12 +111,16 @@ class CommunicationPlan:
     (:626-637; impl/Cabana_Halo_Mpi.hpp:73-101).
     """
 
-    def __init__(self, export_ranks: torch.Tensor, export_ids: torch.Tensor | None = None,
-                 group=None, kernels=None):
+    def __init__(self, export_ranks: torch.Tensor | None, export_ids: torch.Tensor | None = None,
+                 group=None, kernels=None, plan=None):
         self.kernels = kernels if kernels is not None else CudaCommKernels()
         self.group = group
         self.rank, self.world = _world(group)
-        counts, offsets, steering = self.kernels.count_and_steer(export_ranks, export_ids, self.world)
+        if plan is not None:
+            # precomputed (counts per rank, block offsets into steering, steering)
+            counts, offsets, steering = plan
+        else:
+            counts, offsets, steering = self.kernels.count_and_steer(export_ranks, export_ids, self.world)
         # counts exchange: one all_gather of the export-count vector (replaces the
         # per-neighbour MPI_Send of one unsigned long, impl/Cabana_CommunicationPlan_Mpi.hpp:152-178)
         mine = torch.tensor(counts, dtype=torch.int64, device=self.kernels.device)
@@ -178,9 +194,9 @@ class CommunicationPlan:
 class Halo(CommunicationPlan):
     """Cabana::Halo<MemorySpace, Export, Nccl> (core/src/Cabana_Halo.hpp:59-268)."""
 
-    def __init__(self, num_local: int, export_ids: torch.Tensor, export_ranks: torch.Tensor,
-                 group=None, kernels=None):
-        super().__init__(export_ranks, export_ids, group, kernels)
+    def __init__(self, num_local: int, export_ids: torch.Tensor | None,
+                 export_ranks: torch.Tensor | None, group=None, kernels=None, plan=None):
+        super().__init__(export_ranks, export_ids, group, kernels, plan)
         self._num_local = int(num_local)
 
     def numLocal(self):
@@ -288,9 +304,21 @@ class SlabDecomposition:
         return gmin, gmax
 
     def create_halo(self, x: Slice, num_local: int) -> Halo:
-        ids, ranks = self.kernels.slab_halo_select(
-            x, num_local, self.lo + self.halo_width, self.hi - self.halo_width,
-            self.lo_rank, self.hi_rank)
+        lo_t, hi_t = self.lo + self.halo_width, self.hi - self.halo_width
+        if hasattr(self.kernels, "slab_halo_plan"):
+            # fused plan: one kernel + one read-back; same plan as the general path below
+            steer, n_lo, n_hi = self.kernels.slab_halo_plan(x, num_local, lo_t, hi_t,
+                                                            self.lo_rank, self.hi_rank)
+            counts = [0] * self.world
+            offsets = [0] * (self.world + 1)
+            if self.lo_rank >= 0:
+                counts[self.lo_rank] = n_lo
+                offsets[self.lo_rank] = 0
+            if self.hi_rank >= 0:
+                counts[self.hi_rank] = n_hi
+                offsets[self.hi_rank] = max(num_local, 1)
+            return Halo(num_local, None, None, self.group, self.kernels, plan=(counts, offsets, steer))
+        ids, ranks = self.kernels.slab_halo_select(x, num_local, lo_t, hi_t, self.lo_rank, self.hi_rank)
         return Halo(num_local, ids, ranks, self.group, self.kernels)
 
     def create_distributor(self, x: Slice, num_local: int) -> Distributor:

@@ -176,6 +176,145 @@ __global__ void __launch_bounds__( kBlock )
     }
 }
 
+// Fused slab-halo plan: ghost selection + STABLE compaction of the two export lists in one
+// kernel (decoupled look-back over a packed (lo,hi) pair of counters), so a plan costs one
+// launch and one 16-byte read-back instead of ten launches and two syncs.
+constexpr int kHaloThreads = 256;
+constexpr int kHaloItems = 4;
+constexpr int kHaloTile = kHaloThreads * kHaloItems;
+
+using ull = unsigned long long;
+CB_D ull halo_pack( unsigned flag, unsigned lo, unsigned hi )
+{
+    return ( (ull)flag << 62 ) | ( (ull)hi << 31 ) | (ull)lo;
+}
+
+__global__ void __launch_bounds__( kHaloThreads )
+    k_halo_compact( PosAccess x, long long n, double lo_thresh, double hi_thresh, int has_lo,
+                    int has_hi, unsigned* __restrict__ steer_lo,
+                    unsigned* __restrict__ steer_hi, ull* status, unsigned* tile_counter,
+                    unsigned num_tiles, long long* totals )
+{
+    __shared__ unsigned s_tile;
+    __shared__ ull s_warp[kHaloThreads / 32];
+    __shared__ ull s_prefix;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if ( t == 0 )
+        s_tile = atomicAdd( tile_counter, 1u );
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const long long base = (long long)tile * kHaloTile + (long long)t * kHaloItems;
+    bool flo[kHaloItems], fhi[kHaloItems];
+    unsigned clo = 0, chi = 0;
+#pragma unroll
+    for ( int e = 0; e < kHaloItems; ++e )
+    {
+        flo[e] = false;
+        fhi[e] = false;
+        if ( base + e < n )
+        {
+            const double px = x.base[x.offset( base + e )];
+            flo[e] = has_lo && px < lo_thresh;
+            fhi[e] = has_hi && px >= hi_thresh;
+        }
+        clo += flo[e] ? 1u : 0u;
+        chi += fhi[e] ? 1u : 0u;
+    }
+    // packed sums: lo in bits 0..30, hi in bits 31..61 (n < 2^31)
+    const ull mine = (ull)clo | ( (ull)chi << 31 );
+    ull incl = mine;
+#pragma unroll
+    for ( int o = 1; o < 32; o <<= 1 )
+    {
+        const ull y = __shfl_up_sync( kFullMask, incl, o );
+        if ( lane >= o )
+            incl += y;
+    }
+    if ( lane == 31 )
+        s_warp[warp] = incl;
+    __syncthreads();
+    if ( warp == 0 )
+    {
+        const ull w = lane < kHaloThreads / 32 ? s_warp[lane] : 0ull;
+        ull wi = w;
+#pragma unroll
+        for ( int o = 1; o < 32; o <<= 1 )
+        {
+            const ull y = __shfl_up_sync( kFullMask, wi, o );
+            if ( lane >= o )
+                wi += y;
+        }
+        if ( lane < kHaloThreads / 32 )
+            s_warp[lane] = wi - w;
+        const ull agg = __shfl_sync( kFullMask, wi, 31 );
+        const ull vmask = ( 1ull << 62 ) - 1ull;
+        ull prefix = 0ull;
+        if ( tile == 0 )
+        {
+            if ( lane == 0 )
+                *reinterpret_cast<volatile ull*>( &status[0] ) = ( 2ull << 62 ) | agg;
+        }
+        else
+        {
+            if ( lane == 0 )
+                *reinterpret_cast<volatile ull*>( &status[tile] ) = ( 1ull << 62 ) | agg;
+            long long idx = (long long)tile - 1 - lane;
+            ull running = 0ull;
+            while ( true )
+            {
+                ull sv;
+                do
+                {
+                    sv = idx >= 0 ? *reinterpret_cast<const volatile ull*>( &status[idx] )
+                                  : ( 2ull << 62 );
+                } while ( __any_sync( kFullMask, ( sv >> 62 ) == 0ull ) );
+                const unsigned flag = (unsigned)( sv >> 62 );
+                const ull val = sv & vmask;
+                const unsigned incl_mask = __ballot_sync( kFullMask, flag == 2u );
+                ull contrib = val;
+                if ( incl_mask )
+                {
+                    const int first = __ffs( incl_mask ) - 1;
+                    contrib = lane <= first ? val : 0ull;
+                }
+#pragma unroll
+                for ( int o = 16; o > 0; o >>= 1 )
+                    contrib += __shfl_xor_sync( kFullMask, contrib, o );
+                running += contrib;
+                if ( incl_mask )
+                    break;
+                idx -= 32;
+            }
+            prefix = running;
+            if ( lane == 0 )
+                *reinterpret_cast<volatile ull*>( &status[tile] ) =
+                    ( 2ull << 62 ) | ( prefix + agg );
+        }
+        if ( lane == 0 )
+        {
+            s_prefix = prefix;
+            if ( tile == num_tiles - 1 )
+            {
+                const ull tot = prefix + agg;
+                totals[0] = (long long)( tot & 0x7fffffffull );
+                totals[1] = (long long)( ( tot >> 31 ) & 0x7fffffffull );
+            }
+        }
+    }
+    __syncthreads();
+    const ull excl = s_prefix + s_warp[warp] + ( incl - mine );
+    unsigned plo = (unsigned)( excl & 0x7fffffffull );
+    unsigned phi = (unsigned)( ( excl >> 31 ) & 0x7fffffffull );
+#pragma unroll
+    for ( int e = 0; e < kHaloItems; ++e )
+    {
+        if ( flo[e] )
+            steer_lo[plo++] = (unsigned)( base + e );
+        if ( fhi[e] )
+            steer_hi[phi++] = (unsigned)( base + e );
+    }
+}
+
 int make_field_set( const cb_field* fields, int num_fields, FieldSet& fs )
 {
     if ( !fields || num_fields < 1 || num_fields > kMaxFields )
@@ -393,5 +532,37 @@ extern "C" int cb_comm_scatter_add( const cb_field* field, const uint32_t* steer
                     (cudaStream_t)stream_>>>( make_access( *field ), steering, count,
                                               (const double*)recv_buffer );
     CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
+extern "C" int cb_slab_halo_plan( const cb_positions* x, int64_t num_local, double lo_thresh,
+                                  double hi_thresh, int has_lo, int has_hi, uint32_t* steer_lo,
+                                  uint32_t* steer_hi, int64_t* counts_h, cb_stream_t stream_ )
+{
+    if ( !x || !steer_lo || !steer_hi || !counts_h || num_local < 0 || num_local > x->n ||
+         x->vlen < 1 || num_local >= 2147483647ll )
+        return fail( CB_ERR_INVALID, "cb_slab_halo_plan: bad argument" );
+    counts_h[0] = counts_h[1] = 0;
+    if ( num_local == 0 )
+        return CB_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CommScratch& s = scratch();
+    CB_TRY( s.pinned.ensure() );
+    const long long num_tiles = ( num_local + kHaloTile - 1 ) / kHaloTile;
+    const size_t bytes = 32 + (size_t)num_tiles * sizeof( unsigned long long );
+    CB_TRY( s.scan.ensure( bytes, 1.25 ) );
+    CB_CUDA( cudaMemsetAsync( s.scan.ptr, 0, bytes, stream ) );
+    unsigned* counter = s.scan.as<unsigned>();
+    long long* totals = reinterpret_cast<long long*>( s.scan.as<char>() + 16 );
+    unsigned long long* status = reinterpret_cast<unsigned long long*>( s.scan.as<char>() + 32 );
+    k_halo_compact<<<(unsigned)num_tiles, kHaloThreads, 0, stream>>>(
+        make_access( *x ), num_local, lo_thresh, hi_thresh, has_lo, has_hi, steer_lo, steer_hi,
+        status, counter, (unsigned)num_tiles, totals );
+    CB_CHECK_LAUNCH();
+    CB_CUDA( cudaMemcpyAsync( s.pinned.ptr, totals, 2 * sizeof( long long ),
+                              cudaMemcpyDeviceToHost, stream ) );
+    CB_CUDA( cudaStreamSynchronize( stream ) );
+    counts_h[0] = s.pinned.ptr[0];
+    counts_h[1] = s.pinned.ptr[1];
     return CB_OK;
 }

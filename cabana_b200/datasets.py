@@ -84,6 +84,10 @@ def clustered(n: int, seed: int = 20240104, radius: float = 3.0, cell_ratio: flo
     which = rng.integers(0, n_blobs, n_bl)
     bl = centres[which] + rng.normal(0.0, s, (n_bl, 3))
     xyz = np.concatenate([bg, bl], axis=0)
+    # reflect stragglers back into the box (clipping would stack them on the faces and
+    # create coincident points, which half lists drop -- SURVEY.md Appendix B.4)
+    xyz = np.abs(xyz)
+    xyz = hi - np.abs(hi - xyz)
     np.clip(xyz, 0.0, np.nextafter(hi, 0.0), out=xyz)
     xyz = xyz[rng.permutation(n)]
     return ParticleSet(f"clustered_{n}", np.ascontiguousarray(xyz), (0.0,) * 3, (hi,) * 3, radius, cell_ratio)

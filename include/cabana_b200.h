@@ -306,6 +306,13 @@ int cb_slab_halo_select(const cb_positions* x, int64_t num_local, double lo_thre
                         double hi_thresh, int lo_rank, int hi_rank,
                         int32_t* export_ranks /* [2*num_local] */,
                         uint32_t* export_ids /* [2*num_local] */, cb_stream_t stream);
+/* Fused slab-halo plan: selection + stable compaction in ONE kernel.  On return
+ * (synchronises once) counts_h[0] / counts_h[1] = exports to the lower / upper neighbour and
+ * steer_lo[0..counts_h[0]) / steer_hi[0..counts_h[1]) = their particle ids in ascending order
+ * -- the same plan cb_slab_halo_select + cb_comm_count_and_steer produce. */
+int cb_slab_halo_plan(const cb_positions* x, int64_t num_local, double lo_thresh,
+                      double hi_thresh, int has_lo, int has_hi, uint32_t* steer_lo,
+                      uint32_t* steer_hi, int64_t* counts_h, cb_stream_t stream);
 /* Migration destination = slab g with bounds_h[g] <= x < bounds_h[g+1] (the last slab
  * owns its upper face); -1 (dropped, impl/Cabana_CommunicationPlan_Mpi.hpp:98-103)
  * outside [bounds_h[0], bounds_h[num_ranks]].  num_ranks <= 64. */

@@ -110,6 +110,23 @@ def test_slab_select_and_destinations(mods):
     assert np.array_equal(dest, exp)
 
 
+def test_fused_halo_plan_equals_general_plan(mods):
+    cb, comm = mods
+    k = comm.CudaCommKernels()
+    rng = np.random.default_rng(6)
+    for n in (1, 1000, 1025, 300_000):
+        x = rng.random((n, 3)) * np.array([10.0, 3.0, 3.0]) + np.array([20.0, 0, 0])
+        for fx in (cb.slice_from_array(x, vlen=32), cb.view_from_array(x)):
+            for lo_rank, hi_rank in ((0, 2), (-1, 2), (0, -1)):
+                steer, n_lo, n_hi = k.slab_halo_plan(fx, n, 21.5, 28.5, lo_rank, hi_rank)
+                steer = steer.cpu().numpy()
+                exp_lo = np.nonzero(x[:, 0] < 21.5)[0] if lo_rank >= 0 else np.zeros(0, dtype=int)
+                exp_hi = np.nonzero(x[:, 0] >= 28.5)[0] if hi_rank >= 0 else np.zeros(0, dtype=int)
+                assert (n_lo, n_hi) == (len(exp_lo), len(exp_hi))
+                assert np.array_equal(steer[:n_lo], exp_lo)
+                assert np.array_equal(steer[max(n, 1):max(n, 1) + n_hi], exp_hi)
+
+
 # ------------------------------------------------------------------------------------ 2 GPUs
 def _free_port():
     s = socket.socket()
