@@ -354,6 +354,28 @@ def neighbor_parallel_reduce_lj(begin, end, lst: VerletList, x: Slice, eps, sigm
     return out.value
 
 
+def lcl_neighbor_parallel_for_lj(begin, end, lcl: LinkedCellList, x: Slice, f: Slice, eps, sigma, rc,
+                                 op_tag=OP_SERIAL):
+    """neighbor_parallel_for(policy, LJ functor, linked_cell_list, FirstNeighborsTag, op_tag):
+    list-free traversal (core/src/Cabana_Parallel.hpp:1511-1595)."""
+    d = x.positions_desc()
+    fd = f.field_desc()
+    capi.check(capi.lib().cb_lcl_neighbor_for_lj(
+        lcl._h, C.byref(d), C.byref(fd), C.c_double(eps), C.c_double(sigma), C.c_double(rc),
+        C.c_int(op_tag), C.c_int64(begin), C.c_int64(end), _stream()))
+
+
+def lcl_neighbor_parallel_for_count(begin, end, lcl: LinkedCellList, x: Slice, cutoff,
+                                    result: torch.Tensor, op_tag=OP_SERIAL):
+    """The functor of checkLinkedCellNeighborInterface (tstLinkedCellList.hpp:704-780):
+    result[i] += 1 for every stencil candidate j != i with r2 <= cutoff^2."""
+    assert result.dtype == torch.int32 and result.is_cuda
+    d = x.positions_desc()
+    capi.check(capi.lib().cb_lcl_neighbor_for_count(
+        lcl._h, C.byref(d), C.c_double(cutoff), C.c_void_p(result.data_ptr()), C.c_int(op_tag),
+        C.c_int64(begin), C.c_int64(end), _stream()))
+
+
 def neighbor_parallel_for_id_sum(begin, end, lst: VerletList, result: torch.Tensor, op_tag=OP_SERIAL):
     """The reference unit tests' functor: result[i] += j (neighbor_unit_test.hpp:291-348)."""
     assert result.dtype == torch.int64 and result.is_cuda

@@ -142,3 +142,16 @@ int bin_particles( const cb_grid& grid, const cb_positions& x, long long begin,
 int launch_grid_for( long long work_items, int block );
 
 } // namespace cb
+
+// The LinkedCellList handle (shared by cb_lcl.cu and the LCL-direct traversal).
+struct cb_lcl
+{
+    cb_grid grid;
+    cb_grid stencil_grid;
+    int cell_range = 1;
+    int sorted = 0;
+    long long begin = 0, end = 0;
+    long long num_cells = 0;
+    cb::DeviceBuffer counts, offsets, permute, bins, bins_alt, rank, scan, field_scratch;
+    bool built = false;
+};

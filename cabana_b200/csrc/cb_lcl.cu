@@ -171,18 +171,6 @@ int bin_particles( const cb_grid& grid, const cb_positions& x, long long begin,
 // =====================================================================================
 using namespace cb;
 
-struct cb_lcl
-{
-    cb_grid grid;
-    cb_grid stencil_grid;
-    int cell_range = 1;
-    int sorted = 0;
-    long long begin = 0, end = 0;
-    long long num_cells = 0;
-    DeviceBuffer counts, offsets, permute, bins, bins_alt, rank, scan, field_scratch;
-    bool built = false;
-};
-
 extern "C" int cb_lcl_create( cb_lcl** out, const double* delta_h, const double* min_h,
                               const double* max_h, double neighborhood_radius,
                               double cell_size_ratio )

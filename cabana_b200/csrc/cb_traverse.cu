@@ -283,6 +283,142 @@ __global__ void __launch_bounds__( kBlock )
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// neighbor_parallel_for directly on a LinkedCellList (LinkedCellParallelFor,
+// core/src/Cabana_Parallel.hpp:1122-1290).  Serial: one thread per particle walks the
+// stencil cells serially (:1156-1207); Team: one warp per particle, lanes stride the
+// particles of each cell (:1209-1268).
+// ---------------------------------------------------------------------------------------
+struct LclAccess
+{
+    Grid grid;         // _grid: binOffset / binSize indexing
+    int snx[3];        // _cell_stencil.grid._nx: decode + clip (Cabana_LinkedCellList.hpp:105-119)
+    int cell_range;
+    int sorted;
+    long long begin;
+    const int* counts;
+    const unsigned* offsets;
+    const unsigned* permute;
+    const int* bins;
+};
+
+template <bool TEAM, int MODE> // MODE 0: count within cutoff, 1: Lennard-Jones force
+__global__ void __launch_bounds__( kBlock )
+    k_lcl_for( LclAccess l, PosAccess x, FieldAccess f, LJ p, double c2, int* result,
+               long long begin, long long end )
+{
+    const unsigned lane = lane_id();
+    long long first, stride;
+    if ( TEAM )
+    {
+        first = begin + ( ( (long long)blockIdx.x * kBlock + threadIdx.x ) >> 5 );
+        stride = ( (long long)gridDim.x * kBlock ) >> 5;
+    }
+    else
+    {
+        first = begin + (long long)blockIdx.x * kBlock + threadIdx.x;
+        stride = (long long)gridDim.x * kBlock;
+    }
+    for ( long long i = first; i < end; i += stride )
+    {
+        const int cell = l.bins[i - l.begin];
+        // getStencilCells: ijk decoded on the stencil grid, +-cell_range, clipped
+        const int ci = cell / ( l.snx[1] * l.snx[2] );
+        const int cj = ( cell / l.snx[2] ) % l.snx[1];
+        const int ck = cell % l.snx[2];
+        const int imin = max( ci - l.cell_range, 0 ), imax = min( ci + l.cell_range + 1, l.snx[0] );
+        const int jmin = max( cj - l.cell_range, 0 ), jmax = min( cj + l.cell_range + 1, l.snx[1] );
+        const int kmin = max( ck - l.cell_range, 0 ), kmax = min( ck + l.cell_range + 1, l.snx[2] );
+        const long long xo = x.offset( i );
+        const double xi = x.base[xo], yi = x.base[xo + x.comp_stride],
+                     zi = x.base[xo + 2 * x.comp_stride];
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        int cnt = 0;
+        for ( int gi = imin; gi < imax; ++gi )
+            for ( int gj = jmin; gj < jmax; ++gj )
+            {
+                // cells (gi,gj,kmin..kmax-1) are consecutive in the binned order
+                const int c0 = cardinal_index( l.grid, gi, gj, kmin );
+                const unsigned n0 = l.offsets[c0];
+                const unsigned n1 = l.offsets[c0 + ( kmax - kmin )];
+                for ( unsigned n = n0 + ( TEAM ? lane : 0u ); n < n1; n += ( TEAM ? 32u : 1u ) )
+                {
+                    // getParticle (:863-872)
+                    const long long j = l.sorted ? (long long)n + l.begin : (long long)l.permute[n];
+                    if ( j == i )
+                        continue; // NeighborDiscriminator<SelfNeighborTag>
+                    const long long jo = x.offset( j );
+                    const double dx = xi - x.base[jo], dy = yi - x.base[jo + x.comp_stride],
+                                 dz = zi - x.base[jo + 2 * x.comp_stride];
+                    if ( MODE == 0 )
+                    {
+                        // un-contracted, like the functor of the reference test
+                        const double r2 = CB_ADD( CB_ADD( CB_MUL( dx, dx ), CB_MUL( dy, dy ) ),
+                                                  CB_MUL( dz, dz ) );
+                        cnt += r2 <= c2 ? 1 : 0;
+                    }
+                    else
+                    {
+                        double fx, fy, fz;
+                        bool within;
+                        lj_pair( p, dx, dy, dz, fx, fy, fz, within );
+                        if ( within )
+                        {
+                            ax += fx;
+                            ay += fy;
+                            az += fz;
+                        }
+                    }
+                }
+            }
+        if ( MODE == 0 )
+        {
+            if ( TEAM )
+                cnt = warp_reduce_sum( cnt );
+            if ( !TEAM || lane == 0 )
+                result[i] += cnt;
+        }
+        else
+        {
+            if ( TEAM )
+            {
+                ax = warp_reduce_sum( ax );
+                ay = warp_reduce_sum( ay );
+                az = warp_reduce_sum( az );
+            }
+            if ( !TEAM || lane == 0 )
+                add3( reinterpret_cast<double*>( f.base ), f.offset( i ), f.comp_stride, ax, ay,
+                      az, false );
+        }
+    }
+}
+
+int lcl_access( const cb_lcl* lcl, LclAccess& l )
+{
+    if ( !lcl || !lcl->built )
+        return fail( CB_ERR_INVALID, "LinkedCellList not built" );
+    // the offsets array is indexed with _grid cardinals over runs of kmax-kmin cells: the
+    // stencil grid and the binning grid must have the same shape for that (they do for
+    // every constructor that passes delta = radius*ratio, e.g. VerletList's and the
+    // benchmark's; the reference would mis-index otherwise as well)
+    for ( int d = 0; d < 3; ++d )
+        if ( lcl->grid.nx[d] != lcl->stencil_grid.nx[d] )
+            return fail( CB_ERR_UNSUPPORTED,
+                         "LCL traversal: stencil grid and binning grid differ in shape" );
+    l.grid = to_grid( lcl->grid );
+    for ( int d = 0; d < 3; ++d )
+        l.snx[d] = lcl->stencil_grid.nx[d];
+    l.cell_range = lcl->cell_range;
+    l.sorted = lcl->sorted;
+    l.begin = lcl->begin;
+    l.counts = lcl->counts.as<int>();
+    l.offsets = lcl->offsets.as<unsigned>();
+    l.permute = lcl->permute.as<unsigned>();
+    l.bins = lcl->bins.as<int>();
+    return CB_OK;
+}
+
 int check_list( const cb_verlet_view* v, int64_t begin, int64_t end, const char* who )
 {
     if ( !v || !v->counts || ( v->total > 0 && !v->neighbors ) )
@@ -410,6 +546,65 @@ extern "C" int cb_neighbor_for_id_sum( const cb_verlet_view* list, int64_t* resu
     else
         k_id_sum<true><<<team_grid( items ), kBlock, 0, stream>>>(
             make_list( *list ), begin, end, reinterpret_cast<long long*>( result ) );
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
+extern "C" int cb_lcl_neighbor_for_lj( const cb_lcl* lcl, const cb_positions* x,
+                                       const cb_field* f, double eps, double sigma, double rc,
+                                       int op, int64_t begin, int64_t end, cb_stream_t stream_ )
+{
+    LclAccess l;
+    CB_TRY( lcl_access( lcl, l ) );
+    if ( !x || !f || x->vlen < 1 || f->vlen < 1 || f->elem_bytes != 8 || f->num_comp != 3 )
+        return fail( CB_ERR_INVALID, "cb_lcl_neighbor_for_lj: bad argument" );
+    if ( begin < lcl->begin || end > lcl->end || end < begin || x->n < lcl->end || f->n < end )
+        return fail( CB_ERR_INVALID, "cb_lcl_neighbor_for_lj: range outside the binned range" );
+    if ( op != CB_OP_SERIAL && op != CB_OP_TEAM )
+        return fail( CB_ERR_INVALID, "cb_lcl_neighbor_for_lj: op must be Serial or Team" );
+    if ( end == begin )
+        return CB_OK;
+    LJ p;
+    p.rc2 = rc * rc;
+    p.s2 = sigma * sigma;
+    p.eps24 = 24.0 * eps;
+    p.eps4 = 4.0 * eps;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long items = end - begin;
+    if ( op == CB_OP_SERIAL )
+        k_lcl_for<false, 1><<<launch_grid_for( items, kBlock ), kBlock, 0, stream>>>(
+            l, make_access( *x ), make_access( *f ), p, 0.0, nullptr, begin, end );
+    else
+        k_lcl_for<true, 1><<<team_grid( items ), kBlock, 0, stream>>>(
+            l, make_access( *x ), make_access( *f ), p, 0.0, nullptr, begin, end );
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
+extern "C" int cb_lcl_neighbor_for_count( const cb_lcl* lcl, const cb_positions* x,
+                                          double cutoff, int32_t* result, int op,
+                                          int64_t begin, int64_t end, cb_stream_t stream_ )
+{
+    LclAccess l;
+    CB_TRY( lcl_access( lcl, l ) );
+    if ( !x || !result || x->vlen < 1 )
+        return fail( CB_ERR_INVALID, "cb_lcl_neighbor_for_count: bad argument" );
+    if ( begin < lcl->begin || end > lcl->end || end < begin || x->n < lcl->end )
+        return fail( CB_ERR_INVALID, "cb_lcl_neighbor_for_count: range outside the binned range" );
+    if ( op != CB_OP_SERIAL && op != CB_OP_TEAM )
+        return fail( CB_ERR_INVALID, "cb_lcl_neighbor_for_count: op must be Serial or Team" );
+    if ( end == begin )
+        return CB_OK;
+    LJ p = {};
+    FieldAccess fa = {};
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long items = end - begin;
+    if ( op == CB_OP_SERIAL )
+        k_lcl_for<false, 0><<<launch_grid_for( items, kBlock ), kBlock, 0, stream>>>(
+            l, make_access( *x ), fa, p, cutoff * cutoff, result, begin, end );
+    else
+        k_lcl_for<true, 0><<<team_grid( items ), kBlock, 0, stream>>>(
+            l, make_access( *x ), fa, p, cutoff * cutoff, result, begin, end );
     CB_CHECK_LAUNCH();
     return CB_OK;
 }

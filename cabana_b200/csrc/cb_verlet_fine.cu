@@ -321,6 +321,7 @@ __global__ void __launch_bounds__( kColBlock, 3 )
     __shared__ int s_id[kColWarps][kIdBuf];
     __shared__ int s_layer[kColWarps][kMaxLayers + 1];
     __shared__ int s_home[kColWarps][kMaxLayers];
+    __shared__ unsigned s_hoff[kColWarps][kMaxLayers + 1];
     const unsigned lane = threadIdx.x & 31u;
     const int wib = threadIdx.x >> 5;
     unsigned* list = s_list[wib];
@@ -328,6 +329,7 @@ __global__ void __launch_bounds__( kColBlock, 3 )
     int* idbuf = s_id[wib];
     int* layer = s_layer[wib];
     int* homepos = s_home[wib];
+    unsigned* homeoff = s_hoff[wib];
     Reservation rs;
     const int nxf = a.nf[0], nyf = a.nf[1], nzf = a.nf[2];
     const int lgm = a.lgm, R = a.R;
@@ -441,7 +443,14 @@ __global__ void __launch_bounds__( kColBlock, 3 )
                 if ( lane == 0 )
                     layer[k - kL0] = base;
                 if ( (int)lane == ( r_home & 31 ) )
-                    homepos[k - kL0] = base + ( r_home < 32 ? incl0 - len[0] : excl1 );
+                {
+                    // the home row's own cell offsets: the home loop below needs no
+                    // dependent global load to find its particles
+                    const int hh = r_home < 32 ? 0 : 1;
+                    homepos[k - kL0] = base + ( hh == 0 ? incl0 - len[0] : excl1 );
+                    homeoff[k - kL0] = st[hh];
+                    homeoff[k - kL0 + 1] = st[hh] + (unsigned)len[hh];
+                }
                 base += tot;
                 ++nbuilt;
             }
@@ -452,8 +461,17 @@ __global__ void __launch_bounds__( kColBlock, 3 )
 
         for ( int cc = cz0; cc < cz1; ++cc )
         {
-            const unsigned h0 = a.cell_off[homebase + cc];
-            const unsigned h1 = a.cell_off[homebase + cc + 1];
+            unsigned h0, h1;
+            if ( cc - kL0 < nbuilt )
+            {
+                h0 = homeoff[cc - kL0];
+                h1 = homeoff[cc - kL0 + 1];
+            }
+            else
+            {
+                h0 = a.cell_off[homebase + cc];
+                h1 = a.cell_off[homebase + cc + 1];
+            }
             if ( h1 == h0 )
                 continue;
             // candidate layers of this home cell: +-Kz, inside the reference stencil

@@ -287,6 +287,21 @@ int cb_neighbor_reduce_lj(const cb_verlet_view* list_h, const cb_positions* x,
 int cb_neighbor_for_id_sum(const cb_verlet_view* list_h, int64_t* result, int op,
                            int64_t begin, int64_t end, cb_stream_t stream);
 
+/* neighbor_parallel_for directly on a LinkedCellList, no stored list:
+ * LinkedCellParallelFor (core/src/Cabana_Parallel.hpp:1122-1290, :1511-1595) through
+ * NeighborList<LinkedCellList> (core/src/Cabana_LinkedCellList.hpp:1149-1303): for i in
+ * [begin,end) every particle j != i of the stencil cells of i's bin is handed to the functor,
+ * which applies its own cutoff.  x must be in the order the list currently describes
+ * (permuted if cb_lcl_permute was called).  op = CB_OP_SERIAL | CB_OP_TEAM.
+ *   cb_lcl_neighbor_for_lj:    f_i += LJ pair force for r2 < rc^2
+ *   cb_lcl_neighbor_for_count: result[i] += 1 for r2 <= cutoff^2 (tstLinkedCellList.hpp:704-780) */
+int cb_lcl_neighbor_for_lj(const cb_lcl* lcl, const cb_positions* x, const cb_field* f,
+                           double eps, double sigma, double rc, int op, int64_t begin,
+                           int64_t end, cb_stream_t stream);
+int cb_lcl_neighbor_for_count(const cb_lcl* lcl, const cb_positions* x, double cutoff,
+                              int32_t* result, int op, int64_t begin, int64_t end,
+                              cb_stream_t stream);
+
 /* -----------------------------------------------------------------------------
  * Slab Halo / Distributor kernels  (core/src/Cabana_CommunicationPlanBase.hpp:96-224
  * countSendsAndCreateSteering, :596-657 createExportSteering;

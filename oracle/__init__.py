@@ -415,6 +415,27 @@ def neighbor_id_sum(layout, counts, offsets, neighbors, width, begin, end):
     return out
 
 
+def lcl_neighbor_for(x: PositionsView, res: LinkedCellResult, stencil: Stencil, sorted_, lcl_begin,
+                     pbegin, pend, mode, cutoff, eps=1.0, sigma=1.0):
+    """LinkedCellParallelFor with the count (mode 0) or LJ (mode 1) functor."""
+    n = x.n
+    counts_out = np.zeros(n, dtype=np.int32)
+    f = np.zeros((n, 3), dtype=np.float64)
+    fabs = np.zeros((n, 3), dtype=np.float64)
+    d = x.desc()
+    offsets = np.ascontiguousarray(res.offsets, dtype=np.int64)
+    permute = np.ascontiguousarray(res.permute, dtype=np.int64)
+    lib().orc_lcl_neighbor_for(
+        C.byref(d), C.byref(res.grid.c), C.byref(stencil.c),
+        res.counts.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p),
+        permute.ctypes.data_as(C.c_void_p), res.particle_bins.ctypes.data_as(C.c_void_p),
+        C.c_int(1 if sorted_ else 0), C.c_int64(lcl_begin), C.c_int64(pbegin), C.c_int64(pend),
+        C.c_int(mode), C.c_double(cutoff), C.c_double(eps), C.c_double(sigma),
+        counts_out.ctypes.data_as(C.c_void_p), f.ctypes.data_as(C.c_void_p),
+        fabs.ctypes.data_as(C.c_void_p))
+    return counts_out, f, fabs
+
+
 def num_threads() -> int:
     return lib().orc_num_threads()
 

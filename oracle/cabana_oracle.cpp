@@ -675,6 +675,71 @@ void orc_neighbor_id_sum( int layout, const int* counts, const int* offsets,
     }
 }
 
+
+// -----------------------------------------------------------------------------
+// neighbor_parallel_for directly on a LinkedCellList (no stored list):
+// LinkedCellParallelFor (core/src/Cabana_Parallel.hpp:1122-1290) with
+// NeighborList<LinkedCellList>::getStencilCells / getParticle semantics
+// (core/src/Cabana_LinkedCellList.hpp:840-872): for particle i in [pbegin,pend), walk the
+// stencil cells of its bin (decoded on the STENCIL grid, :105-119), candidates
+// j = sorted ? offset + lcl_begin : permute[offset]; the functor runs for j != i
+// (NeighborDiscriminator<SelfNeighborTag>, Cabana_NeighborList.hpp:68-83) and applies its
+// own cutoff.
+//   mode 0: result_count[i] += 1 for r2 <= cutoff^2   (tstLinkedCellList.hpp:704-780)
+//   mode 1: Lennard-Jones force on i (r2 < cutoff^2), f[3*i+c] accumulated
+// -----------------------------------------------------------------------------
+void orc_lcl_neighbor_for( const orc_positions* x, const orc_grid* grid,
+                           const orc_stencil* stencil, const int* counts,
+                           const int64_t* offsets, const int64_t* permute,
+                           const int* particle_bins, int sorted, int64_t lcl_begin,
+                           int64_t pbegin, int64_t pend, int mode, double cutoff,
+                           double eps, double sigma, int* result_count, double* f,
+                           double* fabs_out )
+{
+    const double c2 = cutoff * cutoff;
+    const double s2 = sigma * sigma;
+#pragma omp parallel for schedule( dynamic, 64 )
+    for ( int64_t i = pbegin; i < pend; ++i )
+    {
+        int mn[3], mx[3];
+        orc_stencil_cells( stencil, particle_bins[i - lcl_begin], mn, mx );
+        const double xi[3] = { pos_at( x, i, 0 ), pos_at( x, i, 1 ), pos_at( x, i, 2 ) };
+        for ( int gi = mn[0]; gi < mx[0]; ++gi )
+            for ( int gj = mn[1]; gj < mx[1]; ++gj )
+                for ( int gk = mn[2]; gk < mx[2]; ++gk )
+                {
+                    const int c = cardinal( grid, gi, gj, gk );
+                    for ( int64_t n = offsets[c]; n < offsets[c] + counts[c]; ++n )
+                    {
+                        const int64_t j = sorted ? n + lcl_begin : permute[n];
+                        if ( i == j )
+                            continue;
+                        const double d[3] = { xi[0] - pos_at( x, j, 0 ),
+                                              xi[1] - pos_at( x, j, 1 ),
+                                              xi[2] - pos_at( x, j, 2 ) };
+                        const double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                        if ( mode == 0 )
+                        {
+                            if ( r2 <= c2 )
+                                result_count[i] += 1;
+                        }
+                        else if ( r2 < c2 )
+                        {
+                            const double sr2 = s2 / r2;
+                            const double sr6 = sr2 * sr2 * sr2;
+                            const double fpair = 24.0 * eps * sr6 * ( 2.0 * sr6 - 1.0 ) / r2;
+                            for ( int k = 0; k < 3; ++k )
+                            {
+                                f[3 * i + k] += fpair * d[k];
+                                if ( fabs_out )
+                                    fabs_out[3 * i + k] += std::fabs( fpair * d[k] );
+                            }
+                        }
+                    }
+                }
+    }
+}
+
 int orc_num_threads( void )
 {
 #ifdef _OPENMP
