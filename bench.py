@@ -49,7 +49,8 @@ def _workload_config(n_gpus):
     return {
         "workload": "cfg3: 16 078 716-atom FCC LJ (rho*=0.8442), r = 2.8 sigma, cell_size_ratio 1.0, "
                     "FullNeighborTag, VerletLayoutCSR" + ("" if n_gpus == 1 else
-                    f", x-slab decomposition over {n_gpus} GPUs with Halo ghost gather each step"),
+                    f", x-slab decomposition over {n_gpus} GPUs with Halo ghost gather each step "
+                    f"({os.environ.get('CB_BENCH_HALO', 'peer')} halo)"),
         "particles": 4 * FCC_CELLS**3,
         "radius": RADIUS,
         "cell_size_ratio": CELL_RATIO,
@@ -211,18 +212,31 @@ def run_ours(args):
     import ctypes as C
 
     L = capi.lib()
-    xyz, bounds, gmax = _fcc_slab(rank, world)
+    algo, layout, radius = cb.FULL, cb.CSR, RADIUS
+    if args.workload == "cfg3":
+        xyz, bounds, gmax = _fcc_slab(rank, world)
+    else:
+        assert world == 1, "only cfg3 is sharded"
+        from cabana_b200 import datasets
+        if args.workload == "cfg1":
+            ps = datasets.uniform_box(100_000, 20240101)
+        elif args.workload == "cfg2":
+            ps = datasets.uniform_box(1_000_000, 20240102)
+            algo, layout = cb.HALF, cb.LAYOUT_2D
+        else:
+            ps = datasets.clustered(8_000_000)
+        xyz, gmax, radius, bounds = ps.xyz, ps.grid_max, ps.radius, None
     num_local = xyz.shape[0]
     gmin = (0.0, 0.0, 0.0)
 
-    lst = cb.VerletList(algorithm=cb.FULL, layout=cb.CSR)
+    lst = cb.VerletList(algorithm=algo, layout=layout)
     capi.check(L.cb_verlet_set_profiling(lst._h, 1))
 
     if world == 1:
         x = cb.slice_from_array(xyz, vlen=32)
 
         def step():
-            lst.build(x, 0, num_local, RADIUS, CELL_RATIO, gmin, gmax)
+            lst.build(x, 0, num_local, radius, CELL_RATIO, gmin, gmax)
             return lst.total
     else:
         slab = comm.SlabDecomposition(bounds, RADIUS)
@@ -237,18 +251,29 @@ def run_ours(args):
 
         trace = os.environ.get("CB_BENCH_TRACE") == "1"
         tr = {"plan": 0.0, "gather": 0.0, "build": 0.0, "n": 0}
+        # ghost exchange: peer-memory windows over NVLink (default) or NCCL send/recv
+        halo_impl = os.environ.get("CB_BENCH_HALO", "peer")
+        peer = slab.create_peer_halo([x_all], cap - num_local) if halo_impl == "peer" else None
 
         def step():
             t0 = time.perf_counter()
             x_own = cb.Slice(x_all.data, num_local, x_all.outer_stride, x_all.vlen, x_all.comp_stride, 3)
-            halo = slab.create_halo(x_own, num_local)
-            n_tot = halo.numLocal() + halo.numGhost()
-            assert n_tot <= cap, "ghost capacity exceeded"
-            x_tot = cb.Slice(x_all.data, n_tot, x_all.outer_stride, x_all.vlen, x_all.comp_stride, 3)
-            if trace:
-                torch.cuda.synchronize()
-                t1 = time.perf_counter()
-            comm.gather(halo, x_tot)
+            if peer is not None:
+                n_lo, n_hi = peer.gather(x_own, [x_all], num_local)
+                n_tot = num_local + n_lo + n_hi
+                x_tot = cb.Slice(x_all.data, n_tot, x_all.outer_stride, x_all.vlen, x_all.comp_stride, 3)
+                if trace:
+                    torch.cuda.synchronize()
+                    t1 = time.perf_counter()
+            else:
+                halo = slab.create_halo(x_own, num_local)
+                n_tot = halo.numLocal() + halo.numGhost()
+                assert n_tot <= cap, "ghost capacity exceeded"
+                x_tot = cb.Slice(x_all.data, n_tot, x_all.outer_stride, x_all.vlen, x_all.comp_stride, 3)
+                if trace:
+                    torch.cuda.synchronize()
+                    t1 = time.perf_counter()
+                comm.gather(halo, x_tot)
             if trace:
                 torch.cuda.synchronize()
                 t2 = time.perf_counter()
@@ -347,12 +372,13 @@ def run_ours(args):
         host_x = torch.from_numpy(np.ascontiguousarray(xyz)).pin_memory()
         counts_h = torch.empty(num_local, dtype=torch.int32).pin_memory()
         offsets_h = torch.empty(num_local, dtype=torch.int32).pin_memory()
-        nb_h = torch.empty(int(lst.total), dtype=torch.int32).pin_memory()
+        nb_h = torch.empty(int(lst.total) if layout == cb.CSR else num_local * int(lst.width),
+                           dtype=torch.int32).pin_memory()
         e_steps = max(1, min(args.steps, 5))
 
         def e2e_step():
-            lst.build_host(host_x, 0, num_local, RADIUS, CELL_RATIO, gmin, gmax)
-            lst.copy_to_host(counts_h, offsets_h, nb_h)
+            lst.build_host(host_x, 0, num_local, radius, CELL_RATIO, gmin, gmax)
+            lst.copy_to_host(counts_h, offsets_h if layout == cb.CSR else None, nb_h)
 
         e2e_step()
         torch.cuda.synchronize()
@@ -384,7 +410,9 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": _workload_config(world),
+        "config": _workload_config(world) if args.workload == "cfg3" else
+        {"workload": args.workload + " (BASELINE.json parity configuration, informational)",
+         "particles": int(num_local)},
         "neighbors_per_step": global_total,
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -424,6 +452,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4"],
+                    help="cfg3 (default) is the headline line; the others are the BASELINE.json "
+                         "parity configurations, timed for DESIGN.md only (1 GPU)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

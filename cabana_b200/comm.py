@@ -324,3 +324,100 @@ class SlabDecomposition:
     def create_distributor(self, x: Slice, num_local: int) -> Distributor:
         dest = self.kernels.slab_destinations(x, num_local, self.bounds)
         return Distributor(dest, self.group, self.kernels)
+
+    def create_peer_halo(self, fields, capacity: int) -> "PeerHalo":
+        """Peer-memory halo (CUDA IPC windows over NVLink) for `fields`-shaped tuples."""
+        return PeerHalo(self, fields, capacity)
+
+
+class PeerHalo:
+    """Ghost gather for the slab decomposition through peer memory instead of send/recv.
+
+    Each rank owns two receive windows (from its lower and upper neighbour) that the
+    neighbours map with CUDA IPC once, at construction.  `gather` then runs, with no NCCL
+    call and ONE host synchronisation:
+        fused plan + pack straight into the neighbours' HBM  (cb_slab_halo_push)
+        bounded device-side wait for the neighbours' pushes    (cb_slab_halo_wait)
+        unpack from the local windows                          (cb_comm_unpack)
+    and produces exactly the ghosts of `gather(slab.create_halo(...))`, in the same order
+    (lower neighbour's first).  Replaces impl/Cabana_Halo_Mpi.hpp:41-125 for this topology.
+    All ranks of the group must be processes on one NVLink/NVSwitch box.
+    """
+
+    def __init__(self, slab: SlabDecomposition, fields, capacity: int):
+        self.slab = slab
+        L = capi.lib()
+        self.capacity = int(capacity)
+        arr = (capi.Field * len(fields))(*[f.field_desc() for f in fields])
+        self.tuple_bytes = int(L.cb_comm_tuple_bytes(arr, len(fields)))
+        self._win = [C.c_void_p(), C.c_void_p()]      # from_lo, from_hi
+        handles = []
+        for w in self._win:
+            capi.check(L.cb_p2p_window_create(C.byref(w), C.c_int64(self.capacity),
+                                              C.c_int64(self.tuple_bytes)))
+            h = (C.c_ubyte * 64)()
+            capi.check(L.cb_p2p_window_get_handle(w, h))
+            handles.append(bytes(h))
+        everyone = [None] * slab.world
+        dist.all_gather_object(everyone, handles, group=slab.group)
+        self._peer = [C.c_void_p(), C.c_void_p()]     # where I push my lo / hi face
+        if slab.lo_rank >= 0:   # my low face lands in the lower neighbour's "from_hi" window
+            h = (C.c_ubyte * 64).from_buffer_copy(everyone[slab.lo_rank][1])
+            capi.check(L.cb_p2p_window_open(h, C.byref(self._peer[0])))
+        if slab.hi_rank >= 0:
+            h = (C.c_ubyte * 64).from_buffer_copy(everyone[slab.hi_rank][0])
+            capi.check(L.cb_p2p_window_open(h, C.byref(self._peer[1])))
+        self._seq = 0
+        self._steer = None
+        dist.barrier(group=slab.group)   # every window is mapped before anyone pushes
+
+    def gather(self, x: Slice, fields, num_local: int):
+        """Push my face layers, receive the neighbours'; ghosts land at [num_local, ...).
+
+        `x` is the position slice the selection reads (its first num_local tuples), `fields`
+        the slices to ship (normally including x) sized for the ghosts.  Returns
+        (num_ghost_from_lo, num_ghost_from_hi)."""
+        L = capi.lib()
+        s = self.slab
+        self._seq += 1
+        if self._steer is None or self._steer.numel() < 2 * max(num_local, 1):
+            self._steer = torch.empty(2 * max(num_local, 1), dtype=torch.int32, device="cuda")
+        arr = (capi.Field * len(fields))(*[f.field_desc() for f in fields])
+        d = x.positions_desc()
+        st = _stream()
+        capi.check(L.cb_slab_halo_push(
+            C.byref(d), arr, len(fields), C.c_int64(num_local),
+            C.c_double(s.lo + s.halo_width), C.c_double(s.hi - s.halo_width),
+            self._peer[0], self._peer[1], C.c_int64(self.capacity), C.c_uint64(self._seq),
+            C.c_void_p(self._steer.data_ptr()), st))
+        counts = (C.c_int64 * 2)()
+        data = [C.c_void_p(), C.c_void_p()]
+        capi.check(L.cb_slab_halo_wait(
+            self._win[0] if s.lo_rank >= 0 else None, self._win[1] if s.hi_rank >= 0 else None,
+            C.c_uint64(self._seq), counts, C.byref(data[0]), C.byref(data[1]), st))
+        n_lo, n_hi = int(counts[0]), int(counts[1])
+        need = num_local + n_lo + n_hi
+        for f in fields:
+            if f.n < need:
+                raise ValueError(f"PeerHalo.gather: slice holds {f.n} tuples, needs {need}")
+        if n_lo:
+            capi.check(L.cb_comm_unpack(arr, len(fields), C.c_int64(num_local), C.c_int64(n_lo),
+                                        data[0], st))
+        if n_hi:
+            capi.check(L.cb_comm_unpack(arr, len(fields), C.c_int64(num_local + n_lo),
+                                        C.c_int64(n_hi), data[1], st))
+        return n_lo, n_hi
+
+    def close(self):
+        L = capi.lib()
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier(group=self.slab.group)
+        for p in self._peer:
+            if p:
+                L.cb_p2p_window_close(p)
+        for w in self._win:
+            if w:
+                L.cb_p2p_window_destroy(w)
+        self._peer = [C.c_void_p(), C.c_void_p()]
+        self._win = [C.c_void_p(), C.c_void_p()]

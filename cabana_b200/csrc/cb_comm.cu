@@ -12,6 +12,9 @@
 // block is not deterministic there (core/unit_test/tstDistributor.hpp:242-244).  Here a
 // stable partition (flag -> decoupled look-back scan -> scatter, one pass per non-empty
 // destination) makes it deterministic: ascending destination rank, ascending export index.
+#include <new>
+#include <string.h>
+
 #include "cb_common.cuh"
 #include "cb_internal.h"
 
@@ -564,5 +567,259 @@ extern "C" int cb_slab_halo_plan( const cb_positions* x, int64_t num_local, doub
     CB_CUDA( cudaStreamSynchronize( stream ) );
     counts_h[0] = s.pinned.ptr[0];
     counts_h[1] = s.pinned.ptr[1];
+    return CB_OK;
+}
+
+// =====================================================================================
+// Peer-memory slab halo (CUDA IPC over NVLink / NVSwitch)
+// =====================================================================================
+namespace cb
+{
+namespace
+{
+constexpr size_t kWinHeader = 128; // per buffer: u64 sequence, i64 count
+
+struct WinLayout
+{
+    long long capacity;
+    long long tuple_bytes;
+    size_t buffer_bytes() const { return kWinHeader + (size_t)capacity * (size_t)tuple_bytes; }
+};
+
+// pack the export list of one side into a (possibly remote) window buffer
+__global__ void __launch_bounds__( kBlock )
+    k_halo_push( FieldSet fs, const unsigned* __restrict__ steering,
+                 const long long* __restrict__ total, long long capacity, char* data )
+{
+    const long long count = min( *total, capacity );
+    for ( long long j = (long long)blockIdx.x * kBlock + threadIdx.x; j < count;
+          j += (long long)gridDim.x * kBlock )
+    {
+        const long long elem = (long long)steering[j];
+        char* tuple = data + j * fs.tuple_bytes;
+        for ( int k = 0; k < fs.num; ++k )
+        {
+            const FieldAccess& f = fs.f[k];
+            const long long off = f.offset( elem );
+            if ( f.elem_bytes == 8 )
+            {
+                const unsigned long long* fb = reinterpret_cast<const unsigned long long*>( f.base );
+                unsigned long long* tb = reinterpret_cast<unsigned long long*>( tuple + fs.byte_off[k] );
+                for ( int c = 0; c < f.num_comp; ++c )
+                    tb[c] = fb[off + f.comp_stride * c];
+            }
+            else
+            {
+                const unsigned* fb = reinterpret_cast<const unsigned*>( f.base );
+                unsigned* tb = reinterpret_cast<unsigned*>( tuple + fs.byte_off[k] );
+                for ( int c = 0; c < f.num_comp; ++c )
+                    tb[c] = fb[off + f.comp_stride * c];
+            }
+        }
+    }
+}
+
+// after the pack kernel: publish (count, sequence) in the remote header
+__global__ void k_halo_signal( const long long* total, char* header, unsigned long long seq )
+{
+    __threadfence_system();
+    *reinterpret_cast<volatile long long*>( header + 8 ) = *total;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>( header ) = seq;
+    __threadfence_system();
+}
+
+// receiver: bounded wait on the local header(s)
+__global__ void k_halo_wait( const char* hdr_lo, const char* hdr_hi, unsigned long long seq,
+                             long long* out /* [3]: count_lo, count_hi, timed_out */ )
+{
+    const long long start = clock64();
+    const long long limit = 20000000000ll; // ~10 s at 2 GHz: never hang the GPU
+    bool ok = true;
+    for ( int side = 0; side < 2; ++side )
+    {
+        const char* h = side ? hdr_hi : hdr_lo;
+        long long count = 0;
+        if ( h )
+        {
+            while ( *reinterpret_cast<const volatile unsigned long long*>( h ) != seq )
+            {
+                if ( clock64() - start > limit )
+                {
+                    ok = false;
+                    break;
+                }
+                __nanosleep( 200 );
+            }
+            __threadfence_system();
+            count = *reinterpret_cast<const volatile long long*>( h + 8 );
+        }
+        out[side] = count;
+    }
+    out[2] = ok ? 0 : 1;
+}
+} // namespace
+} // namespace cb
+
+struct cb_p2p_window
+{
+    char* base = nullptr; // two buffers: [header|data][header|data]
+    cb::WinLayout lay{};
+    cb::DeviceBuffer scratch; // wait results
+};
+
+extern "C" int cb_p2p_window_create( cb_p2p_window** out, int64_t capacity_tuples,
+                                     int64_t tuple_bytes )
+{
+    if ( !out || capacity_tuples < 1 || tuple_bytes < 1 )
+        return fail( CB_ERR_INVALID, "cb_p2p_window_create: bad argument" );
+    cb_p2p_window* w = new ( std::nothrow ) cb_p2p_window();
+    if ( !w )
+        return fail( CB_ERR_NOMEM, "cb_p2p_window_create" );
+    w->lay.capacity = capacity_tuples;
+    w->lay.tuple_bytes = tuple_bytes;
+    const size_t bytes = 2 * w->lay.buffer_bytes();
+    cudaError_t e = cudaMalloc( (void**)&w->base, bytes ); // plain cudaMalloc: IPC-exportable
+    if ( e == cudaSuccess )
+        e = cudaMemset( w->base, 0, bytes );
+    if ( e != cudaSuccess )
+    {
+        delete w;
+        return cuda_fail( e, "cb_p2p_window_create", __FILE__, __LINE__ );
+    }
+    *out = w;
+    return CB_OK;
+}
+
+extern "C" int cb_p2p_window_destroy( cb_p2p_window* w )
+{
+    if ( w )
+    {
+        if ( w->base )
+            cudaFree( w->base );
+        delete w;
+    }
+    return CB_OK;
+}
+
+extern "C" int cb_p2p_window_get_handle( const cb_p2p_window* w, void* handle_h )
+{
+    if ( !w || !handle_h )
+        return fail( CB_ERR_INVALID, "cb_p2p_window_get_handle: null argument" );
+    static_assert( sizeof( cudaIpcMemHandle_t ) == CB_IPC_HANDLE_BYTES, "" );
+    cudaIpcMemHandle_t h;
+    CB_CUDA( cudaIpcGetMemHandle( &h, w->base ) );
+    memcpy( handle_h, &h, sizeof( h ) );
+    return CB_OK;
+}
+
+extern "C" int cb_p2p_window_open( const void* handle_h, void** peer_base )
+{
+    if ( !handle_h || !peer_base )
+        return fail( CB_ERR_INVALID, "cb_p2p_window_open: null argument" );
+    cudaIpcMemHandle_t h;
+    memcpy( &h, handle_h, sizeof( h ) );
+    CB_CUDA( cudaIpcOpenMemHandle( peer_base, h, cudaIpcMemLazyEnablePeerAccess ) );
+    return CB_OK;
+}
+
+extern "C" int cb_p2p_window_close( void* peer_base )
+{
+    if ( peer_base )
+        CB_CUDA( cudaIpcCloseMemHandle( peer_base ) );
+    return CB_OK;
+}
+
+extern "C" int cb_slab_halo_push( const cb_positions* x, const cb_field* fields,
+                                  int num_fields, int64_t num_local, double lo_thresh,
+                                  double hi_thresh, void* peer_lo, void* peer_hi,
+                                  int64_t capacity_tuples, uint64_t sequence,
+                                  uint32_t* steer_scratch, cb_stream_t stream_ )
+{
+    FieldSet fs;
+    CB_TRY( make_field_set( fields, num_fields, fs ) );
+    if ( !x || !steer_scratch || num_local < 0 || num_local > x->n || x->vlen < 1 ||
+         num_local >= 2147483647ll || capacity_tuples < 1 )
+        return fail( CB_ERR_INVALID, "cb_slab_halo_push: bad argument" );
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CommScratch& s = scratch();
+    const long long nl = num_local > 0 ? num_local : 1;
+    const long long num_tiles = ( nl + kHaloTile - 1 ) / kHaloTile;
+    const size_t bytes = 32 + (size_t)num_tiles * sizeof( unsigned long long );
+    CB_TRY( s.scan.ensure( bytes, 1.25 ) );
+    CB_CUDA( cudaMemsetAsync( s.scan.ptr, 0, bytes, stream ) );
+    unsigned* counter = s.scan.as<unsigned>();
+    long long* totals = reinterpret_cast<long long*>( s.scan.as<char>() + 16 );
+    unsigned long long* status = reinterpret_cast<unsigned long long*>( s.scan.as<char>() + 32 );
+    uint32_t* steer_lo = steer_scratch;
+    uint32_t* steer_hi = steer_scratch + nl;
+    if ( num_local > 0 )
+    {
+        k_halo_compact<<<(unsigned)num_tiles, kHaloThreads, 0, stream>>>(
+            make_access( *x ), num_local, lo_thresh, hi_thresh, peer_lo ? 1 : 0,
+            peer_hi ? 1 : 0, steer_lo, steer_hi, status, counter, (unsigned)num_tiles, totals );
+        CB_CHECK_LAUNCH();
+    }
+    WinLayout lay{ capacity_tuples, fs.tuple_bytes };
+    const size_t parity_off = ( sequence & 1ull ) ? lay.buffer_bytes() : 0;
+    // my LOWER neighbour receives my low-face particles in ITS "from_hi" window and vice
+    // versa; the caller passes the matching peer bases, so side only selects the list.
+    for ( int side = 0; side < 2; ++side )
+    {
+        char* peer = (char*)( side ? peer_hi : peer_lo );
+        if ( !peer )
+            continue;
+        char* buf = peer + parity_off;
+        // ghost layers are thin: a grid sized for the capacity, threads past the count exit
+        const int grid = launch_grid_for( capacity_tuples, kBlock );
+        k_halo_push<<<grid, kBlock, 0, stream>>>( fs, side ? steer_hi : steer_lo, totals + side,
+                                                  capacity_tuples, buf + kWinHeader );
+        CB_CHECK_LAUNCH();
+        k_halo_signal<<<1, 1, 0, stream>>>( totals + side, buf, (unsigned long long)sequence );
+        CB_CHECK_LAUNCH();
+    }
+    return CB_OK;
+}
+
+extern "C" int cb_slab_halo_wait( cb_p2p_window* from_lo, cb_p2p_window* from_hi,
+                                  uint64_t sequence, int64_t* counts_h, const void** data_lo,
+                                  const void** data_hi, cb_stream_t stream_ )
+{
+    if ( !counts_h || !data_lo || !data_hi )
+        return fail( CB_ERR_INVALID, "cb_slab_halo_wait: null argument" );
+    cudaStream_t stream = (cudaStream_t)stream_;
+    counts_h[0] = counts_h[1] = 0;
+    *data_lo = *data_hi = nullptr;
+    if ( !from_lo && !from_hi )
+        return CB_OK;
+    CommScratch& s = scratch();
+    CB_TRY( s.pinned.ensure() );
+    cb_p2p_window* any = from_lo ? from_lo : from_hi;
+    CB_TRY( any->scratch.ensure( 64 ) );
+    const char* hl = nullptr;
+    const char* hh = nullptr;
+    if ( from_lo )
+    {
+        hl = from_lo->base + ( ( sequence & 1ull ) ? from_lo->lay.buffer_bytes() : 0 );
+        *data_lo = hl + kWinHeader;
+    }
+    if ( from_hi )
+    {
+        hh = from_hi->base + ( ( sequence & 1ull ) ? from_hi->lay.buffer_bytes() : 0 );
+        *data_hi = hh + kWinHeader;
+    }
+    k_halo_wait<<<1, 1, 0, stream>>>( hl, hh, (unsigned long long)sequence,
+                                      any->scratch.as<long long>() );
+    CB_CHECK_LAUNCH();
+    CB_CUDA( cudaMemcpyAsync( s.pinned.ptr + 8, any->scratch.ptr, 3 * sizeof( long long ),
+                              cudaMemcpyDeviceToHost, stream ) );
+    CB_CUDA( cudaStreamSynchronize( stream ) );
+    if ( s.pinned.ptr[10] != 0 )
+        return fail( CB_ERR_CUDA, "cb_slab_halo_wait: timed out waiting for a neighbour's push" );
+    counts_h[0] = s.pinned.ptr[8];
+    counts_h[1] = s.pinned.ptr[9];
+    if ( ( from_lo && counts_h[0] > from_lo->lay.capacity ) ||
+         ( from_hi && counts_h[1] > from_hi->lay.capacity ) )
+        return fail( CB_ERR_NOMEM, "cb_slab_halo_wait: ghost layer larger than the window" );
     return CB_OK;
 }

@@ -356,6 +356,41 @@ int cb_comm_scatter_add(const cb_field* field_h, const uint32_t* steering,
 /* bytes of one packed tuple */
 int64_t cb_comm_tuple_bytes(const cb_field* fields_h, int num_fields);
 
+/* -----------------------------------------------------------------------------
+ * Peer-memory halo for the slab decomposition (one process per GPU on one NVSwitch box).
+ *
+ * Instead of pack -> NCCL send/recv -> unpack with a host-side count exchange, each rank owns
+ * a receive WINDOW in its HBM that its two slab neighbours map through CUDA IPC; the fused
+ * push below selects the ghost layer, compacts it (stable) and packs it STRAIGHT INTO the
+ * neighbours' windows over NVLink, then publishes (count, sequence) in the window header.
+ * The receiver waits on its own headers, reads the two counts back (the only host sync of
+ * the exchange) and unpacks from local memory.  Windows are double-buffered by sequence
+ * parity, which is sufficient because a rank can run at most one exchange ahead of a
+ * neighbour.  This replaces impl/Cabana_Halo_Mpi.hpp:70-124 (Irecv/Send/Waitall/Barrier)
+ * and the count exchange of impl/Cabana_CommunicationPlan_Mpi.hpp:152-178 for this topology.
+ * -------------------------------------------------------------------------- */
+typedef struct cb_p2p_window cb_p2p_window;
+#define CB_IPC_HANDLE_BYTES 64
+/* capacity_tuples per buffer; tuple_bytes from cb_comm_tuple_bytes */
+int cb_p2p_window_create(cb_p2p_window** out, int64_t capacity_tuples, int64_t tuple_bytes);
+int cb_p2p_window_destroy(cb_p2p_window* w);
+int cb_p2p_window_get_handle(const cb_p2p_window* w, void* handle_h /* 64 bytes */);
+int cb_p2p_window_open(const void* handle_h, void** peer_base);   /* in the PEER process */
+int cb_p2p_window_close(void* peer_base);
+/* Fused plan + pack into the neighbours' windows (peer_lo / peer_hi from cb_p2p_window_open,
+ * NULL when there is no neighbour on that side).  steer_scratch holds 2*num_local ids.
+ * No host synchronisation. */
+int cb_slab_halo_push(const cb_positions* x, const cb_field* fields_h, int num_fields,
+                      int64_t num_local, double lo_thresh, double hi_thresh, void* peer_lo,
+                      void* peer_hi, int64_t capacity_tuples, uint64_t sequence,
+                      uint32_t* steer_scratch, cb_stream_t stream);
+/* Wait (on the device, bounded) for the pushes of `sequence` into my windows, return the ghost
+ * counts and the local buffers holding them; synchronises the stream once.
+ * CB_ERR_NOMEM if a neighbour had more ghosts than capacity, CB_ERR_CUDA on time-out. */
+int cb_slab_halo_wait(cb_p2p_window* from_lo, cb_p2p_window* from_hi, uint64_t sequence,
+                      int64_t* counts_h /* [2] */, const void** data_lo, const void** data_hi,
+                      cb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

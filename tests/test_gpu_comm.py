@@ -191,6 +191,36 @@ def _rank_main(rank, world, port, ret):
                 f_tot = cb.Slice(f.data, nt, 3, 1, 1, 3)
                 cb.neighbor_parallel_for_lj(0, nl, lst, x_tot, f_tot, 1.0, 1.0, 2.5, cb.OP_SERIAL)
                 out["f_full"] = (mine, f.to_array().cpu().numpy()[:nl])
+        # peer-memory halo (CUDA IPC windows): same ghosts, same order, across repeated
+        # exchanges (double-buffered windows) and with positions changing between them
+        ph = slab.create_peer_halo([x_all, g_all], capacity=30000)
+        ref_x = x_tot.to_array().cpu().numpy().copy()
+        ref_g = g_tot.to_array().cpu().numpy().copy()
+        peer_ok = True
+        for it in range(5):
+            store2 = np.zeros((cap, 3))
+            store2[:nl] = ps.xyz[mine]
+            if it % 2 == 1:   # shift x a little: a different ghost set on odd exchanges
+                store2[:nl, 0] += 0.37 * (1 if rank == 0 else -1)
+            x2 = cb.slice_from_array(store2, vlen=32)
+            g2 = cb.view_from_array(gid)
+            n_lo, n_hi = ph.gather(cb.Slice(x2.data, nl, x2.outer_stride, x2.vlen, x2.comp_stride, 3),
+                                   [x2, g2], nl)
+            x2_own = cb.Slice(x2.data, nl, x2.outer_stride, x2.vlen, x2.comp_stride, 3)
+            halo2 = slab.create_halo(x2_own, nl)
+            nt2 = nl + halo2.numGhost()
+            x3 = cb.slice_from_array(store2, vlen=32)
+            g3 = cb.view_from_array(gid)
+            comm.gather(halo2, cb.Slice(x3.data, nt2, x3.outer_stride, x3.vlen, x3.comp_stride, 3),
+                        cb.Slice(g3.data, nt2, 1, 1, 1, 1))
+            peer_ok &= (nl + n_lo + n_hi == nt2)
+            peer_ok &= bool(np.array_equal(x2.to_array().cpu().numpy()[:nt2], x3.to_array().cpu().numpy()[:nt2]))
+            peer_ok &= bool(np.array_equal(g2.to_array().cpu().numpy()[:nt2], g3.to_array().cpu().numpy()[:nt2]))
+            if it == 0:
+                peer_ok &= bool(np.array_equal(x2.to_array().cpu().numpy()[:nt], ref_x))
+                peer_ok &= bool(np.array_equal(g2.to_array().cpu().numpy()[:nt], ref_g))
+        ph.close()
+        out["peer_halo_ok"] = peer_ok
         ret[rank] = out
     except Exception:
         import traceback
@@ -211,6 +241,7 @@ def test_two_gpu_slab_build_equals_single_gpu(orc):
     mp.spawn(_rank_main, args=(world, _free_port(), ret), nprocs=world, join=True)
     for r in range(world):
         assert isinstance(ret[r], dict), ret[r]
+        assert ret[r]["peer_halo_ok"], "peer-memory halo differs from the send/recv halo"
     ps = datasets.fcc_lattice(24, jitter=0.03)
     ox = orc.view_from_xyz(ps.xyz)
     for algo, oalgo in ((0, orc.FULL), (1, orc.HALF)):
