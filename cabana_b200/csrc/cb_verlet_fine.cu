@@ -159,19 +159,31 @@ CB_D void emit_row( const FineArgs& a, Reservation& rs, const unsigned* list,
     {
         __syncwarp();
         // the candidates' ids were parked in shared memory by the test loop (they arrive
-        // in the float4's w): no global gather, no dependent-load chain
-        const int* mine = idbuf + lane;
-        while ( hm )
+        // in the float4's w): no global gather, no dependent-load chain.  Branch-free walk
+        // over the iteration bits (predicated load/store/bump, immediate offsets) instead of
+        // a data-dependent loop whose trip count is the MAXIMUM hit count over the lanes.
         {
-            const int it = __ffs( hm ) - 1;
-            hm &= hm - 1;
-            rowbuf[wr++] = mine[it * 32];
+            const int* mine = idbuf + lane;
+            int* out = rowbuf + wr;
+#pragma unroll
+            for ( int it = 0; it < kIdBuf / 32; ++it )
+            {
+                if ( hm & ( 1u << it ) )
+                    *out++ = mine[it * 32];
+            }
         }
         __syncwarp();
         // streaming stores: the rows are not read again by this kernel and must not evict
         // the candidate positions from L1
-        for ( int i = (int)lane; i < tot; i += 32 )
-            __stcs( &a.tmp[at + i], rowbuf[i] );
+        {
+            int* dst = a.tmp + at + lane;
+            const int* src = rowbuf + lane;
+            const int left = tot - (int)lane;
+#pragma unroll
+            for ( int k = 0; k < kRowBuf / 32; ++k )
+                if ( left > 32 * k )
+                    __stcs( dst + 32 * k, src[32 * k] );
+        }
     }
     else
     {
@@ -430,8 +442,14 @@ __global__ void __launch_bounds__( kColBlock, 3 )
                 if ( base + tot > kColCap )
                     break;
                 {
+                    // cells of ~r/2 hold a handful of particles: predicated straight-line
+                    // stores for the first four, a loop only for denser cells
                     unsigned* dst = list + base + ( incl0 - len[0] );
-                    for ( int j = 0; j < len[0]; ++j )
+#pragma unroll
+                    for ( int j = 0; j < 4; ++j )
+                        if ( j < len[0] )
+                            dst[j] = st[0] + (unsigned)j;
+                    for ( int j = 4; j < len[0]; ++j )
                         dst[j] = st[0] + (unsigned)j;
                     if ( nrows > 32 )
                     {
