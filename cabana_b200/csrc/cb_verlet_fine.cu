@@ -229,7 +229,7 @@ CB_D void test_one( const float4& c, float xi, float yi, float zi, float t_lo, f
 
 // Hot loop over list positions [t0, t1): every lane tests ONE candidate per iteration
 // against NP home particles.  Lanes past t1 read the sentinel at infinity.
-template <int NP, bool HALF>
+template <int NP, bool HALF, bool COL>
 CB_D void test_range( const float4* __restrict__ q, const unsigned* list, int* idbuf,
                       int t0, int t1, unsigned lane, unsigned sentinel, float t_lo,
                       float t_hi,
@@ -242,9 +242,11 @@ CB_D void test_range( const float4* __restrict__ q, const unsigned* list, int* i
     for ( int tb = t0; tb < t1; tb += 32 )
     {
         const int t = tb + (int)lane;
-        const unsigned idx = t < t1 ? list[t] : sentinel;
+        // column kernel: the list is padded with sentinels and whatever follows t1 is a
+        // candidate outside the cutoff's reach, so the tail needs no select
+        const unsigned idx = ( COL || t < t1 ) ? list[t] : sentinel;
         const float4 c = q[idx];
-        if ( idbuf )
+        if ( COL )
             idbuf[t - t0] = __float_as_int( c.w );
 #pragma unroll
         for ( int p = 0; p < NP; ++p )
@@ -253,7 +255,7 @@ CB_D void test_range( const float4* __restrict__ q, const unsigned* list, int* i
     }
 }
 
-template <bool HALF>
+template <bool HALF, bool COL>
 CB_D void test_group( int np, const float4* __restrict__ q, const unsigned* list,
                       int* idbuf, int t0, int t1, unsigned lane, unsigned sentinel,
                       float t_lo, float t_hi,
@@ -264,19 +266,19 @@ CB_D void test_group( int np, const float4* __restrict__ q, const unsigned* list
     switch ( np )
     {
     case 1:
-        test_range<1, HALF>( q, list, idbuf, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
+        test_range<1, HALF, COL>( q, list, idbuf, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
                              amb );
         break;
     case 2:
-        test_range<2, HALF>( q, list, idbuf, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
+        test_range<2, HALF, COL>( q, list, idbuf, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
                              amb );
         break;
     case 3:
-        test_range<3, HALF>( q, list, idbuf, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
+        test_range<3, HALF, COL>( q, list, idbuf, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
                              amb );
         break;
     default:
-        test_range<4, HALF>( q, list, idbuf, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
+        test_range<4, HALF, COL>( q, list, idbuf, t0, t1, lane, sentinel, t_lo, t_hi, xi, yi, zi, hit,
                              amb );
         break;
     }
@@ -439,8 +441,8 @@ __global__ void __launch_bounds__( kColBlock, 3 )
                     tot += __shfl_sync( kFullMask, incl1, 31 );
                     excl1 = tot0 + incl1 - len[1];
                 }
-                if ( base + tot > kColCap )
-                    break;
+                if ( base + tot > kColCap - 32 )
+                    break; // (32 entries are kept for the sentinel pad)
                 {
                     // cells of ~r/2 hold a handful of particles: predicated straight-line
                     // stores for the first four, a loop only for denser cells
@@ -474,6 +476,7 @@ __global__ void __launch_bounds__( kColBlock, 3 )
             }
             if ( lane == 0 )
                 layer[nbuilt] = base;
+            list[base + (int)lane] = sentinel; // pad: the test loop reads whole 32-blocks
         }
         __syncwarp();
 
@@ -504,7 +507,12 @@ __global__ void __launch_bounds__( kColBlock, 3 )
             }
             const int t0 = layer[lo - kL0];
             const int t1 = layer[hi + 1 - kL0];
-            if ( t1 - t0 > kIdBuf )
+            // The test loop runs over whole blocks of 32 list entries, so up to 31 entries
+            // past t1 are tested too: the pad, or candidates of layers beyond cc+Kz, which
+            // the cutoff cannot reach (a rounding-level d2 == r^2 there is rejected by the
+            // reference stencil check of tier 2).  If the reference stencil cut the range
+            // short (hi < cc+Kz inside the grid) that argument does not hold: general kernel.
+            if ( t1 - t0 > kIdBuf || ( hi != cc + Kz && hi - kL0 + 1 != nbuilt ) )
             {
                 push_overflow( a, (unsigned)( homebase + cc ), lane );
                 continue;
@@ -523,8 +531,8 @@ __global__ void __launch_bounds__( kColBlock, 3 )
                 unsigned hit[kGroup] = { 0u, 0u, 0u, 0u };
                 unsigned amb[kGroup] = { 0u, 0u, 0u, 0u };
                 __syncwarp();
-                test_group<HALF>( np, a.q, list, idbuf, t0, t1, lane, sentinel, a.t_lo,
-                                  a.t_hi, xi, yi, zi, hit, amb );
+                test_group<HALF, true>( np, a.q, list, idbuf, t0, t1, lane, sentinel, a.t_lo,
+                                        a.t_hi, xi, yi, zi, hit, amb );
                 __syncwarp();
 
                 // j != i: home particle pg+p sits at list position selfbase + (pg-h0) + p
@@ -708,8 +716,9 @@ __global__ void __launch_bounds__( kBlock, 3 )
 
                         unsigned hit[kGroup] = { 0u, 0u, 0u, 0u };
                         unsigned amb[kGroup] = { 0u, 0u, 0u, 0u };
-                        test_group<HALF>( np, a.q, list, nullptr, 0, count, lane, sentinel,
-                                          a.t_lo, a.t_hi, xi, yi, zi, hit, amb );
+                        test_group<HALF, false>( np, a.q, list, nullptr, 0, count, lane,
+                                                 sentinel, a.t_lo, a.t_hi, xi, yi, zi, hit,
+                                                 amb );
 
                         const int sp0 = self0 - w0;
                         if ( self0 >= 0 && sp0 + kGroup > 0 && sp0 < kListCap )
