@@ -92,6 +92,11 @@ __device__ __noinline__ unsigned resolve_exact( const FineArgs& a, const unsigne
         const int it = __ffs( am ) - 1;
         am &= am - 1;
         const unsigned idx = list[it * 32 + (int)lane];
+        if ( idx == ps )
+        {
+            hit &= ~( 1u << it ); // j != i (the band mask is shared by the home particles)
+            continue;
+        }
         const double xn = a.xs[idx];
         const double yn = a.ys[idx];
         const double zn = a.zs[idx];
@@ -136,7 +141,7 @@ CB_D long long reserve_ids( const FineArgs& a, Reservation& rs, int need, unsign
 // lanes scatter their ids into a shared-memory row at their scanned positions, then the
 // warp streams the row out with coalesced stores.  All lanes must call this.
 CB_D void emit_row( const FineArgs& a, Reservation& rs, const unsigned* list,
-                    const int* idbuf, int* rowbuf, unsigned lane, unsigned hm, int pid,
+                    const int* idbuf, int* rowbuf, unsigned lane, unsigned hm,
                     unsigned slot )
 {
     const int c = __popc( hm );
@@ -145,6 +150,9 @@ CB_D void emit_row( const FineArgs& a, Reservation& rs, const unsigned* list,
     const long long at = reserve_ids( a, rs, tot, lane );
     if ( lane == 0 )
     {
+        // the row's particle id is re-read here (L1-resident) rather than held in a
+        // register across the test loop
+        const int pid = __float_as_int( a.q[slot].w );
         __stcs( &a.counts[pid], tot );
         __stcs( &a.tmp_off[slot], (unsigned)at );
     }
@@ -235,7 +243,7 @@ CB_D void test_range( const float4* __restrict__ q, const unsigned* list, int* i
                       float t_hi,
                       const float ( &xi )[kGroup], const float ( &yi )[kGroup],
                       const float ( &zi )[kGroup], unsigned ( &hit )[kGroup],
-                      unsigned ( &amb )[kGroup] )
+                      unsigned& amb )
 {
     unsigned bit = 1u;
 #pragma unroll 2
@@ -250,7 +258,7 @@ CB_D void test_range( const float4* __restrict__ q, const unsigned* list, int* i
             idbuf[t - t0] = __float_as_int( c.w );
 #pragma unroll
         for ( int p = 0; p < NP; ++p )
-            test_one<HALF>( c, xi[p], yi[p], zi[p], t_lo, t_hi, bit, hit[p], amb[p] );
+            test_one<HALF>( c, xi[p], yi[p], zi[p], t_lo, t_hi, bit, hit[p], amb );
         bit <<= 1;
     }
 }
@@ -261,7 +269,7 @@ CB_D void test_group( int np, const float4* __restrict__ q, const unsigned* list
                       float t_lo, float t_hi,
                       const float ( &xi )[kGroup], const float ( &yi )[kGroup],
                       const float ( &zi )[kGroup], unsigned ( &hit )[kGroup],
-                      unsigned ( &amb )[kGroup] )
+                      unsigned& amb )
 {
     switch ( np )
     {
@@ -529,7 +537,7 @@ __global__ void __launch_bounds__( kColBlock, 3 )
                     continue;
 
                 unsigned hit[kGroup] = { 0u, 0u, 0u, 0u };
-                unsigned amb[kGroup] = { 0u, 0u, 0u, 0u };
+                unsigned amb = 0u; // candidates inside the FP32 band of ANY home particle
                 __syncwarp();
                 test_group<HALF, true>( np, a.q, list, idbuf, t0, t1, lane, sentinel, a.t_lo,
                                         a.t_hi, xi, yi, zi, hit, amb );
@@ -543,26 +551,24 @@ __global__ void __launch_bounds__( kColBlock, 3 )
                     {
                         const int sp = sp0 + p;
                         if ( ( sp & 31 ) == (int)lane )
-                        {
                             hit[p] &= ~( 1u << ( sp >> 5 ) );
-                            amb[p] &= ~( 1u << ( sp >> 5 ) );
-                        }
                     }
                 }
-                // tier 2 (rare): exact arithmetic for the ambiguous band
-                if ( __any_sync( kFullMask, ( amb[0] | amb[1] | amb[2] | amb[3] ) != 0u ) )
+                // tier 2 (rare): exact arithmetic for every home particle against the
+                // candidates that were inside the band of any of them
+                if ( amb )
                 {
 #pragma unroll
                     for ( int p = 0; p < kGroup; ++p )
-                        if ( amb[p] )
+                        if ( p < np )
                             hit[p] = resolve_exact<HALF>( a, list + t0, lane, pg + p, hit[p],
-                                                          amb[p] );
+                                                          amb );
                 }
+                __syncwarp();
 #pragma unroll
                 for ( int p = 0; p < kGroup; ++p )
                     if ( ( active >> p ) & 1u )
-                        emit_row( a, rs, list + t0, idbuf, rowbuf, lane, hit[p], pid[p],
-                                  pg + p );
+                        emit_row( a, rs, list + t0, idbuf, rowbuf, lane, hit[p], pg + p );
             }
         }
     }
@@ -715,7 +721,7 @@ __global__ void __launch_bounds__( kBlock, 3 )
                         __syncwarp();
 
                         unsigned hit[kGroup] = { 0u, 0u, 0u, 0u };
-                        unsigned amb[kGroup] = { 0u, 0u, 0u, 0u };
+                        unsigned amb = 0u;
                         test_group<HALF, false>( np, a.q, list, nullptr, 0, count, lane,
                                                  sentinel, a.t_lo, a.t_hi, xi, yi, zi, hit,
                                                  amb );
@@ -728,20 +734,16 @@ __global__ void __launch_bounds__( kBlock, 3 )
                             {
                                 const int sp = sp0 + p;
                                 if ( sp >= 0 && sp < kListCap && ( sp & 31 ) == (int)lane )
-                                {
                                     hit[p] &= ~( 1u << ( sp >> 5 ) );
-                                    amb[p] &= ~( 1u << ( sp >> 5 ) );
-                                }
                             }
                         }
-                        if ( __any_sync( kFullMask,
-                                         ( amb[0] | amb[1] | amb[2] | amb[3] ) != 0u ) )
+                        if ( amb )
                         {
 #pragma unroll
                             for ( int p = 0; p < kGroup; ++p )
-                                if ( amb[p] )
+                                if ( p < np )
                                     hit[p] = resolve_exact<HALF>( a, list, lane, pg + p,
-                                                                  hit[p], amb[p] );
+                                                                  hit[p], amb );
                         }
 
                         if ( phase == 0 )
