@@ -840,9 +840,21 @@ int launch_fine_single( const FineArgs& a, int algorithm, cudaStream_t stream )
         const int nchunk = ( a.nf[2] + kChunk - 1 ) / kChunk;
         const long long items = (long long)a.nf[0] * a.nf[1] * nchunk;
         long long blocks = ( items + kColWarps - 1 ) / kColWarps;
-        // persistent grid: 3 CTAs per SM (keeps the reservation slack of the temporary
-        // buffer at warps * kReserve ids ~ 58 MB)
-        const long long cap = (long long)kNumSMs * 3;
+        // persistent grid: every resident CTA slot once (keeps the reservation slack of
+        // the temporary buffer at warps * kReserve ids)
+        static int per_sm[2] = { 0, 0 };
+        if ( per_sm[half] == 0 )
+        {
+            int nb = 0;
+            if ( half )
+                CB_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                    &nb, k_verlet_column<true>, kColBlock, 0 ) );
+            else
+                CB_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                    &nb, k_verlet_column<false>, kColBlock, 0 ) );
+            per_sm[half] = nb > 0 ? nb : 1;
+        }
+        const long long cap = (long long)kNumSMs * per_sm[half];
         if ( blocks > cap )
             blocks = cap;
         if ( half )
