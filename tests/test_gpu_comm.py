@@ -261,3 +261,109 @@ def test_two_gpu_slab_build_equals_single_gpu(orc):
             mine, f = ret[r][key]
             got[mine] = f
         assert np.all(np.abs(got - f_ref) <= 1e-12 * np.maximum(fabs, 1e-300)), key
+
+
+# ------------------------------------------------------------------ 2 GPUs: migrate + halo + build
+def _rank_migrate(rank, world, port, ret):
+    """cfg5 in miniature: particles drift, some cross the slab face, Distributor/migrate moves
+    them to their new owner over NCCL, then the ghost layer is gathered and a Half CSR list
+    is built.  Returns owner-local rows mapped to global ids."""
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from cabana_b200 import comm
+        from cabana_b200 import core as cb
+
+        ps = datasets.uniform_box(40000, 20240105, radius=3.0)
+        L = ps.grid_max[0]
+        moved = _drifted(ps)
+        bounds = [L * g / world for g in range(world + 1)]
+        # ownership BEFORE the drift
+        owner0 = np.minimum((ps.xyz[:, 0] / (L / world)).astype(int), world - 1)
+        mine0 = np.nonzero(owner0 == rank)[0]
+        n0 = len(mine0)
+        slab = comm.SlabDecomposition(bounds, ps.radius)
+        x_src = cb.slice_from_array(moved[mine0], vlen=32)          # already drifted
+        g_src = cb.view_from_array(mine0.astype(np.int32).reshape(-1, 1))
+        distributor = slab.create_distributor(x_src, n0)
+        n1 = distributor.totalNumImport()
+        cap = n1 + 20000
+        x_all = cb.slice_from_array(np.zeros((cap, 3)), vlen=32)
+        g_all = cb.view_from_array(np.full((cap, 1), -1, dtype=np.int32))
+        comm.migrate(distributor, [x_src, g_src],
+                     [cb.Slice(x_all.data, n1, x_all.outer_stride, x_all.vlen, x_all.comp_stride, 3),
+                      cb.Slice(g_all.data, n1, 1, 1, 1, 1)])
+        # ghosts through the peer-memory halo, then the owner-local half list
+        ph = slab.create_peer_halo([x_all, g_all], capacity=20000)
+        x_own = cb.Slice(x_all.data, n1, x_all.outer_stride, x_all.vlen, x_all.comp_stride, 3)
+        n_lo, n_hi = ph.gather(x_own, [x_all, g_all], n1)
+        nt = n1 + n_lo + n_hi
+        x_tot = cb.Slice(x_all.data, nt, x_all.outer_stride, x_all.vlen, x_all.comp_stride, 3)
+        lgx = slab.local_grid_x()
+        lst = cb.VerletList(x_tot, 0, n1, ps.radius, 1.0, (lgx[0], 0.0, 0.0),
+                            (lgx[1], ps.grid_max[1], ps.grid_max[2]), algorithm=cb.HALF, layout=cb.CSR)
+        counts = lst._data.counts.cpu().numpy()[:n1]
+        offs = lst._data.offsets.cpu().numpy()[:n1]
+        nb = lst._data.neighbors.cpu().numpy()
+        g = g_all.to_array().cpu().numpy()[:nt, 0]
+        xs = x_all.to_array().cpu().numpy()[:n1]
+        rows = {int(g[i]): sorted(int(v) for v in g[nb[offs[i]:offs[i] + counts[i]]]) for i in range(n1)}
+        ph.close()
+        ret[rank] = {"rows": rows, "owned": g[:n1].copy(), "x": xs,
+                     "num_stay": distributor.numExport(0), "n0": n0}
+    except Exception:
+        import traceback
+
+        ret[rank] = traceback.format_exc()
+    finally:
+        dist.destroy_process_group()
+
+
+def _drifted(ps):
+    """Deterministic drift: ~2 % of the particles change slab (reflected at the box faces)."""
+    rng = np.random.Generator(np.random.Philox(key=515))
+    L = np.asarray(ps.grid_max)
+    moved = ps.xyz + rng.normal(0.0, 0.6, ps.xyz.shape)
+    moved = np.abs(moved)
+    moved = L - np.abs(L - moved)
+    return np.clip(moved, 0.0, np.nextafter(L, 0.0))
+
+
+def test_two_gpu_migrate_then_half_list(orc):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_rank_migrate, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for r in range(world):
+        assert isinstance(ret[r], dict), ret[r]
+    ps = datasets.uniform_box(40000, 20240105, radius=3.0)
+    moved = _drifted(ps)
+    L = ps.grid_max[0]
+    owner1 = np.minimum((moved[:, 0] / (L / world)).astype(int), world - 1)
+    crossed = 0
+    for r in range(world):
+        owned = ret[r]["owned"]
+        # conservation and ownership: every particle is owned exactly once, by its new slab
+        assert sorted(owned.tolist()) == np.nonzero(owner1 == r)[0].tolist()
+        # payload integrity: coordinates travelled bit-exactly with their ids
+        assert np.array_equal(ret[r]["x"], moved[owned])
+        # staying elements come first (Cabana_Distributor.hpp: self is neighbour 0)
+        assert ret[r]["num_stay"] <= ret[r]["n0"]
+        crossed += ret[r]["n0"] - ret[r]["num_stay"]
+    assert crossed > 100, "the drift was meant to move particles across the slab face"
+    ox = orc.view_from_xyz(moved)
+    ref = orc.verlet_build(ox, 0, ps.n, ps.radius, 1.0, ps.grid_min, ps.grid_max, algo=orc.HALF)
+    merged = {}
+    for r in range(world):
+        merged.update(ret[r]["rows"])
+    assert len(merged) == ps.n
+    for i in range(ps.n):
+        assert merged[i] == sorted(int(v) for v in ref.row(i)), i
