@@ -31,7 +31,7 @@ NVCC_FLAGS = [
     "-ccbin", HOST_CXX,
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + os.environ.get("CB_NVCC_EXTRA", "").split()   # e.g. -DCB_ABLATE_EMIT for profiling ablations
 
 
 def _digest() -> str:

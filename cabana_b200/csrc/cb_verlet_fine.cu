@@ -204,6 +204,101 @@ CB_D void emit_row( const FineArgs& a, Reservation& rs, const unsigned* list,
     }
 }
 
+// Append the rows of one group of home particles (slots pg .. pg+kGroup-1, `active` bit per
+// row).  Everything that is a latency chain -- the four warp scans, the reservation, the
+// counts/offsets bookkeeping -- is done for the whole group up front so the chains overlap;
+// the rows then go through the shared-memory row buffer one after the other and land
+// back-to-back in the temporary buffer.  All lanes must call this.
+CB_D void emit_group( const FineArgs& a, Reservation& rs, const int* idbuf, int* rowbuf,
+                      unsigned lane, unsigned ( &hit )[kGroup], unsigned active, unsigned pg )
+{
+    int c[kGroup], inc[kGroup], tot[kGroup];
+#pragma unroll
+    for ( int p = 0; p < kGroup; ++p )
+    {
+        if ( !( ( active >> p ) & 1u ) )
+            hit[p] = 0u;
+        c[p] = __popc( hit[p] );
+        inc[p] = c[p];
+    }
+    // four independent inclusive scans, interleaved step by step
+#pragma unroll
+    for ( int o = 1; o < 32; o <<= 1 )
+    {
+#pragma unroll
+        for ( int p = 0; p < kGroup; ++p )
+        {
+            const int y = __shfl_up_sync( kFullMask, inc[p], o );
+            if ( (int)lane >= o )
+                inc[p] += y;
+        }
+    }
+#pragma unroll
+    for ( int p = 0; p < kGroup; ++p )
+        tot[p] = __shfl_sync( kFullMask, inc[p], 31 );
+    const int gtot = tot[0] + tot[1] + tot[2] + tot[3];
+    const long long at = reserve_ids( a, rs, gtot, lane );
+    // lanes 0..3 record (count, offset) of rows 0..3 in parallel
+    if ( lane < (unsigned)kGroup && ( ( active >> lane ) & 1u ) )
+    {
+        const int mytot = lane == 0 ? tot[0] : lane == 1 ? tot[1] : lane == 2 ? tot[2] : tot[3];
+        const int before = ( lane > 0 ? tot[0] : 0 ) + ( lane > 1 ? tot[1] : 0 ) +
+                           ( lane > 2 ? tot[2] : 0 );
+        const int pid = __float_as_int( a.q[pg + lane].w );
+        __stcs( &a.counts[pid], mytot );
+        __stcs( &a.tmp_off[pg + lane], (unsigned)( at + before ) );
+    }
+    if ( at + gtot > a.tmp_capacity )
+    {
+        if ( lane == 0 )
+            *a.overflow = 1; // the host grows the buffer to *cursor and reruns the pass
+        return;
+    }
+    long long row_at = at;
+#pragma unroll
+    for ( int p = 0; p < kGroup; ++p )
+    {
+        if ( !( ( active >> p ) & 1u ) )
+            continue; // (uniform)
+        unsigned hm = hit[p];
+        int wr = inc[p] - c[p];
+        if ( tot[p] <= kRowBuf )
+        {
+            __syncwarp();
+            {
+                const int* mine = idbuf + lane;
+                int* out = rowbuf + wr;
+#pragma unroll
+                for ( int it = 0; it < kIdBuf / 32; ++it )
+                {
+                    if ( hm & ( 1u << it ) )
+                        *out++ = mine[it * 32];
+                }
+            }
+            __syncwarp();
+            {
+                int* dst = a.tmp + row_at + lane;
+                const int* src = rowbuf + lane;
+                const int left = tot[p] - (int)lane;
+#pragma unroll
+                for ( int k = 0; k < kRowBuf / 32; ++k )
+                    if ( left > 32 * k )
+                        __stcs( dst + 32 * k, src[32 * k] );
+            }
+        }
+        else
+        {
+            while ( hm )
+            {
+                const int it = __ffs( hm ) - 1;
+                hm &= hm - 1;
+                a.tmp[row_at + wr++] = idbuf[it * 32 + (int)lane];
+            }
+        }
+        row_at += tot[p];
+    }
+}
+
 // Tier 1 test of one candidate (c) against home particle (xi,yi,zi): sets `bit` in hit/amb.
 template <bool HALF>
 CB_D void test_one( const float4& c, float xi, float yi, float zi, float t_lo, float t_hi,
@@ -539,8 +634,12 @@ __global__ void __launch_bounds__( kColBlock, 3 )
                 unsigned hit[kGroup] = { 0u, 0u, 0u, 0u };
                 unsigned amb = 0u; // candidates inside the FP32 band of ANY home particle
                 __syncwarp();
+#ifdef CB_ABLATE_TEST
+                hit[0] = list[t0 + lane] + __float_as_uint( xi[0] + yi[1] + zi[2] + xi[3] );
+#else
                 test_group<HALF, true>( np, a.q, list, idbuf, t0, t1, lane, sentinel, a.t_lo,
                                         a.t_hi, xi, yi, zi, hit, amb );
+#endif
                 __syncwarp();
 
                 // j != i: home particle pg+p sits at list position selfbase + (pg-h0) + p
@@ -565,10 +664,15 @@ __global__ void __launch_bounds__( kColBlock, 3 )
                                                           amb );
                 }
                 __syncwarp();
-#pragma unroll
-                for ( int p = 0; p < kGroup; ++p )
-                    if ( ( active >> p ) & 1u )
-                        emit_row( a, rs, list + t0, idbuf, rowbuf, lane, hit[p], pg + p );
+#ifdef CB_ABLATE_EMIT
+                {
+                    unsigned acc = hit[0] ^ hit[1] ^ hit[2] ^ hit[3];
+                    if ( acc == 0x12345678u )
+                        a.counts[0] = 1;
+                }
+#else
+                emit_group( a, rs, idbuf, rowbuf, lane, hit, active, pg );
+#endif
             }
         }
     }
