@@ -28,7 +28,10 @@
 //  * ONE test pass.  The reference counts, scans, then repeats every distance test to fill
 //    (:1454-1480).  Here each row is compacted through shared memory straight after its
 //    tests and appended to a temporary buffer in binned order (space reserved per warp
-//    with one atomic per 4096 ids); counts[] come out of the same pass.  After the offsets
+//    with one atomic per 4096 ids); counts[] come out of the same pass.  The rows of a
+//    group of four home particles are emitted together: interleaved warp scans, 16-bit
+//    list positions dropped into shared memory by a branch-free walk over the block bits,
+//    then one coalesced stream position -> id -> temporary buffer.  After the offsets
 //    scan a streaming kernel (k_reorder_rows) moves every row to its reference position
 //    (offsets = exclusive scan of counts in particle order, or row-major 2D).
 #include "cb_common.cuh"
@@ -42,7 +45,8 @@ namespace
 
 constexpr int kGroup = 4;      // home particles per register group
 constexpr int kReserve = 4096; // ids a warp reserves in the temporary buffer per atomic
-constexpr int kRowBuf = 128;   // ids compacted through shared memory per row
+constexpr int kRowBuf = 128;   // ids compacted through shared memory per row (general kernel)
+constexpr int kGroupBuf = 512; // list positions (u16) of all hits of one group of home particles
 constexpr int kIdBuf = 384;    // candidate ids of the current home cell kept in shared memory
 
 CB_D int warp_inclusive_scan( int v, unsigned lane )
@@ -137,80 +141,14 @@ CB_D long long reserve_ids( const FineArgs& a, Reservation& rs, int need, unsign
     return at;
 }
 
-// Append one home particle's hits (per-lane masks over `list`) to the temporary buffer:
-// lanes scatter their ids into a shared-memory row at their scanned positions, then the
-// warp streams the row out with coalesced stores.  All lanes must call this.
-CB_D void emit_row( const FineArgs& a, Reservation& rs, const unsigned* list,
-                    const int* idbuf, int* rowbuf, unsigned lane, unsigned hm,
-                    unsigned slot )
-{
-    const int c = __popc( hm );
-    const int inc = warp_inclusive_scan( c, lane );
-    const int tot = __shfl_sync( kFullMask, inc, 31 );
-    const long long at = reserve_ids( a, rs, tot, lane );
-    if ( lane == 0 )
-    {
-        // the row's particle id is re-read here (L1-resident) rather than held in a
-        // register across the test loop
-        const int pid = __float_as_int( a.q[slot].w );
-        __stcs( &a.counts[pid], tot );
-        __stcs( &a.tmp_off[slot], (unsigned)at );
-    }
-    if ( at + tot > a.tmp_capacity )
-    {
-        if ( lane == 0 )
-            *a.overflow = 1; // the host grows the buffer to *cursor and reruns the pass
-        return;
-    }
-    int wr = inc - c;
-    if ( tot <= kRowBuf )
-    {
-        __syncwarp();
-        // the candidates' ids were parked in shared memory by the test loop (they arrive
-        // in the float4's w): no global gather, no dependent-load chain.  Branch-free walk
-        // over the iteration bits (predicated load/store/bump, immediate offsets) instead of
-        // a data-dependent loop whose trip count is the MAXIMUM hit count over the lanes.
-        {
-            const int* mine = idbuf + lane;
-            int* out = rowbuf + wr;
-#pragma unroll
-            for ( int it = 0; it < kIdBuf / 32; ++it )
-            {
-                if ( hm & ( 1u << it ) )
-                    *out++ = mine[it * 32];
-            }
-        }
-        __syncwarp();
-        // streaming stores: the rows are not read again by this kernel and must not evict
-        // the candidate positions from L1
-        {
-            int* dst = a.tmp + at + lane;
-            const int* src = rowbuf + lane;
-            const int left = tot - (int)lane;
-#pragma unroll
-            for ( int k = 0; k < kRowBuf / 32; ++k )
-                if ( left > 32 * k )
-                    __stcs( dst + 32 * k, src[32 * k] );
-        }
-    }
-    else
-    {
-        while ( hm )
-        {
-            const int it = __ffs( hm ) - 1;
-            hm &= hm - 1;
-            a.tmp[at + wr++] = idbuf[it * 32 + (int)lane];
-        }
-    }
-}
-
 // Append the rows of one group of home particles (slots pg .. pg+kGroup-1, `active` bit per
 // row).  Everything that is a latency chain -- the four warp scans, the reservation, the
 // counts/offsets bookkeeping -- is done for the whole group up front so the chains overlap;
 // the rows then go through the shared-memory row buffer one after the other and land
 // back-to-back in the temporary buffer.  All lanes must call this.
-CB_D void emit_group( const FineArgs& a, Reservation& rs, const int* idbuf, int* rowbuf,
-                      unsigned lane, unsigned ( &hit )[kGroup], unsigned active, unsigned pg )
+CB_D void emit_group( const FineArgs& a, Reservation& rs, const int* idbuf,
+                      unsigned short* rowbuf, unsigned lane, unsigned ( &hit )[kGroup],
+                      unsigned active, unsigned pg )
 {
     int c[kGroup], inc[kGroup], tot[kGroup];
 #pragma unroll
@@ -254,48 +192,57 @@ CB_D void emit_group( const FineArgs& a, Reservation& rs, const int* idbuf, int*
             *a.overflow = 1; // the host grows the buffer to *cursor and reruns the pass
         return;
     }
-    long long row_at = at;
-#pragma unroll
-    for ( int p = 0; p < kGroup; ++p )
+    if ( gtot <= kGroupBuf )
     {
-        if ( !( ( active >> p ) & 1u ) )
-            continue; // (uniform)
-        unsigned hm = hit[p];
-        int wr = inc[p] - c[p];
-        if ( tot[p] <= kRowBuf )
+        // Phase 1: every lane drops the LIST POSITIONS of its hits (16 bits each) at their
+        // scanned places; the four rows sit back to back, exactly as in the temporary
+        // buffer.  Branch-free walk over the block bits, four independent chains.
+        __syncwarp();
+        int base = 0;
+#pragma unroll
+        for ( int p = 0; p < kGroup; ++p )
         {
-            __syncwarp();
-            {
-                const int* mine = idbuf + lane;
-                int* out = rowbuf + wr;
+            unsigned short* out = rowbuf + base + ( inc[p] - c[p] );
+            const unsigned hm = hit[p];
 #pragma unroll
-                for ( int it = 0; it < kIdBuf / 32; ++it )
-                {
-                    if ( hm & ( 1u << it ) )
-                        *out++ = mine[it * 32];
-                }
-            }
-            __syncwarp();
+            for ( int it = 0; it < kIdBuf / 32; ++it )
             {
-                int* dst = a.tmp + row_at + lane;
-                const int* src = rowbuf + lane;
-                const int left = tot[p] - (int)lane;
-#pragma unroll
-                for ( int k = 0; k < kRowBuf / 32; ++k )
-                    if ( left > 32 * k )
-                        __stcs( dst + 32 * k, src[32 * k] );
+                if ( hm & ( 1u << it ) )
+                    *out++ = (unsigned short)( it * 32 + (int)lane );
             }
+            base += tot[p];
         }
-        else
+        __syncwarp();
+        // Phase 2: one coalesced stream for the whole group: position -> id (the ids were
+        // parked in shared memory by the test loop) -> temporary buffer
+        int* dst = a.tmp + at + lane;
+        const unsigned short* src = rowbuf + lane;
+        for ( int i0 = 0; i0 < gtot; i0 += 128 )
         {
+            const int left = gtot - i0 - (int)lane;
+#pragma unroll
+            for ( int k = 0; k < 4; ++k )
+                if ( left > 32 * k )
+                    __stcs( dst + i0 + 32 * k, idbuf[src[i0 + 32 * k]] );
+        }
+    }
+    else
+    {
+        // very long rows: straight to global memory
+        long long row_at = at;
+#pragma unroll
+        for ( int p = 0; p < kGroup; ++p )
+        {
+            unsigned hm = hit[p];
+            int wr = inc[p] - c[p];
             while ( hm )
             {
                 const int it = __ffs( hm ) - 1;
                 hm &= hm - 1;
                 a.tmp[row_at + wr++] = idbuf[it * 32 + (int)lane];
             }
+            row_at += tot[p];
         }
-        row_at += tot[p];
     }
 }
 
@@ -422,6 +369,9 @@ constexpr int kColBlock = kColWarps * 32;
 constexpr int kColCap = 896;  // list entries per warp (static shared memory <= 48 KB)
 constexpr int kChunk = 8;     // home cells per work item
 constexpr int kMaxLayers = kChunk + 2 * 8 + 1;
+constexpr int kColWarpSmem =
+    ( ( kColCap + kIdBuf + 3 * kMaxLayers + 2 ) * 4 + kGroupBuf * 2 + 15 ) / 16 * 16;
+constexpr int kColSmem = kColWarps * kColWarpSmem;
 
 CB_D void push_overflow( const FineArgs& a, unsigned cell, unsigned lane )
 {
@@ -433,20 +383,16 @@ template <bool HALF>
 __global__ void __launch_bounds__( kColBlock, 3 )
     k_verlet_column( const __grid_constant__ FineArgs a )
 {
-    __shared__ unsigned s_list[kColWarps][kColCap];
-    __shared__ int s_row[kColWarps][kRowBuf];
-    __shared__ int s_id[kColWarps][kIdBuf];
-    __shared__ int s_layer[kColWarps][kMaxLayers + 1];
-    __shared__ int s_home[kColWarps][kMaxLayers];
-    __shared__ unsigned s_hoff[kColWarps][kMaxLayers + 1];
+    // per-warp shared memory (dynamic: 8 warps x 6.4 KB > 48 KB)
+    extern __shared__ __align__( 16 ) unsigned char s_dyn[];
     const unsigned lane = threadIdx.x & 31u;
     const int wib = threadIdx.x >> 5;
-    unsigned* list = s_list[wib];
-    int* rowbuf = s_row[wib];
-    int* idbuf = s_id[wib];
-    int* layer = s_layer[wib];
-    int* homepos = s_home[wib];
-    unsigned* homeoff = s_hoff[wib];
+    unsigned* list = reinterpret_cast<unsigned*>( s_dyn + (size_t)wib * kColWarpSmem );
+    int* idbuf = reinterpret_cast<int*>( list + kColCap );
+    int* layer = idbuf + kIdBuf;
+    int* homepos = layer + ( kMaxLayers + 1 );
+    unsigned* homeoff = reinterpret_cast<unsigned*>( homepos + kMaxLayers );
+    unsigned short* rowbuf = reinterpret_cast<unsigned short*>( homeoff + ( kMaxLayers + 1 ) );
     Reservation rs;
     const int nxf = a.nf[0], nyf = a.nf[1], nzf = a.nf[2];
     const int lgm = a.lgm, R = a.R;
@@ -951,20 +897,30 @@ int launch_fine_single( const FineArgs& a, int algorithm, cudaStream_t stream )
         {
             int nb = 0;
             if ( half )
+            {
+                CB_CUDA( cudaFuncSetAttribute( k_verlet_column<true>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               kColSmem ) );
                 CB_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                    &nb, k_verlet_column<true>, kColBlock, 0 ) );
+                    &nb, k_verlet_column<true>, kColBlock, kColSmem ) );
+            }
             else
+            {
+                CB_CUDA( cudaFuncSetAttribute( k_verlet_column<false>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               kColSmem ) );
                 CB_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                    &nb, k_verlet_column<false>, kColBlock, 0 ) );
+                    &nb, k_verlet_column<false>, kColBlock, kColSmem ) );
+            }
             per_sm[half] = nb > 0 ? nb : 1;
         }
         const long long cap = (long long)kNumSMs * per_sm[half];
         if ( blocks > cap )
             blocks = cap;
         if ( half )
-            k_verlet_column<true><<<(int)blocks, kColBlock, 0, stream>>>( a );
+            k_verlet_column<true><<<(int)blocks, kColBlock, kColSmem, stream>>>( a );
         else
-            k_verlet_column<false><<<(int)blocks, kColBlock, 0, stream>>>( a );
+            k_verlet_column<false><<<(int)blocks, kColBlock, kColSmem, stream>>>( a );
         CB_CHECK_LAUNCH();
     }
     // General kernel: everything (no worklist) or the column kernel's leftovers.  The
