@@ -159,16 +159,30 @@ CB_D void emit_group( const FineArgs& a, Reservation& rs, const int* idbuf,
         c[p] = __popc( hit[p] );
         inc[p] = c[p];
     }
-    // four independent inclusive scans, interleaved step by step
+    // independent inclusive scans, interleaved step by step (rows 2,3 only if present)
 #pragma unroll
     for ( int o = 1; o < 32; o <<= 1 )
     {
 #pragma unroll
-        for ( int p = 0; p < kGroup; ++p )
+        for ( int p = 0; p < 2; ++p )
         {
             const int y = __shfl_up_sync( kFullMask, inc[p], o );
             if ( (int)lane >= o )
                 inc[p] += y;
+        }
+    }
+    if ( active > 3u )
+    {
+#pragma unroll
+        for ( int o = 1; o < 32; o <<= 1 )
+        {
+#pragma unroll
+            for ( int p = 2; p < kGroup; ++p )
+            {
+                const int y = __shfl_up_sync( kFullMask, inc[p], o );
+                if ( (int)lane >= o )
+                    inc[p] += y;
+            }
         }
     }
 #pragma unroll
@@ -202,6 +216,8 @@ CB_D void emit_group( const FineArgs& a, Reservation& rs, const int* idbuf,
 #pragma unroll
         for ( int p = 0; p < kGroup; ++p )
         {
+            if ( tot[p] == 0 )
+                continue; // (uniform) absent or empty row
             unsigned short* out = rowbuf + base + ( inc[p] - c[p] );
             const unsigned hm = hit[p];
 #pragma unroll
