@@ -393,6 +393,28 @@ def run_ours(args):
                "d2h_bytes_per_step": int(4 * (2 * num_local + lst.total)),
                "api": "cb_verlet_build_host + cb_verlet_copy_to_host (pinned host buffers)"}
 
+    # ---- informational: the same build with CB_ROWS_BINNED (rows stay in cell order; no
+    # offsets scan / reorder pass).  NOT the headline: `value` above is the reference layout.
+    binned = None
+    if world == 1 and layout == cb.CSR:
+        lst_b = cb.VerletList(algorithm=algo, layout=layout, row_placement=cb.ROWS_BINNED)
+        for _ in range(max(args.warmup, 2)):
+            lst_b.build(x, 0, num_local, radius, CELL_RATIO, gmin, gmax)
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b_steps = max(1, min(args.steps, 10))
+        b0.record()
+        for _ in range(b_steps):
+            lst_b.build(x, 0, num_local, radius, CELL_RATIO, gmin, gmax)
+        b1.record()
+        torch.cuda.synchronize()
+        b_ms = b0.elapsed_time(b1) / b_steps
+        assert lst_b.total == lst.total
+        binned = {"ms_per_step": b_ms, "value": lst_b.total / (b_ms * 1e-3), "unit": UNIT,
+                  "note": "opt-in cb_verlet_set_row_placement(CB_ROWS_BINNED): same neighbour sets, "
+                          "rows left in cell order inside `neighbors` (offsets not monotone)"}
+        del lst_b
+
     if world > 1 and os.environ.get("CB_BENCH_TRACE") == "1":
         sys.stderr.write("rank %d trace (ms/step): plan %.3f gather %.3f build %.3f\n" % (
             rank, 1e3 * tr["plan"] / max(tr["n"], 1), 1e3 * tr["gather"] / max(tr["n"], 1),
@@ -417,6 +439,7 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "e2e": e2e,
+        "binned_rows": binned,
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

@@ -18,6 +18,7 @@ CB_OK, CB_ERR_INVALID, CB_ERR_CUDA, CB_ERR_OVERFLOW, CB_ERR_UNSUPPORTED, CB_ERR_
 FULL, HALF = 0, 1
 CSR, LAYOUT_2D = 0, 1
 OP_SERIAL, OP_TEAM, OP_TEAM_VECTOR = 0, 1, 2
+ROWS_REFERENCE, ROWS_BINNED = 0, 1
 
 
 class Positions(C.Structure):
@@ -82,6 +83,7 @@ class VerletView(C.Structure):
         ("row_stride", C.c_int64),
         ("col_stride", C.c_int64),
         ("refilled", C.c_int32),
+        ("extent", C.c_int64),
     ]
 
 

@@ -15,7 +15,8 @@ import numpy as np
 import torch
 
 from . import capi
-from .capi import CSR, FULL, HALF, LAYOUT_2D, OP_SERIAL, OP_TEAM, OP_TEAM_VECTOR  # noqa: F401
+from .capi import (CSR, FULL, HALF, LAYOUT_2D, OP_SERIAL, OP_TEAM, OP_TEAM_VECTOR,  # noqa: F401
+                   ROWS_BINNED, ROWS_REFERENCE)
 
 
 def _stream() -> C.c_void_p:
@@ -235,10 +236,15 @@ class VerletList:
 
     def __init__(self, x: Slice | None = None, begin=None, end=None, neighborhood_radius=None,
                  cell_size_ratio=None, grid_min=None, grid_max=None, max_neigh=0, *,
-                 algorithm=FULL, layout=CSR, build_tag=OP_TEAM_VECTOR):
+                 algorithm=FULL, layout=CSR, build_tag=OP_TEAM_VECTOR, row_placement=ROWS_REFERENCE):
         self.algorithm, self.layout, self.build_tag = algorithm, layout, build_tag
         self._h = C.c_void_p()
         capi.check(capi.lib().cb_verlet_create(C.byref(self._h)))
+        # ROWS_BINNED: CSR rows stay in cell order (no offsets scan / reorder pass); see
+        # cb_verlet_set_row_placement in include/cabana_b200.h
+        self.row_placement = row_placement
+        if row_placement != ROWS_REFERENCE:
+            capi.check(capi.lib().cb_verlet_set_row_placement(self._h, C.c_int(row_placement)))
         self._data = VerletListData()
         if x is not None:
             self.build(x, begin, end, neighborhood_radius, cell_size_ratio, grid_min, grid_max, max_neigh)
@@ -291,12 +297,13 @@ class VerletList:
         d.counts = _as_tensor(v.counts, (v.n,), "<i4", torch.int32, self)
         if v.layout == CSR:
             d.offsets = _as_tensor(v.offsets, (v.n,), "<i4", torch.int32, self)
-            d.neighbors = _as_tensor(v.neighbors, (v.total,), "<i4", torch.int32, self)
+            d.neighbors = _as_tensor(v.neighbors, (v.extent,), "<i4", torch.int32, self)
         else:
             d.offsets = None
             d.neighbors = _as_tensor(v.neighbors, (v.n, v.width), "<i4", torch.int32, self)
         d.max_n = int(v.max_n)
         self.total = int(v.total)
+        self.extent = int(v.extent)
         self.width = int(v.width)
         self.refilled = bool(v.refilled)
 

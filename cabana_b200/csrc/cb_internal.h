@@ -52,6 +52,16 @@ struct DeviceBuffer
     DeviceBuffer& operator=( const DeviceBuffer& ) = delete;
     ~DeviceBuffer() { release(); }
 
+    void swap( DeviceBuffer& o )
+    {
+        void* p = ptr;
+        ptr = o.ptr;
+        o.ptr = p;
+        const size_t c = capacity;
+        capacity = o.capacity;
+        o.capacity = c;
+    }
+
     // Ensure at least `bytes`; contents are NOT preserved on growth.
     int ensure( size_t bytes, double growth = 1.0 )
     {

@@ -255,7 +255,9 @@ struct cb_verlet
     long long total = 0;
     long long max_n = 0;
     long long width = 0;
+    long long extent = 0;
     int refilled = 0;
+    int row_placement = CB_ROWS_REFERENCE;
     bool built = false;
     DeviceBuffer counts, offsets, neighbors;
     // workspace
@@ -562,6 +564,8 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
             CB_TRY( v->tmp.ensure( sizeof( int ) * (size_t)est ) );
         }
         fa.tmp_off = v->tmp_off.as<unsigned>();
+        const bool binned_rows = v->row_placement == CB_ROWS_BINNED && layout == CB_LAYOUT_CSR;
+        fa.offsets_direct = binned_rows ? v->offsets.as<int>() : nullptr;
         fa.cursor = reinterpret_cast<unsigned long long*>( v->ctrl.as<char>() );
         fa.overflow = reinterpret_cast<int*>( v->ctrl.as<char>() + 8 );
         for ( int attempt = 0;; ++attempt )
@@ -572,7 +576,7 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
             CB_TRY( launch_fine_single( fa, algorithm, stream ) );
             v->mark( 3, stream );
             CB_TRY( max_and_sum_i32( v->counts.as<int>(), n, stats_dev, stream ) );
-            if ( layout == CB_LAYOUT_CSR )
+            if ( layout == CB_LAYOUT_CSR && !binned_rows )
                 CB_TRY( exclusive_scan_i32( v->counts.as<int>(), v->offsets.as<int>(), n,
                                             false, nullptr, v->scan, stream ) );
             CB_CUDA( cudaMemcpyAsync( stats_h, stats_dev, 2 * sizeof( long long ),
@@ -590,6 +594,21 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
         }
         v->max_n = stats_h[0];
         v->total = stats_h[1];
+        if ( binned_rows )
+        {
+            // the temporary buffer IS the neighbour array: offsets[pid] were written by the
+            // test pass; rows outside [begin,end) keep count 0 (their offsets are unused)
+            if ( stats_h[2] > 2147483647ll )
+                return fail( CB_ERR_OVERFLOW,
+                             "cb_verlet_build: neighbour array exceeds INT_MAX entries" );
+            v->neighbors.swap( v->tmp );
+            v->extent = stats_h[2] > 0 ? stats_h[2] : 0;
+            v->width = 0;
+            v->mark( 5, stream );
+            v->built = true;
+            return CB_OK;
+        }
+        v->extent = v->total;
         if ( layout == CB_LAYOUT_CSR )
         {
             if ( v->total > 2147483647ll )
@@ -641,6 +660,7 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
         CB_CUDA( cudaStreamSynchronize( stream ) ); // sizes the allocation (:518-528)
         v->max_n = stats_h[0];
         v->total = stats_h[1];
+        v->extent = v->total;
         if ( v->total > 2147483647ll )
             return fail( CB_ERR_OVERFLOW,
                          "cb_verlet_build: total neighbours exceed INT_MAX" );
@@ -676,6 +696,7 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
         CB_CUDA( cudaStreamSynchronize( stream ) );
         v->max_n = stats_h[0];
         v->total = stats_h[1];
+        v->extent = v->total;
         if ( count || v->max_n > v->width )
         {
             v->width = v->max_n;
@@ -747,6 +768,15 @@ extern "C" int cb_verlet_get( const cb_verlet* v, cb_verlet_view* view )
     view->row_stride = v->layout == CB_LAYOUT_2D ? v->width : 0;
     view->col_stride = v->layout == CB_LAYOUT_2D ? 1 : 0;
     view->refilled = v->refilled;
+    view->extent = v->layout == CB_LAYOUT_CSR ? v->extent : 0;
+    return CB_OK;
+}
+
+extern "C" int cb_verlet_set_row_placement( cb_verlet* v, int placement )
+{
+    if ( !v || ( placement != CB_ROWS_REFERENCE && placement != CB_ROWS_BINNED ) )
+        return fail( CB_ERR_INVALID, "cb_verlet_set_row_placement: bad argument" );
+    v->row_placement = placement;
     return CB_OK;
 }
 
@@ -804,7 +834,7 @@ extern "C" int cb_verlet_copy_to_host( const cb_verlet* v, int32_t* counts_h,
         return fail( CB_ERR_INVALID, "cb_verlet_copy_to_host: list not built" );
     cudaStream_t stream = (cudaStream_t)stream_;
     const long long nn =
-        v->layout == CB_LAYOUT_CSR ? v->total : v->n * v->width;
+        v->layout == CB_LAYOUT_CSR ? v->extent : v->n * v->width;
     if ( neighbors_h && neighbors_capacity < nn )
         return fail( CB_ERR_NOMEM, "cb_verlet_copy_to_host: neighbors_h too small" );
     if ( counts_h && v->n > 0 )

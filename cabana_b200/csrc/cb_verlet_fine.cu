@@ -198,7 +198,10 @@ CB_D void emit_group( const FineArgs& a, Reservation& rs, const int* idbuf,
                            ( lane > 2 ? tot[2] : 0 );
         const int pid = __float_as_int( a.q[pg + lane].w );
         __stcs( &a.counts[pid], mytot );
-        __stcs( &a.tmp_off[pg + lane], (unsigned)( at + before ) );
+        if ( a.offsets_direct )
+            __stcs( &a.offsets_direct[pid], (int)( at + before ) );
+        else
+            __stcs( &a.tmp_off[pg + lane], (unsigned)( at + before ) );
     }
     if ( at + gtot > a.tmp_capacity )
     {
@@ -724,7 +727,10 @@ __global__ void __launch_bounds__( kBlock, 3 )
                             if ( lane == 0 )
                             {
                                 a.counts[pid[p]] = tot;
-                                a.tmp_off[pg + p] = (unsigned)at[p];
+                                if ( a.offsets_direct )
+                                    a.offsets_direct[pid[p]] = (int)at[p];
+                                else
+                                    a.tmp_off[pg + p] = (unsigned)at[p];
                             }
                             if ( at[p] + tot > a.tmp_capacity )
                                 fits = false;

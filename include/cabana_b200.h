@@ -223,6 +223,8 @@ typedef struct
     int64_t row_stride; /* 2D element (i,k) = neighbors[i*row_stride + k*col_stride] */
     int64_t col_stride;
     int32_t refilled;   /* 2D with max_neigh: 1 if the realloc+refill path ran (:554-561) */
+    int64_t extent;     /* neighbors.extent(0) (CSR): == total with reference row placement,
+                           >= total with CB_ROWS_BINNED (rows are not packed) */
 } cb_verlet_view;
 
 int cb_verlet_create(cb_verlet** out);
@@ -232,6 +234,18 @@ int cb_verlet_build(cb_verlet* list, const cb_positions* x, int64_t begin,
                     const double* grid_max_h, int64_t max_neigh, int algorithm,
                     int layout, int build_op, cb_stream_t stream);
 int cb_verlet_get(const cb_verlet* list, cb_verlet_view* view_h);
+/* Where the CSR rows live inside `neighbors` (set before cb_verlet_build; 2D lists ignore it).
+ *   CB_ROWS_REFERENCE (default): offsets = exclusive scan of counts in particle order, rows
+ *       packed, exactly the reference's arrays (Cabana_VerletList.hpp:478-491, :507-532).
+ *   CB_ROWS_BINNED: rows stay where the single test pass wrote them (cell order, small gaps
+ *       between warps' reservations); offsets[i] is still the start of row i, so everything
+ *       that goes through NeighborList<>::getNeighbor / neighbor_parallel_for is unchanged
+ *       (the reference leaves row placement to the implementation: rows are claimed with an
+ *       atomic, :69-70), but offsets is not monotone and neighbors.extent(0) > total.  Saves
+ *       the offsets scan and the row-reorder pass (~23 % of a build). */
+#define CB_ROWS_REFERENCE 0
+#define CB_ROWS_BINNED 1
+int cb_verlet_set_row_placement(cb_verlet* list, int placement);
 /* setNeighbor(particle, neighbor, new_index) :1488-1494 */
 int cb_verlet_set_neighbor(cb_verlet* list, int64_t particle_index,
                            int64_t neighbor_index, int32_t new_index,

@@ -379,3 +379,45 @@ def test_fcc_16m_properties(cb):
     half = cb.VerletList(x, 0, ps.n, ps.radius, 1.0, ps.grid_min, ps.grid_max,
                          algorithm=cb.HALF, layout=cb.CSR)
     assert 2 * half.total == total_full
+
+
+# ------------------------------------------------------------- CB_ROWS_BINNED (opt-in placement)
+@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("case", ["fcc", "uniform", "partial"])
+def test_binned_row_placement_same_sets(cb, orc, algo, case):
+    """Rows left where the single test pass wrote them: identical counts and neighbour SETS,
+    rows disjoint inside `neighbors`, LJ traversal identical to the reference placement."""
+    if case == "fcc":
+        ps = datasets.fcc_lattice(14, jitter=0.04)
+        b, e = 0, ps.n
+    elif case == "uniform":
+        ps = datasets.uniform_box(30000, 99)
+        b, e = 0, ps.n
+    else:
+        ps = datasets.uniform_box(20000, 98)
+        b, e = 3000, 17000
+    x = cb.slice_from_array(ps.xyz, vlen=32)
+    ref = orc.verlet_build(orc.view_from_xyz(ps.xyz), b, e, ps.radius, 1.0, ps.grid_min, ps.grid_max,
+                           algo=orc.FULL if algo == 0 else orc.HALF)
+    lst = cb.VerletList(x, b, e, ps.radius, 1.0, ps.grid_min, ps.grid_max, algorithm=algo, layout=cb.CSR,
+                        row_placement=cb.ROWS_BINNED)
+    _assert_list_equal(orc, lst, ref, check_offsets=False)
+    counts, offsets, nb = _gpu_rows(orc, lst)
+    assert lst.extent >= lst.total and nb.shape[0] == lst.extent
+    # rows are disjoint intervals of the neighbour array
+    rows = np.nonzero(counts > 0)[0]
+    order = rows[np.argsort(offsets[rows])]
+    starts, ends = offsets[order].astype(np.int64), offsets[order].astype(np.int64) + counts[order]
+    assert np.all(starts[1:] >= ends[:-1]) and ends[-1] <= lst.extent
+    # a rebuild (buffers swap roles) gives the same sets again
+    lst.build(x, b, e, ps.radius, 1.0, ps.grid_min, ps.grid_max)
+    _assert_list_equal(orc, lst, ref, check_offsets=False)
+    # traversal through offsets[i] is placement-agnostic: same forces, bit for bit per row order
+    lst_ref = cb.VerletList(x, b, e, ps.radius, 1.0, ps.grid_min, ps.grid_max, algorithm=algo, layout=cb.CSR)
+    f1 = cb.view_from_array(np.zeros((ps.n, 3)))
+    f2 = cb.view_from_array(np.zeros((ps.n, 3)))
+    cb.neighbor_parallel_for_lj(b, e, lst, x, f1, 1.0, 1.0, 2.5, cb.OP_TEAM if algo == 1 else cb.OP_SERIAL)
+    cb.neighbor_parallel_for_lj(b, e, lst_ref, x, f2, 1.0, 1.0, 2.5, cb.OP_TEAM if algo == 1 else cb.OP_SERIAL)
+    a1, a2 = f1.to_array().cpu().numpy(), f2.to_array().cpu().numpy()
+    scale = np.abs(a2).max() + 1.0
+    assert np.max(np.abs(a1 - a2)) <= 1e-12 * scale
