@@ -415,6 +415,31 @@ def run_ours(args):
                           "rows left in cell order inside `neighbors` (offsets not monotone)"}
         del lst_b
 
+    # ---- informational: LJ neighbor_parallel_for over the list just built (SURVEY.md 8d
+    # "t_traverse"), thread-per-particle and warp-per-particle
+    traverse = None
+    if world == 1:
+        traverse = {}
+        f = cb.view_from_array(np.zeros((num_local, 3)))
+        for name, op in (("serial", cb.OP_SERIAL), ("team", cb.OP_TEAM)):
+            for _ in range(2):
+                cb.neighbor_parallel_for_lj(0, num_local, lst, x, f, 1.0, 1.0, 2.5, op)
+            torch.cuda.synchronize()
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_steps = 5
+            t0e.record()
+            for _ in range(t_steps):
+                cb.neighbor_parallel_for_lj(0, num_local, lst, x, f, 1.0, 1.0, 2.5, op)
+            t1e.record()
+            torch.cuda.synchronize()
+            t_ms = t0e.elapsed_time(t1e) / t_steps
+            # worst-case algorithmic bytes: ids 4 K_s + x_i 24 + gathered x_j 24 K_s + f_i 24
+            t_bytes = num_local * (48.0 + 28.0 * (lst.total / max(num_local, 1)))
+            traverse[name] = {"ms": t_ms, "neighbors_per_s": lst.total / (t_ms * 1e-3),
+                              "worst_case_gbs": t_bytes / (t_ms * 1e-3) / 1e9,
+                              "frac_of_hbm_peak": t_bytes / (t_ms * 1e-3) / 1e9 / peak}
+        del f
+
     if world > 1 and os.environ.get("CB_BENCH_TRACE") == "1":
         sys.stderr.write("rank %d trace (ms/step): plan %.3f gather %.3f build %.3f\n" % (
             rank, 1e3 * tr["plan"] / max(tr["n"], 1), 1e3 * tr["gather"] / max(tr["n"], 1),
@@ -440,6 +465,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "e2e": e2e,
         "binned_rows": binned,
+        "lj_traverse": traverse,
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

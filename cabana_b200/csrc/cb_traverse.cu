@@ -63,9 +63,12 @@ CB_D void lj_pair( const LJ& p, double dx, double dy, double dz, double& fx, dou
     within = r2 < p.rc2;
     if ( within )
     {
-        const double sr2 = p.s2 / r2;
+        // one FP64 reciprocal instead of two divisions (the kernel is bound by the FP64
+        // pipe); differs from s2/r2, fpair/r2 by an ulp or two, far inside the 1e-12 bar
+        const double inv = 1.0 / r2;
+        const double sr2 = p.s2 * inv;
         const double sr6 = sr2 * sr2 * sr2;
-        const double fpair = p.eps24 * sr6 * ( 2.0 * sr6 - 1.0 ) / r2;
+        const double fpair = p.eps24 * sr6 * ( 2.0 * sr6 - 1.0 ) * inv;
         fx = fpair * dx;
         fy = fpair * dy;
         fz = fpair * dz;
@@ -89,20 +92,60 @@ CB_D void add3( double* base, long long off, long long cs, double fx, double fy,
     }
 }
 
+// x_j is a random gather.  In an AoSoA slice the three components of one particle sit in
+// three different 32-byte sectors; the LJ kernels therefore read a packed copy
+// (x, y, z, pad: exactly one sector per particle) made by k_pack_positions right before
+// the traversal (one coalesced pass, 56 B per particle).  The values are the same doubles,
+// so every pair force is bit-identical to reading the slice.
+struct Packed
+{
+    const double2* p;
+    CB_D void get( long long j, double& x, double& y, double& z ) const
+    {
+        // one 256-bit load (sm_100 LDG.E.256): ONE sector lookup per gathered particle --
+        // the traversal is bound by L1 tag lookups of the gathers, not by bytes
+        double pad;
+        asm( "ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+             : "=d"( x ), "=d"( y ), "=d"( z ), "=d"( pad )
+             : "l"( p + 2 * j ) );
+        (void)pad;
+    }
+};
+
+__global__ void __launch_bounds__( kBlock )
+    k_pack_positions( PosAccess x, long long n, double2* out )
+{
+    for ( long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n;
+          i += (long long)gridDim.x * kBlock )
+    {
+        const long long o = x.offset( i );
+        out[2 * i] = make_double2( x.base[o], x.base[o + x.comp_stride] );
+        out[2 * i + 1] = make_double2( x.base[o + 2 * x.comp_stride], 0.0 );
+    }
+}
+
+constexpr int kTeam = 8; // lanes per particle in the Team kernels (4 particles per warp)
+
+CB_D double team_reduce_sum( double v )
+{
+#pragma unroll
+    for ( int o = kTeam / 2; o > 0; o >>= 1 )
+        v += __shfl_xor_sync( kFullMask, v, o );
+    return v;
+}
+
 // Serial: Cabana_Parallel.hpp:280-288
 template <bool NEWTON>
 __global__ void __launch_bounds__( kBlock )
-    k_lj_serial( ListAccess l, PosAccess x, FieldAccess f, LJ p, long long begin,
+    k_lj_serial( ListAccess l, Packed x, FieldAccess f, LJ p, long long begin,
                  long long end )
 {
     double* fb = reinterpret_cast<double*>( f.base );
     for ( long long i = begin + (long long)blockIdx.x * kBlock + threadIdx.x; i < end;
           i += (long long)gridDim.x * kBlock )
     {
-        const long long xo = x.offset( i );
-        const double xi = x.base[xo];
-        const double yi = x.base[xo + x.comp_stride];
-        const double zi = x.base[xo + 2 * x.comp_stride];
+        double xi, yi, zi;
+        x.get( i, xi, yi, zi );
         const int nn = l.num( i );
         const long long row = l.row( i );
         const long long step = l.step();
@@ -110,11 +153,11 @@ __global__ void __launch_bounds__( kBlock )
         for ( int n = 0; n < nn; ++n )
         {
             const long long j = l.neighbors[row + n * step];
-            const long long jo = x.offset( j );
+            double xj, yj, zj;
+            x.get( j, xj, yj, zj );
             double fx, fy, fz;
             bool within;
-            lj_pair( p, xi - x.base[jo], yi - x.base[jo + x.comp_stride],
-                     zi - x.base[jo + 2 * x.comp_stride], fx, fy, fz, within );
+            lj_pair( p, xi - xj, yi - yj, zi - zj, fx, fy, fz, within );
             if ( within )
             {
                 ax += fx;
@@ -128,47 +171,54 @@ __global__ void __launch_bounds__( kBlock )
     }
 }
 
-// Team: Cabana_Parallel.hpp:416-430 -- one warp per particle.
+// Team: Cabana_Parallel.hpp:416-430 -- a team of kTeam lanes per particle (rows of ~50-80
+// neighbours would leave most of a full warp idle and pay a 32-lane reduction each).
 template <bool NEWTON>
 __global__ void __launch_bounds__( kBlock )
-    k_lj_team( ListAccess l, PosAccess x, FieldAccess f, LJ p, long long begin,
+    k_lj_team( ListAccess l, Packed x, FieldAccess f, LJ p, long long begin,
                long long end )
 {
     double* fb = reinterpret_cast<double*>( f.base );
-    const unsigned lane = lane_id();
-    const long long warp = ( (long long)blockIdx.x * kBlock + threadIdx.x ) >> 5;
-    const long long nwarps = ( (long long)gridDim.x * kBlock ) >> 5;
-    for ( long long i = begin + warp; i < end; i += nwarps )
+    const unsigned sub = threadIdx.x & ( kTeam - 1 );
+    const long long team = ( (long long)blockIdx.x * kBlock + threadIdx.x ) / kTeam;
+    const long long nteams = ( (long long)gridDim.x * kBlock ) / kTeam;
+    // whole warps iterate together (the team reduction is a full-mask shuffle)
+    const long long span = end - begin;
+    const long long rounds = ( span + nteams - 1 ) / nteams;
+    for ( long long r = 0; r < rounds; ++r )
     {
-        const long long xo = x.offset( i );
-        const double xi = x.base[xo];
-        const double yi = x.base[xo + x.comp_stride];
-        const double zi = x.base[xo + 2 * x.comp_stride];
-        const int nn = l.num( i );
-        const long long row = l.row( i );
-        const long long step = l.step();
+        const long long i = begin + r * nteams + team;
+        const bool live = i < end;
         double ax = 0.0, ay = 0.0, az = 0.0;
-        for ( int n = (int)lane; n < nn; n += 32 )
+        if ( live )
         {
-            const long long j = l.neighbors[row + n * step];
-            const long long jo = x.offset( j );
-            double fx, fy, fz;
-            bool within;
-            lj_pair( p, xi - x.base[jo], yi - x.base[jo + x.comp_stride],
-                     zi - x.base[jo + 2 * x.comp_stride], fx, fy, fz, within );
-            if ( within )
+            double xi, yi, zi;
+            x.get( i, xi, yi, zi );
+            const int nn = l.num( i );
+            const long long row = l.row( i );
+            const long long step = l.step();
+            for ( int n = (int)sub; n < nn; n += kTeam )
             {
-                ax += fx;
-                ay += fy;
-                az += fz;
-                if ( NEWTON )
-                    add3( fb, f.offset( j ), f.comp_stride, -fx, -fy, -fz, true );
+                const long long j = l.neighbors[row + n * step];
+                double xj, yj, zj;
+                x.get( j, xj, yj, zj );
+                double fx, fy, fz;
+                bool within;
+                lj_pair( p, xi - xj, yi - yj, zi - zj, fx, fy, fz, within );
+                if ( within )
+                {
+                    ax += fx;
+                    ay += fy;
+                    az += fz;
+                    if ( NEWTON )
+                        add3( fb, f.offset( j ), f.comp_stride, -fx, -fy, -fz, true );
+                }
             }
         }
-        ax = warp_reduce_sum( ax );
-        ay = warp_reduce_sum( ay );
-        az = warp_reduce_sum( az );
-        if ( lane == 0 )
+        ax = team_reduce_sum( ax );
+        ay = team_reduce_sum( ay );
+        az = team_reduce_sum( az );
+        if ( live && sub == 0 )
             add3( fb, f.offset( i ), f.comp_stride, ax, ay, az, NEWTON );
     }
 }
@@ -176,7 +226,7 @@ __global__ void __launch_bounds__( kBlock )
 // neighbor_parallel_reduce with the LJ pair energy.  TEAM selects warp-per-particle.
 template <bool TEAM>
 __global__ void __launch_bounds__( kBlock )
-    k_lj_energy( ListAccess l, PosAccess x, LJ p, double scale, long long begin,
+    k_lj_energy( ListAccess l, Packed x, LJ p, double scale, long long begin,
                  long long end, double* energy )
 {
     __shared__ double s_part[kBlock / 32];
@@ -188,16 +238,15 @@ __global__ void __launch_bounds__( kBlock )
         const long long nwarps = ( (long long)gridDim.x * kBlock ) >> 5;
         for ( long long i = begin + warp; i < end; i += nwarps )
         {
-            const long long xo = x.offset( i );
-            const double xi = x.base[xo], yi = x.base[xo + x.comp_stride],
-                         zi = x.base[xo + 2 * x.comp_stride];
+            double xi, yi, zi;
+            x.get( i, xi, yi, zi );
             const int nn = l.num( i );
             const long long row = l.row( i ), step = l.step();
             for ( int n = (int)lane; n < nn; n += 32 )
             {
-                const long long jo = x.offset( l.neighbors[row + n * step] );
-                const double dx = xi - x.base[jo], dy = yi - x.base[jo + x.comp_stride],
-                             dz = zi - x.base[jo + 2 * x.comp_stride];
+                double xj, yj, zj;
+                x.get( l.neighbors[row + n * step], xj, yj, zj );
+                const double dx = xi - xj, dy = yi - yj, dz = zi - zj;
                 const double r2 = dx * dx + dy * dy + dz * dz;
                 if ( r2 < p.rc2 )
                 {
@@ -213,16 +262,15 @@ __global__ void __launch_bounds__( kBlock )
         for ( long long i = begin + (long long)blockIdx.x * kBlock + threadIdx.x;
               i < end; i += (long long)gridDim.x * kBlock )
         {
-            const long long xo = x.offset( i );
-            const double xi = x.base[xo], yi = x.base[xo + x.comp_stride],
-                         zi = x.base[xo + 2 * x.comp_stride];
+            double xi, yi, zi;
+            x.get( i, xi, yi, zi );
             const int nn = l.num( i );
             const long long row = l.row( i ), step = l.step();
             for ( int n = 0; n < nn; ++n )
             {
-                const long long jo = x.offset( l.neighbors[row + n * step] );
-                const double dx = xi - x.base[jo], dy = yi - x.base[jo + x.comp_stride],
-                             dz = zi - x.base[jo + 2 * x.comp_stride];
+                double xj, yj, zj;
+                x.get( l.neighbors[row + n * step], xj, yj, zj );
+                const double dx = xi - xj, dy = yi - yj, dz = zi - zj;
                 const double r2 = dx * dx + dy * dy + dz * dz;
                 if ( r2 < p.rc2 )
                 {
@@ -444,6 +492,31 @@ int team_grid( long long items )
 
 using namespace cb;
 
+namespace
+{
+// packed positions scratch (grow-only, one per process: the library is single-caller per GPU)
+cb::DeviceBuffer& packed_scratch()
+{
+    static cb::DeviceBuffer b;
+    return b;
+}
+
+int pack_positions( const cb_positions* x, cudaStream_t stream, Packed& out )
+{
+    cb::DeviceBuffer& b = packed_scratch();
+    const long long n = x->n > 0 ? x->n : 1;
+    CB_TRY( b.ensure( (size_t)n * 32, 1.1 ) );
+    if ( x->n > 0 )
+    {
+        k_pack_positions<<<launch_grid_for( x->n, kBlock ), kBlock, 0, stream>>>(
+            make_access( *x ), x->n, b.as<double2>() );
+        CB_CHECK_LAUNCH();
+    }
+    out.p = b.as<double2>();
+    return CB_OK;
+}
+} // namespace
+
 extern "C" int cb_neighbor_for_lj( const cb_verlet_view* list, const cb_positions* x,
                                    const cb_field* f, double eps, double sigma,
                                    double rc, int newton, int op, int64_t begin,
@@ -465,7 +538,8 @@ extern "C" int cb_neighbor_for_lj( const cb_verlet_view* list, const cb_position
     p.eps24 = 24.0 * eps;
     p.eps4 = 4.0 * eps;
     const ListAccess l = make_list( *list );
-    const PosAccess xa = make_access( *x );
+    Packed xa;
+    CB_TRY( pack_positions( x, stream, xa ) );
     const FieldAccess fa = make_access( *f );
     const long long items = end - begin;
     if ( op == CB_OP_SERIAL )
@@ -478,7 +552,7 @@ extern "C" int cb_neighbor_for_lj( const cb_verlet_view* list, const cb_position
     }
     else
     {
-        const int grid = team_grid( items );
+        const int grid = launch_grid_for( items * kTeam, kBlock );
         if ( newton )
             k_lj_team<true><<<grid, kBlock, 0, stream>>>( l, xa, fa, p, begin, end );
         else
@@ -510,14 +584,14 @@ extern "C" int cb_neighbor_reduce_lj( const cb_verlet_view* list, const cb_posit
     const long long items = end - begin;
     if ( items > 0 )
     {
+        Packed xa;
+        CB_TRY( pack_positions( x, stream, xa ) );
         if ( op == CB_OP_SERIAL )
             k_lj_energy<false><<<launch_grid_for( items, kBlock ), kBlock, 0, stream>>>(
-                make_list( *list ), make_access( *x ), p, scale, begin, end,
-                energy_dev );
+                make_list( *list ), xa, p, scale, begin, end, energy_dev );
         else
             k_lj_energy<true><<<team_grid( items ), kBlock, 0, stream>>>(
-                make_list( *list ), make_access( *x ), p, scale, begin, end,
-                energy_dev );
+                make_list( *list ), xa, p, scale, begin, end, energy_dev );
         CB_CHECK_LAUNCH();
     }
     CB_CUDA( cudaMemcpyAsync( energy_h, energy_dev, sizeof( double ),
