@@ -70,15 +70,17 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.rows = []
+        self.rows = []          # (arrival time, csv row)
         self.proc = None
         self.index = index
+        self.t_begin = None     # timed region, perf_counter clock
+        self.t_end = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.index)],
+                 "-lms", "20", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -87,7 +89,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -100,7 +108,16 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
+        # the sampler runs from before the warm-up; keep the samples that fell inside the timed
+        # region, or -- if the region was shorter than the sampling period -- the ones taken
+        # under the identical warm-up load just before it
+        window = "timed region"
+        rows = [r for t, r in self.rows
+                if self.t_begin is None or (self.t_begin <= t <= (self.t_end or t) + 0.03)]
+        if not rows:
+            window = "warm-up + timed region (timed region shorter than the sampling period)"
+            rows = [r for _, r in self.rows[-8:]]
+        for row in rows:
             parts = [p.strip() for p in row.split(",")]
             if len(parts) < 7:
                 continue
@@ -116,6 +133,7 @@ class ClockSampler:
             "sm_mhz": float(np.median(sm)) if sm else None,
             "sm_max_mhz": float(max(smax)) if smax else None,
             "samples": len(sm),
+            "window": window,
             "reasons": sorted(reasons),
         }
 
@@ -292,19 +310,20 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler is already running so that it is warm too)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         local_total = step()
     sync_all()
 
     # ---- timed region: device events on the launching stream, barrier+sync both sides
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     phase_sum = np.zeros(6)
     launches0 = L.cb_kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    sampler.mark_begin()
     ev0.record()
     for _ in range(args.steps):
         local_total = step()
@@ -313,6 +332,7 @@ def run_ours(args):
         phase_sum += np.array(list(ph))
     ev1.record()
     sync_all()
+    sampler.mark_end()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = L.cb_kernel_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
