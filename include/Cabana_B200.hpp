@@ -211,6 +211,10 @@ struct VerletLayout2D
 class FirstNeighborsTag
 {
 };
+//! Second-neighbour (triplet) traversal tag (Cabana_Parallel.hpp:200-204)
+class SecondNeighborsTag
+{
+};
 class SerialOpTag
 {
 };
@@ -839,6 +843,93 @@ __global__ void k_neighbor_reduce( FunctorType functor, ListType list, int begin
     }
     atomicAdd( result, local );
 }
+// SecondNeighborsTag: every unordered pair (j,k) of neighbours of i, j before k in the row
+// (Cabana_Parallel.hpp:315-365 Serial, :458-522 Team, :527-594 TeamVector)
+template <class WorkTag, class FunctorType, class ListType>
+__global__ void k_second_neighbor_for_serial( FunctorType functor, ListType list, int begin,
+                                              int end )
+{
+    using traits = NeighborList<ListType>;
+    for ( int i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end;
+          i += gridDim.x * blockDim.x )
+    {
+        const int nn = (int)traits::numNeighbor( list, i );
+        for ( int n = 0; n < nn; ++n )
+        {
+            const int j = (int)traits::getNeighbor( list, i, n );
+            for ( int a = n + 1; a < nn; ++a )
+                functorTagDispatch<WorkTag>( functor, i, j,
+                                             (int)traits::getNeighbor( list, i, a ) );
+        }
+    }
+}
+// Team / TeamVector: one warp per particle; VECTOR = false: lanes stride the first neighbour
+// and walk the second serially (:497-515); VECTOR = true: the warp strides the flattened
+// (first, second) pairs so short rows still fill the lanes (:566-587)
+template <class WorkTag, class FunctorType, class ListType, bool VECTOR>
+__global__ void k_second_neighbor_for_team( FunctorType functor, ListType list, int begin,
+                                            int end )
+{
+    using traits = NeighborList<ListType>;
+    const int lane = threadIdx.x & 31;
+    const int warp = ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
+    const int nwarps = ( gridDim.x * blockDim.x ) >> 5;
+    for ( int i = begin + warp; i < end; i += nwarps )
+    {
+        const int nn = (int)traits::numNeighbor( list, i );
+        if ( VECTOR )
+        {
+            // pair index p -> (n, a), n < a: row n of the strict upper triangle holds nn-1-n pairs
+            const long long npairs = (long long)nn * ( nn - 1 ) / 2;
+            int n = 0;
+            long long row0 = 0; // first pair index of row n
+            for ( long long p = lane; p < npairs; p += 32 )
+            {
+                while ( p >= row0 + ( nn - 1 - n ) )
+                {
+                    row0 += nn - 1 - n;
+                    ++n;
+                }
+                const int a = n + 1 + (int)( p - row0 );
+                functorTagDispatch<WorkTag>( functor, i, (int)traits::getNeighbor( list, i, n ),
+                                             (int)traits::getNeighbor( list, i, a ) );
+            }
+        }
+        else
+        {
+            for ( int n = lane; n < nn; n += 32 )
+            {
+                const int j = (int)traits::getNeighbor( list, i, n );
+                for ( int a = n + 1; a < nn; ++a )
+                    functorTagDispatch<WorkTag>( functor, i, j,
+                                                 (int)traits::getNeighbor( list, i, a ) );
+            }
+        }
+    }
+}
+template <class WorkTag, class FunctorType, class ListType, class ReduceType, bool Team>
+__global__ void k_second_neighbor_reduce( FunctorType functor, ListType list, int begin,
+                                          int end, ReduceType* result )
+{
+    using traits = NeighborList<ListType>;
+    ReduceType local = ReduceType();
+    const int lane = threadIdx.x & 31;
+    const int first = Team ? ( ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5 )
+                           : ( blockIdx.x * blockDim.x + threadIdx.x );
+    const int stride = Team ? ( ( gridDim.x * blockDim.x ) >> 5 ) : ( gridDim.x * blockDim.x );
+    for ( int i = begin + first; i < end; i += stride )
+    {
+        const int nn = (int)traits::numNeighbor( list, i );
+        for ( int n = Team ? lane : 0; n < nn; n += Team ? 32 : 1 )
+        {
+            const int j = (int)traits::getNeighbor( list, i, n );
+            for ( int a = n + 1; a < nn; ++a )
+                functorTagDispatch<WorkTag>( functor, i, j,
+                                             (int)traits::getNeighbor( list, i, a ), local );
+        }
+    }
+    atomicAdd( result, local );
+}
 inline int grid_for( long long items, int block )
 {
     long long b = ( items + block - 1 ) / block;
@@ -878,6 +969,58 @@ inline void neighbor_parallel_for( const RangePolicy<WorkTag>& exec_policy,
                                                                      b, e );
     if ( cudaGetLastError() != cudaSuccess )
         throw std::runtime_error( "Cabana::neighbor_parallel_for: launch failed" );
+}
+//! neighbor_parallel_for, SecondNeighborsTag x {Serial,Team,TeamVector} (:315-365, :458-594)
+template <class FunctorType, class NeighborListType, class WorkTag, class OpTag>
+inline void neighbor_parallel_for( const RangePolicy<WorkTag>& exec_policy,
+                                   const FunctorType& functor, const NeighborListType& list,
+                                   const SecondNeighborsTag, const OpTag,
+                                   const std::string& = "" )
+{
+    const int b = (int)exec_policy.begin(), e = (int)exec_policy.end();
+    if ( e <= b )
+        return;
+    using view_type = typename NeighborListType::device_view_type;
+    if ( std::is_same<OpTag, SerialOpTag>::value )
+        Impl::k_second_neighbor_for_serial<WorkTag, FunctorType, view_type>
+            <<<Impl::grid_for( e - b, 128 ), 128>>>( functor, list.deviceView(), b, e );
+    else if ( std::is_same<OpTag, TeamOpTag>::value )
+        Impl::k_second_neighbor_for_team<WorkTag, FunctorType, view_type, false>
+            <<<Impl::grid_for( (long long)( e - b ) * 32, 256 ), 256>>>(
+                functor, list.deviceView(), b, e );
+    else
+        Impl::k_second_neighbor_for_team<WorkTag, FunctorType, view_type, true>
+            <<<Impl::grid_for( (long long)( e - b ) * 32, 256 ), 256>>>(
+                functor, list.deviceView(), b, e );
+    if ( cudaGetLastError() != cudaSuccess )
+        throw std::runtime_error( "Cabana::neighbor_parallel_for: launch failed" );
+}
+//! neighbor_parallel_reduce, SecondNeighborsTag x {Serial,Team,TeamVector} (:704-759, :866-1001)
+template <class FunctorType, class NeighborListType, class ReduceType, class WorkTag,
+          class OpTag>
+inline void neighbor_parallel_reduce( const RangePolicy<WorkTag>& exec_policy,
+                                      const FunctorType& functor,
+                                      const NeighborListType& list, const SecondNeighborsTag,
+                                      const OpTag, ReduceType& reduce_val,
+                                      const std::string& = "" )
+{
+    const int b = (int)exec_policy.begin(), e = (int)exec_policy.end();
+    auto dev = Impl::device_alloc<ReduceType>( 1 );
+    const ReduceType zero = ReduceType();
+    cudaMemcpy( dev.get(), &zero, sizeof( ReduceType ), cudaMemcpyHostToDevice );
+    if ( e > b )
+    {
+        constexpr bool team = !std::is_same<OpTag, SerialOpTag>::value;
+        const long long threads = team ? (long long)( e - b ) * 32 : ( e - b );
+        Impl::k_second_neighbor_reduce<WorkTag, FunctorType,
+                                       typename NeighborListType::device_view_type,
+                                       ReduceType, team>
+            <<<Impl::grid_for( threads, 256 ), 256>>>( functor, list.deviceView(), b, e,
+                                                       dev.get() );
+    }
+    ReduceType out;
+    cudaMemcpy( &out, dev.get(), sizeof( ReduceType ), cudaMemcpyDeviceToHost );
+    reduce_val = out;
 }
 //! neighbor_parallel_reduce, FirstNeighborsTag x {SerialOpTag,TeamOpTag} (:638-685, :787-844)
 template <class FunctorType, class NeighborListType, class ReduceType, class WorkTag,

@@ -181,6 +181,24 @@ struct TaggedIdSumFunctor
                    (unsigned long long)( 2 * j ) );
     }
 };
+// second-neighbour functors (neighbor_unit_test.hpp:474-492, :632-642)
+struct TripletIdSumFunctor
+{
+    long long* result;
+    __device__ void operator()( const int i, const int j, const int k ) const
+    {
+        atomicAdd( reinterpret_cast<unsigned long long*>( result + i ),
+                   (unsigned long long)( j + k ) );
+    }
+};
+struct TripletSumPositionsFunctor
+{
+    Cabana::Slice<double, 3> x;
+    __device__ void operator()( const int i, const int j, const int k, double& sum ) const
+    {
+        sum += x( i, 0 ) + x( j, 0 ) + x( k, 0 );
+    }
+};
 struct SumPositionsFunctor
 {
     Cabana::Slice<double, 3> x;
@@ -364,6 +382,49 @@ static void testNeighborParallelFor()
         EXPECT_TRUE( std::fabs( e_s - e_t ) <= 1e-11 * std::fabs( e_s ) );
         cudaFree( d_f );
         cudaFree( d_g );
+    }
+    // SecondNeighborsTag: Serial, Team, TeamVector (checkSecondNeighborParallelFor,
+    // neighbor_unit_test.hpp:327-362) and the reduce (checkSecondNeighborParallelReduce)
+    {
+        std::vector<long long> expect2( n, 0 );
+        double expect_sum2 = 0.0;
+        for ( std::size_t i = 0; i < n; ++i )
+            for ( std::size_t a = 0; a < n2[i].size(); ++a )
+                for ( std::size_t b = a + 1; b < n2[i].size(); ++b )
+                {
+                    expect2[i] += n2[i][a] + n2[i][b];
+                    expect_sum2 += t.xyz[3 * i] + t.xyz[3 * n2[i][a]] + t.xyz[3 * n2[i][b]];
+                }
+        for ( int op = 0; op < 3; ++op )
+        {
+            cudaMemset( d_res, 0, n * sizeof( long long ) );
+            TripletIdSumFunctor f{ d_res };
+            if ( op == 0 )
+                Cabana::neighbor_parallel_for( policy, f, nlist, Cabana::SecondNeighborsTag(),
+                                               Cabana::SerialOpTag(), "test_2nd_serial" );
+            else if ( op == 1 )
+                Cabana::neighbor_parallel_for( policy, f, nlist, Cabana::SecondNeighborsTag(),
+                                               Cabana::TeamOpTag(), "test_2nd_team" );
+            else
+                Cabana::neighbor_parallel_for( policy, f, nlist, Cabana::SecondNeighborsTag(),
+                                               Cabana::TeamVectorOpTag(), "test_2nd_vector" );
+            cudaMemcpy( res.data(), d_res, n * sizeof( long long ), cudaMemcpyDeviceToHost );
+            EXPECT_TRUE( res == expect2 );
+        }
+        for ( int op = 0; op < 2; ++op )
+        {
+            double sum = 0.0;
+            TripletSumPositionsFunctor f{ x };
+            if ( op == 0 )
+                Cabana::neighbor_parallel_reduce( policy, f, nlist,
+                                                  Cabana::SecondNeighborsTag(),
+                                                  Cabana::SerialOpTag(), sum );
+            else
+                Cabana::neighbor_parallel_reduce( policy, f, nlist,
+                                                  Cabana::SecondNeighborsTag(),
+                                                  Cabana::TeamOpTag(), sum );
+            EXPECT_TRUE( std::fabs( sum - expect_sum2 ) <= 1e-6 * std::fabs( expect_sum2 ) );
+        }
     }
     // setNeighbor (testModifyNeighbors, tstNeighborList.hpp:256-292)
     {
