@@ -414,6 +414,9 @@ class LinkedCellList
 
     cb_lcl* handle() const { return _h.get(); }
     void refresh() { Impl::check( cb_lcl_get( _h.get(), &_v ), "cb_lcl_get" ); }
+    //! POD copy (device pointers + grids) that kernels take by value
+    using device_view_type = cb_lcl_view;
+    const cb_lcl_view& deviceView() const { return _v; }
 
   private:
     template <class ArrayType>
@@ -930,6 +933,47 @@ __global__ void k_second_neighbor_reduce( FunctorType functor, ListType list, in
     }
     atomicAdd( result, local );
 }
+// neighbor_parallel_for directly on a LinkedCellList (LinkedCellParallelFor,
+// Cabana_Parallel.hpp:1122-1290): every particle j != i of the stencil cells of i's bin is
+// handed to the functor, which applies its own cutoff.  TEAM: one warp per particle.
+template <class WorkTag, class FunctorType, bool TEAM>
+__global__ void k_linked_cell_for( FunctorType functor, cb_lcl_view l, int begin, int end )
+{
+    const int lane = threadIdx.x & 31;
+    const int first = TEAM ? ( ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5 )
+                           : ( blockIdx.x * blockDim.x + threadIdx.x );
+    const int stride = TEAM ? ( ( gridDim.x * blockDim.x ) >> 5 ) : ( gridDim.x * blockDim.x );
+    const int sny = l.stencil_grid.nx[1], snz = l.stencil_grid.nx[2];
+    const int ny = l.grid.nx[1], nz = l.grid.nx[2];
+    for ( int i = begin + first; i < end; i += stride )
+    {
+        // getStencilCells( getParticleBin( i ) ) (Cabana_LinkedCellList.hpp:105-119, :841-858)
+        const int cell = l.particle_bins[i - l.begin];
+        const int ci = cell / ( sny * snz ), cj = ( cell / snz ) % sny, ck = cell % snz;
+        const int R = l.cell_range;
+        const int imin = ci - R > 0 ? ci - R : 0;
+        const int imax = ci + R + 1 < l.stencil_grid.nx[0] ? ci + R + 1 : l.stencil_grid.nx[0];
+        const int jmin = cj - R > 0 ? cj - R : 0;
+        const int jmax = cj + R + 1 < sny ? cj + R + 1 : sny;
+        const int kmin = ck - R > 0 ? ck - R : 0;
+        const int kmax = ck + R + 1 < snz ? ck + R + 1 : snz;
+        for ( int gi = imin; gi < imax; ++gi )
+            for ( int gj = jmin; gj < jmax; ++gj )
+                for ( int gk = kmin; gk < kmax; ++gk )
+                {
+                    const int c = ( gi * ny + gj ) * nz + gk; // cardinalBinIndex (:226-231)
+                    const unsigned n0 = l.offsets[c];
+                    const unsigned n1 = n0 + (unsigned)l.counts[c];
+                    for ( unsigned n = n0 + ( TEAM ? lane : 0 ); n < n1; n += TEAM ? 32 : 1 )
+                    {
+                        // getParticle (:863-872)
+                        const int j = l.sorted ? (int)( n + l.begin ) : (int)l.permute[n];
+                        if ( j != i ) // NeighborDiscriminator<SelfNeighborTag>
+                            functorTagDispatch<WorkTag>( functor, i, j );
+                    }
+                }
+    }
+}
 inline int grid_for( long long items, int block )
 {
     long long b = ( items + block - 1 ) / block;
@@ -944,7 +988,10 @@ template <class FunctorType, class NeighborListType, class WorkTag>
 inline void neighbor_parallel_for( const RangePolicy<WorkTag>& exec_policy,
                                    const FunctorType& functor, const NeighborListType& list,
                                    const FirstNeighborsTag, const SerialOpTag,
-                                   const std::string& = "" )
+                                   const std::string& = "",
+                                   typename std::enable_if<
+                                       !is_linked_cell_list<NeighborListType>::value,
+                                       int>::type* = 0 )
 {
     const int b = (int)exec_policy.begin(), e = (int)exec_policy.end();
     if ( e <= b )
@@ -959,7 +1006,10 @@ template <class FunctorType, class NeighborListType, class WorkTag>
 inline void neighbor_parallel_for( const RangePolicy<WorkTag>& exec_policy,
                                    const FunctorType& functor, const NeighborListType& list,
                                    const FirstNeighborsTag, const TeamOpTag,
-                                   const std::string& = "" )
+                                   const std::string& = "",
+                                   typename std::enable_if<
+                                       !is_linked_cell_list<NeighborListType>::value,
+                                       int>::type* = 0 )
 {
     const int b = (int)exec_policy.begin(), e = (int)exec_policy.end();
     if ( e <= b )
@@ -967,6 +1017,29 @@ inline void neighbor_parallel_for( const RangePolicy<WorkTag>& exec_policy,
     Impl::k_neighbor_for_team<WorkTag>
         <<<Impl::grid_for( (long long)( e - b ) * 32, 256 ), 256>>>( functor, list.deviceView(),
                                                                      b, e );
+    if ( cudaGetLastError() != cudaSuccess )
+        throw std::runtime_error( "Cabana::neighbor_parallel_for: launch failed" );
+}
+//! neighbor_parallel_for on a LinkedCellList, no stored list (:1511-1595): Serial / Team.
+//! Positions must be in the order the list currently describes (permuted iff sorted()).
+template <class FunctorType, class M, class S, std::size_t D, class WorkTag, class OpTag>
+inline void neighbor_parallel_for( const RangePolicy<WorkTag>& exec_policy,
+                                   const FunctorType& functor,
+                                   const LinkedCellList<M, S, D>& list, const FirstNeighborsTag,
+                                   const OpTag, const std::string& = "" )
+{
+    static_assert( std::is_same<OpTag, SerialOpTag>::value ||
+                       std::is_same<OpTag, TeamOpTag>::value,
+                   "LinkedCellList traversal is Serial or Team" );
+    const int b = (int)exec_policy.begin(), e = (int)exec_policy.end();
+    if ( e <= b )
+        return;
+    if ( b < (int)list.getParticleBegin() || e > (int)list.getParticleEnd() )
+        throw std::runtime_error( "Cabana::neighbor_parallel_for: range outside the binned range" );
+    constexpr bool team = std::is_same<OpTag, TeamOpTag>::value;
+    const long long threads = team ? (long long)( e - b ) * 32 : ( e - b );
+    Impl::k_linked_cell_for<WorkTag, FunctorType, team>
+        <<<Impl::grid_for( threads, 256 ), 256>>>( functor, list.deviceView(), b, e );
     if ( cudaGetLastError() != cudaSuccess )
         throw std::runtime_error( "Cabana::neighbor_parallel_for: launch failed" );
 }

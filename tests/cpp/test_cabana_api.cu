@@ -512,6 +512,78 @@ static void testLinkedList()
     cudaFree( d_id );
 }
 
+// neighbor_parallel_for directly on a LinkedCellList (tstLinkedCellList.hpp:704-780,
+// checkLinkedCellNeighborPar): the functor applies the cutoff; counts must equal the N^2
+// list's, Serial and Team, before and after permute.
+struct LclCountFunctor
+{
+    Cabana::View2D<double, 3> x;
+    double rsqr;
+    int* result;
+    __device__ void operator()( const int i, const int j ) const
+    {
+        const double dx = x( i, 0 ) - x( j, 0 ), dy = x( i, 1 ) - x( j, 1 ),
+                     dz = x( i, 2 ) - x( j, 2 );
+        const double d2 = __dadd_rn( __dadd_rn( __dmul_rn( dx, dx ), __dmul_rn( dy, dy ) ),
+                                     __dmul_rn( dz, dz ) );
+        if ( d2 <= rsqr )
+            atomicAdd( result + i, 1 );
+    }
+};
+
+static void testLinkedCellParallelFor()
+{
+    TestData t;
+    auto n2 = bruteForce( t );
+    const std::size_t n = t.num_particle;
+    double* d_x = nullptr;
+    int *d_id = nullptr, *d_res = nullptr;
+    cudaMalloc( &d_x, 3 * n * sizeof( double ) );
+    cudaMalloc( &d_id, n * sizeof( int ) );
+    cudaMalloc( &d_res, n * sizeof( int ) );
+    cudaMemcpy( d_x, t.xyz.data(), 3 * n * sizeof( double ), cudaMemcpyHostToDevice );
+    std::vector<int> ids( n );
+    for ( std::size_t i = 0; i < n; ++i )
+        ids[i] = (int)i;
+    cudaMemcpy( d_id, ids.data(), n * sizeof( int ), cudaMemcpyHostToDevice );
+    Cabana::View2D<double, 3> pos( d_x, n );
+    Cabana::View2D<int, 1> pid( d_id, n );
+    const double dcell = t.test_radius * t.cell_size_ratio;
+    std::array<double, 3> delta = { dcell, dcell, dcell };
+    auto lcl = Cabana::createLinkedCellList( pos, delta, t.grid_min, t.grid_max, t.test_radius,
+                                             t.cell_size_ratio );
+    Cabana::RangePolicy<> policy( 0, n );
+    std::vector<int> res( n ), hid( n );
+    for ( int sorted = 0; sorted < 2; ++sorted )
+    {
+        if ( sorted )
+        {
+            Cabana::permute( lcl, pos, pid );
+            EXPECT_TRUE( lcl.sorted() );
+        }
+        cudaMemcpy( hid.data(), d_id, n * sizeof( int ), cudaMemcpyDeviceToHost );
+        for ( int team = 0; team < 2; ++team )
+        {
+            cudaMemset( d_res, 0, n * sizeof( int ) );
+            LclCountFunctor f{ pos, t.test_radius * t.test_radius, d_res };
+            if ( team )
+                Cabana::neighbor_parallel_for( policy, f, lcl, Cabana::FirstNeighborsTag(),
+                                               Cabana::TeamOpTag(), "lcl_team" );
+            else
+                Cabana::neighbor_parallel_for( policy, f, lcl, Cabana::FirstNeighborsTag(),
+                                               Cabana::SerialOpTag(), "lcl_serial" );
+            cudaMemcpy( res.data(), d_res, n * sizeof( int ), cudaMemcpyDeviceToHost );
+            bool ok = true;
+            for ( std::size_t i = 0; i < n; ++i )
+                ok = ok && res[i] == (int)n2[hid[i]].size();
+            EXPECT_TRUE( ok );
+        }
+    }
+    cudaFree( d_x );
+    cudaFree( d_id );
+    cudaFree( d_res );
+}
+
 int main()
 {
     if ( cb_device_count() < 1 )
@@ -526,6 +598,7 @@ int main()
     testVerletListHalf<Cabana::VerletLayout2D>();
     testNeighborParallelFor<Cabana::VerletLayoutCSR>();
     testNeighborParallelFor<Cabana::VerletLayout2D>();
+    testLinkedCellParallelFor();
     cudaDeviceSynchronize();
     if ( g_fail == 0 )
         std::printf( "ALL CABANA API TESTS PASSED\n" );
