@@ -201,7 +201,7 @@ CB_D void emit_group( const FineArgs& a, Reservation& rs, const int* idbuf,
         if ( a.offsets_direct )
             __stcs( &a.offsets_direct[pid], (int)( at + before ) );
         else
-            __stcs( &a.tmp_off[pg + lane], (unsigned)( at + before ) );
+            __stcs( &a.tmp_off[pid], (unsigned)( at + before ) );
     }
     if ( at + gtot > a.tmp_capacity )
     {
@@ -730,7 +730,7 @@ __global__ void __launch_bounds__( kBlock, 3 )
                                 if ( a.offsets_direct )
                                     a.offsets_direct[pid[p]] = (int)at[p];
                                 else
-                                    a.tmp_off[pg + p] = (unsigned)at[p];
+                                    a.tmp_off[pid[p]] = (unsigned)at[p];
                             }
                             if ( at[p] + tot > a.tmp_capacity )
                                 fits = false;
@@ -868,21 +868,20 @@ __global__ void __launch_bounds__( 256 )
                     const int* __restrict__ offsets, int* __restrict__ neighbors,
                     long long width, long long n, long long begin, long long end )
 {
-    // a quarter-warp per row, four rows in flight per warp: short rows (~78 ids) would
-    // otherwise leave each warp with only three loads outstanding
+    // A quarter-warp per row, four rows in flight per warp.  Rows are visited in PARTICLE
+    // order: the three per-row words (count, source offset, destination offset) and the
+    // destination stream are then fully coalesced, and only the source rows (written in
+    // cell order by the test pass) are scattered reads.
     const unsigned sub = threadIdx.x & 7u;
     const long long group = ( (long long)blockIdx.x * 256 + threadIdx.x ) >> 3;
     const long long ngroups = ( (long long)gridDim.x * 256 ) >> 3;
-    for ( long long s = group; s < n; s += ngroups )
+    for ( long long pid = begin + group; pid < end; pid += ngroups )
     {
-        const int pid = (int)ids[s];
-        if ( pid < begin || pid >= end )
-            continue;
         int c = counts[pid];
         if ( !CSR && c > width )
             c = (int)width;
-        const int* src = tmp + tmp_off[s];
-        int* dst = neighbors + ( CSR ? (long long)offsets[pid] : (long long)pid * width );
+        const int* src = tmp + tmp_off[pid];
+        int* dst = neighbors + ( CSR ? (long long)offsets[pid] : pid * width );
         int i = (int)sub;
         for ( ; i + 24 < c; i += 32 )
         {

@@ -40,7 +40,7 @@ struct FineArgs
     unsigned* work_count; // device counter; nullptr worklist = general kernel only
     // single test pass: rows are appended here in binned order, then reordered
     int* tmp;                   // [tmp_capacity] neighbour ids
-    unsigned* tmp_off;          // [n] row start in tmp, per SORTED slot
+    unsigned* tmp_off;          // [n] row start in tmp, per particle id
     int* offsets_direct;        // CB_ROWS_BINNED: offsets[pid] = row start in tmp (no reorder)
     unsigned long long* cursor; // bump allocator of tmp (ids reserved so far)
     int* overflow;              // set when tmp_capacity was too small
