@@ -206,6 +206,138 @@ def _fcc_slab(rank, world):
     return xyz, bounds, (FCC_CELLS * a,) * 3
 
 
+def run_cfg5(args):
+    """cfg5 (BASELINE.json configs[4], informational): WEAK scaling.  8 M uniform particles per
+    GPU (rho = 0.455, r = 3, Half CSR); every step = ballistic drift (synthetic stand-in for the
+    integrator: ~0.4 % of the particles change slab), Distributor/migrate over NCCL to the new
+    owners, ghost gather through the peer-memory halo, owner-local Half CSR build."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29577")
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", local_rank))
+    from cabana_b200 import build as cb_build
+    if rank == 0:
+        cb_build.build()
+    dist.barrier()
+    from cabana_b200 import capi, comm
+    from cabana_b200 import core as cb
+
+    Lc = capi.lib()
+    n_per = int(os.environ.get("CB_CFG5_N", "8000000"))
+    radius = 3.0
+    Lbox = 1.3 * float(n_per) ** (1.0 / 3.0)
+    bounds = [Lbox * g for g in range(world + 1)]
+    rng = np.random.Generator(np.random.Philox(key=20240105 + rank))
+    xyz = rng.random((n_per, 3)) * Lbox
+    xyz[:, 0] += bounds[rank]
+    vel = rng.normal(0.0, 1.0, (n_per, 3))
+    cap = int(n_per * 1.25) + 4096
+    slab = comm.SlabDecomposition(bounds, radius)
+    lgx = slab.local_grid_x()
+    lmin, lmax = (lgx[0], 0.0, 0.0), (lgx[1], Lbox, Lbox)
+
+    def alloc(a):
+        buf = np.zeros((cap, 3))
+        buf[: a.shape[0]] = a
+        return cb.slice_from_array(buf, vlen=32)
+
+    xs = [alloc(xyz), alloc(xyz[:1])]      # double-buffered: migrate is out of place
+    vs = [alloc(vel), alloc(vel[:1])]
+    state = {"cur": 0, "n": n_per}
+    peer = slab.create_peer_halo([xs[0]], cap // 8)
+    lst = cb.VerletList(algorithm=cb.HALF, layout=cb.CSR)
+    hi_global = bounds[-1]
+    DT = 1.0    # displacement = DT * v, v ~ N(0,1)
+
+    def sub(sl, n):
+        return cb.Slice(sl.data, n, sl.outer_stride, sl.vlen, sl.comp_stride, 3)
+
+    def drift(x, v, n):
+        # synthetic integrator (plumbing, torch ops): x += DT v, reflected at the global box
+        nso = (n + 31) // 32
+        X = x.data[: nso * 96].view(nso, 3, 32)
+        V = v.data[: nso * 96].view(nso, 3, 32)
+        X.add_(V, alpha=DT)
+        for d, hi in ((0, hi_global), (1, Lbox), (2, Lbox)):
+            xd, vd = X[:, d, :], V[:, d, :]
+            lo_m = xd < 0.0
+            hi_m = xd >= hi
+            xd.copy_(torch.where(lo_m, -xd, torch.where(hi_m, 2.0 * hi - xd, xd)))
+            xd.clamp_(0.0, float(np.nextafter(hi, 0.0)))
+            vd.copy_(torch.where(lo_m | hi_m, -vd, vd))
+
+    def step():
+        c, n = state["cur"], state["n"]
+        x, v = xs[c], vs[c]
+        drift(x, v, n)
+        distributor = slab.create_distributor(sub(x, n), n)
+        n_new = distributor.totalNumImport()
+        assert n_new <= int(n_per * 1.1), "slab over capacity"
+        comm.migrate(distributor, [sub(x, n), sub(v, n)], [sub(xs[1 - c], n_new), sub(vs[1 - c], n_new)])
+        x2 = xs[1 - c]
+        n_lo, n_hi = peer.gather(sub(x2, n_new), [x2], n_new)
+        n_tot = n_new + n_lo + n_hi
+        lst.build(sub(x2, n_tot), 0, n_new, radius, 1.0, lmin, lmax)
+        state["cur"], state["n"] = 1 - c, n_new
+        return lst.total, n - distributor.numExport(0)
+
+    def sync_all():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    launches0 = Lc.cb_kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
+    ev0.record()
+    tot_sum, moved_sum = 0.0, 0.0
+    for _ in range(args.steps):
+        t_, m_ = step()
+        tot_sum += t_
+        moved_sum += m_
+    ev1.record()
+    sync_all()
+    sampler.mark_end()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = Lc.cb_kernel_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, tot_sum / args.steps, moved_sum / args.steps, float(launches)],
+                     dtype=torch.float64, device="cuda")
+    tmax, tsum = t.clone(), t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    peer.close()
+    if rank == 0:
+        ms_g = float(tmax[0])
+        _emit({
+            "metric": METRIC, "value": float(tsum[1]) / (ms_g * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_g,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "cfg5 (informational): %d uniform particles per GPU, rho 0.455, r = 3, "
+                                   "HalfNeighborTag CSR; step = drift + Distributor migrate (NCCL) + "
+                                   "peer-memory halo + build" % n_per,
+                       "particles": n_per * world, "radius": radius,
+                       "migrated_per_step": float(tsum[2])},
+            "neighbors_per_step": float(tsum[1]), "gpu_launches": int(tsum[3]), "clocks": clocks,
+        })
+    dist.destroy_process_group()
+    return 0
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -555,7 +687,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4"],
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
                     help="cfg3 (default) is the headline line; the others are the BASELINE.json "
                          "parity configurations, timed for DESIGN.md only (1 GPU)")
     args = ap.parse_args()
@@ -563,6 +695,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "cfg5":
+        return run_cfg5(args)
     return run_ours(args)
 
 
