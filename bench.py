@@ -34,7 +34,7 @@ UNIT = "neighbors/s"
 FCC_CELLS = 159          # 4 * 159^3 = 16 078 716 atoms
 RADIUS = 2.8             # 2.5 sigma cutoff + 0.3 sigma skin
 CELL_RATIO = 1.0
-CPU_SAMPLE_CELLS = 64    # bounded CPU sample: 4 * 64^3 = 1 048 576 atoms of the same lattice
+CPU_SAMPLE_CELLS = int(os.environ.get("CB_BENCH_CPU_CELLS", "64"))  # FCC cells per side of the CPU sample
 
 
 def _peaks():
