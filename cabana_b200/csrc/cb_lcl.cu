@@ -254,6 +254,56 @@ extern "C" int cb_lcl_get( const cb_lcl* l, cb_lcl_view* v )
     return CB_OK;
 }
 
+// permute(BinningData, data) (Cabana_Sort.hpp:600-656): tmp[i] = data[perm[i]], then
+// data[begin+i] = tmp[i], one field at a time through `scratch`.
+static int permute_fields( long long begin, long long end, const unsigned* perm,
+                           const cb_field* fields, int num_fields, cb::DeviceBuffer& scratch,
+                           cudaStream_t stream, const char* who )
+{
+    const long long np = end - begin;
+    const int grid = launch_grid_for( np, kBlock );
+    for ( int fi = 0; fi < num_fields && np > 0; ++fi )
+    {
+        const cb_field& f = fields[fi];
+        if ( f.n < end || f.vlen < 1 || f.num_comp < 1 ||
+             ( f.elem_bytes != 4 && f.elem_bytes != 8 ) )
+            return fail( CB_ERR_INVALID, who );
+        CB_TRY( scratch.ensure( (size_t)np * f.num_comp * f.elem_bytes, 1.1 ) );
+        FieldAccess a = make_access( f );
+        if ( f.elem_bytes == 8 )
+        {
+            k_gather_field<unsigned long long><<<grid, kBlock, 0, stream>>>(
+                a, np, perm, scratch.as<unsigned long long>() );
+            CB_CHECK_LAUNCH();
+            k_copy_back<unsigned long long><<<grid, kBlock, 0, stream>>>(
+                a, begin, np, scratch.as<unsigned long long>() );
+            CB_CHECK_LAUNCH();
+        }
+        else
+        {
+            k_gather_field<unsigned><<<grid, kBlock, 0, stream>>>( a, np, perm,
+                                                                   scratch.as<unsigned>() );
+            CB_CHECK_LAUNCH();
+            k_copy_back<unsigned><<<grid, kBlock, 0, stream>>>( a, begin, np,
+                                                                scratch.as<unsigned>() );
+            CB_CHECK_LAUNCH();
+        }
+    }
+    return CB_OK;
+}
+
+extern "C" int cb_binning_permute( int64_t begin, int64_t end, const uint32_t* permute,
+                                   const cb_field* fields, int num_fields,
+                                   cb_stream_t stream_ )
+{
+    if ( begin < 0 || end < begin || ( end > begin && !permute ) ||
+         ( num_fields > 0 && !fields ) )
+        return fail( CB_ERR_INVALID, "cb_binning_permute: bad argument" );
+    static cb::DeviceBuffer scratch; // single caller per GPU (see cabana_b200.h)
+    return permute_fields( begin, end, permute, fields, num_fields, scratch,
+                           (cudaStream_t)stream_, "cb_binning_permute: bad field descriptor" );
+}
+
 extern "C" int cb_lcl_permute( cb_lcl* l, const cb_field* fields, int num_fields,
                                cb_stream_t stream_ )
 {
@@ -264,34 +314,8 @@ extern "C" int cb_lcl_permute( cb_lcl* l, const cb_field* fields, int num_fields
     cudaStream_t stream = (cudaStream_t)stream_;
     const long long np = l->end - l->begin;
     const int grid = launch_grid_for( np, kBlock );
-    for ( int fi = 0; fi < num_fields && np > 0; ++fi )
-    {
-        const cb_field& f = fields[fi];
-        if ( f.n < l->end || f.vlen < 1 || f.num_comp < 1 ||
-             ( f.elem_bytes != 4 && f.elem_bytes != 8 ) )
-            return fail( CB_ERR_INVALID, "cb_lcl_permute: bad field descriptor" );
-        CB_TRY( l->field_scratch.ensure( (size_t)np * f.num_comp * f.elem_bytes, 1.1 ) );
-        FieldAccess a = make_access( f );
-        if ( f.elem_bytes == 8 )
-        {
-            k_gather_field<unsigned long long><<<grid, kBlock, 0, stream>>>(
-                a, np, l->permute.as<unsigned>(),
-                l->field_scratch.as<unsigned long long>() );
-            CB_CHECK_LAUNCH();
-            k_copy_back<unsigned long long><<<grid, kBlock, 0, stream>>>(
-                a, l->begin, np, l->field_scratch.as<unsigned long long>() );
-            CB_CHECK_LAUNCH();
-        }
-        else
-        {
-            k_gather_field<unsigned><<<grid, kBlock, 0, stream>>>(
-                a, np, l->permute.as<unsigned>(), l->field_scratch.as<unsigned>() );
-            CB_CHECK_LAUNCH();
-            k_copy_back<unsigned><<<grid, kBlock, 0, stream>>>(
-                a, l->begin, np, l->field_scratch.as<unsigned>() );
-            CB_CHECK_LAUNCH();
-        }
-    }
+    CB_TRY( permute_fields( l->begin, l->end, l->permute.as<unsigned>(), fields, num_fields,
+                            l->field_scratch, stream, "cb_lcl_permute: bad field descriptor" ) );
     // update(true) + storeParticleBins() (:1141-1144)
     if ( !l->sorted && np > 0 )
     {

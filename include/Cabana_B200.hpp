@@ -277,6 +277,106 @@ std::array<double, 3> to_array3( const ArrayType& a )
 } // namespace Impl
 
 //---------------------------------------------------------------------------//
+// BinningData (core/src/Cabana_Sort.hpp:37-136): a value type over the binning arrays.  The
+// accessors read DEVICE memory, so (as in the reference, where they are KOKKOS_INLINE_FUNCTIONs
+// over device Views) they are for device code, or for a host mirror of the arrays.
+//---------------------------------------------------------------------------//
+template <class MemorySpace>
+class BinningData
+{
+  public:
+    using memory_space = MemorySpace;
+    using size_type = typename MemorySpace::size_type;
+
+    BinningData() = default;
+    BinningData( const std::size_t begin, const std::size_t end, const int* counts,
+                 const size_type* offsets, const size_type* permute_vector, const int nbin )
+        : _begin( begin )
+        , _end( end )
+        , _nbin( nbin )
+        , _counts( counts )
+        , _offsets( offsets )
+        , _permute_vector( permute_vector )
+    {
+    }
+    CABANA_B200_FUNCTION int numBin() const { return _nbin; }
+    CABANA_B200_FUNCTION int binSize( const size_type bin_id ) const { return _counts[bin_id]; }
+    CABANA_B200_FUNCTION size_type binOffset( const size_type bin_id ) const
+    {
+        return _offsets[bin_id];
+    }
+    CABANA_B200_FUNCTION size_type permutation( const size_type tuple_id ) const
+    {
+        return _permute_vector[tuple_id];
+    }
+    CABANA_B200_FUNCTION std::size_t rangeBegin() const { return _begin; }
+    CABANA_B200_FUNCTION std::size_t rangeEnd() const { return _end; }
+    const size_type* permuteData() const { return _permute_vector; }
+
+  private:
+    std::size_t _begin = 0, _end = 0;
+    int _nbin = 0;
+    const int* _counts = nullptr;
+    const size_type* _offsets = nullptr;
+    const size_type* _permute_vector = nullptr;
+};
+
+//! Device-side view of a LinkedCellList: the accessors of Cabana_LinkedCellList.hpp:489-650,
+//! :841-872 that functors call (binSize/binOffset by ijk or cardinal, permutation,
+//! getParticleBin, getParticle, getStencilCells, cardinalBinIndex/ijkBinIndex).
+struct LinkedCellListView
+{
+    cb_lcl_view v;
+    CABANA_B200_FUNCTION int totalBins() const { return (int)v.num_cells; }
+    CABANA_B200_FUNCTION int numBin( const int dim ) const { return v.grid.nx[dim]; }
+    CABANA_B200_FUNCTION int cardinalBinIndex( const int i, const int j, const int k ) const
+    {
+        return ( i * v.grid.nx[1] + j ) * v.grid.nx[2] + k;
+    }
+    CABANA_B200_FUNCTION void ijkBinIndex( const int cardinal, int& i, int& j, int& k ) const
+    {
+        i = cardinal / ( v.grid.nx[1] * v.grid.nx[2] );
+        j = ( cardinal / v.grid.nx[2] ) % v.grid.nx[1];
+        k = cardinal % v.grid.nx[2];
+    }
+    CABANA_B200_FUNCTION int binSize( const int i, const int j, const int k ) const
+    {
+        return v.counts[cardinalBinIndex( i, j, k )];
+    }
+    CABANA_B200_FUNCTION unsigned binOffset( const int i, const int j, const int k ) const
+    {
+        return v.offsets[cardinalBinIndex( i, j, k )];
+    }
+    CABANA_B200_FUNCTION unsigned permutation( const int particle_id ) const
+    {
+        return v.permute[particle_id];
+    }
+    CABANA_B200_FUNCTION std::size_t rangeBegin() const { return (std::size_t)v.begin; }
+    CABANA_B200_FUNCTION std::size_t rangeEnd() const { return (std::size_t)v.end; }
+    CABANA_B200_FUNCTION bool sorted() const { return v.sorted != 0; }
+    CABANA_B200_FUNCTION int getParticleBin( const int particle_index ) const
+    {
+        return v.particle_bins[particle_index - v.begin];
+    }
+    CABANA_B200_FUNCTION std::size_t getParticle( const int offset ) const
+    {
+        return v.sorted ? (std::size_t)( offset + v.begin ) : (std::size_t)v.permute[offset];
+    }
+    CABANA_B200_FUNCTION void getStencilCells( const int cell, int& imin, int& imax, int& jmin,
+                                               int& jmax, int& kmin, int& kmax ) const
+    {
+        const int ny = v.stencil_grid.nx[1], nz = v.stencil_grid.nx[2], R = v.cell_range;
+        const int ci = cell / ( ny * nz ), cj = ( cell / nz ) % ny, ck = cell % nz;
+        imin = ci - R > 0 ? ci - R : 0;
+        imax = ci + R + 1 < v.stencil_grid.nx[0] ? ci + R + 1 : v.stencil_grid.nx[0];
+        jmin = cj - R > 0 ? cj - R : 0;
+        jmax = cj + R + 1 < ny ? cj + R + 1 : ny;
+        kmin = ck - R > 0 ? ck - R : 0;
+        kmax = ck + R + 1 < nz ? ck + R + 1 : nz;
+    }
+};
+
+//---------------------------------------------------------------------------//
 // LinkedCellList (core/src/Cabana_LinkedCellList.hpp:128-909)
 //---------------------------------------------------------------------------//
 template <class MemorySpace, class Scalar = double, std::size_t NumSpaceDim = 3>
@@ -414,9 +514,15 @@ class LinkedCellList
 
     cb_lcl* handle() const { return _h.get(); }
     void refresh() { Impl::check( cb_lcl_get( _h.get(), &_v ), "cb_lcl_get" ); }
-    //! POD copy (device pointers + grids) that kernels take by value
-    using device_view_type = cb_lcl_view;
-    const cb_lcl_view& deviceView() const { return _v; }
+    //! POD copy (device pointers + grids) that kernels and functors take by value
+    using device_view_type = LinkedCellListView;
+    LinkedCellListView deviceView() const { return LinkedCellListView{ _v }; }
+    //! binningData() (:745-749): 1-D binning data over the cells
+    BinningData<MemorySpace> binningData() const
+    {
+        return BinningData<MemorySpace>( (std::size_t)_v.begin, (std::size_t)_v.end, _v.counts,
+                                         _v.offsets, _v.permute, (int)_v.num_cells );
+    }
 
   private:
     template <class ArrayType>
@@ -469,10 +575,24 @@ struct is_linked_cell_list<LinkedCellList<M, S, D>> : public std::true_type
 {
 };
 
+//! permute(BinningData, slice...) (core/src/Cabana_Sort.hpp:549-715): tmp[i] = data[perm[i]],
+//! data[begin+i] = tmp[i] for every member passed.
+template <class MemorySpace, class... Members>
+void permute( const BinningData<MemorySpace>& binning_data, Members&... members )
+{
+    cb_field f[] = { members.field()... };
+    Impl::check( cb_binning_permute( (int64_t)binning_data.rangeBegin(),
+                                     (int64_t)binning_data.rangeEnd(),
+                                     binning_data.permuteData(), f,
+                                     (int)sizeof...( Members ), nullptr ),
+                 "Cabana::permute" );
+}
+
 //! permute(LinkedCellList&, slice...) (:1130-1145).  Pass every member slice of the
 //! AoSoA to permute the whole AoSoA.
 template <class LinkedCellListType, class... Members>
-void permute( LinkedCellListType& linked_cell_list, Members&... members )
+typename std::enable_if<is_linked_cell_list<LinkedCellListType>::value>::type
+permute( LinkedCellListType& linked_cell_list, Members&... members )
 {
     cb_field f[] = { members.field()... };
     Impl::check( cb_lcl_permute( linked_cell_list.handle(), f, (int)sizeof...( Members ), nullptr ),
@@ -1039,7 +1159,7 @@ inline void neighbor_parallel_for( const RangePolicy<WorkTag>& exec_policy,
     constexpr bool team = std::is_same<OpTag, TeamOpTag>::value;
     const long long threads = team ? (long long)( e - b ) * 32 : ( e - b );
     Impl::k_linked_cell_for<WorkTag, FunctorType, team>
-        <<<Impl::grid_for( threads, 256 ), 256>>>( functor, list.deviceView(), b, e );
+        <<<Impl::grid_for( threads, 256 ), 256>>>( functor, list.deviceView().v, b, e );
     if ( cudaGetLastError() != cudaSuccess )
         throw std::runtime_error( "Cabana::neighbor_parallel_for: launch failed" );
 }

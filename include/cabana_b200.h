@@ -184,6 +184,11 @@ int cb_lcl_create(cb_lcl** out, const double* delta_h, const double* min_h,
 int cb_lcl_build(cb_lcl* lcl, const cb_positions* x, int64_t begin, int64_t end,
                  cb_stream_t stream);
 int cb_lcl_get(const cb_lcl* lcl, cb_lcl_view* view_h);
+/* permute(BinningData, aosoa|slice|view) (core/src/Cabana_Sort.hpp:549-715): for each field
+ * tmp[i] = data[permute[i]], data[begin+i] = tmp[i], i in [0, end-begin).  `permute` is a device
+ * array of absolute particle ids (BinningData::permutation, :96-100). */
+int cb_binning_permute(int64_t begin, int64_t end, const uint32_t* permute,
+                       const cb_field* fields_h, int num_fields, cb_stream_t stream);
 int cb_lcl_permute(cb_lcl* lcl, const cb_field* fields_h, int num_fields,
                    cb_stream_t stream);
 int cb_lcl_update(cb_lcl* lcl, int sorted); /* update(bool) :829 */

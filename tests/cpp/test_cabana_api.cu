@@ -512,6 +512,76 @@ static void testLinkedList()
     cudaFree( d_id );
 }
 
+// Device-side LinkedCellList accessors used inside a user kernel (the reference's functors call
+// binSize/binOffset/permutation/getParticleBin/getStencilCells on the captured list), and
+// permute(BinningData, slices) (tstSort.hpp / Cabana_Sort.hpp:549-715).
+__global__ void k_check_lcl_view( Cabana::LinkedCellListView l, int n, int* bad )
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( p >= n )
+        return;
+    // slot p of the binned order holds particle permutation(p); its bin must contain slot p
+    const int pid = (int)l.permutation( p );
+    // after permute() the particle in slot p IS particle rangeBegin()+p (storeParticleBins, :806-823)
+    const int cell = l.getParticleBin( l.sorted() ? p + (int)l.rangeBegin() : pid );
+    int i, j, k;
+    l.ijkBinIndex( cell, i, j, k );
+    const unsigned off = l.binOffset( i, j, k );
+    const int size = l.binSize( i, j, k );
+    if ( l.cardinalBinIndex( i, j, k ) != cell || (unsigned)p < off || (unsigned)p >= off + size )
+        atomicAdd( bad, 1 );
+    if ( (int)l.getParticle( p ) != ( l.sorted() ? p + (int)l.rangeBegin() : pid ) )
+        atomicAdd( bad, 1 );
+    int imin, imax, jmin, jmax, kmin, kmax;
+    l.getStencilCells( cell, imin, imax, jmin, jmax, kmin, kmax );
+    if ( i < imin || i >= imax || j < jmin || j >= jmax || k < kmin || k >= kmax )
+        atomicAdd( bad, 1 );
+}
+
+static void testBinningData()
+{
+    TestData t;
+    const std::size_t n = t.num_particle;
+    double *d_x = nullptr, *d_y = nullptr;
+    int* d_bad = nullptr;
+    cudaMalloc( &d_x, 3 * n * sizeof( double ) );
+    cudaMalloc( &d_y, 3 * n * sizeof( double ) );
+    cudaMalloc( &d_bad, sizeof( int ) );
+    cudaMemset( d_bad, 0, sizeof( int ) );
+    cudaMemcpy( d_x, t.xyz.data(), 3 * n * sizeof( double ), cudaMemcpyHostToDevice );
+    cudaMemcpy( d_y, t.xyz.data(), 3 * n * sizeof( double ), cudaMemcpyHostToDevice );
+    Cabana::View2D<double, 3> pos( d_x, n ), pos2( d_y, n );
+    const double dcell = t.test_radius * t.cell_size_ratio;
+    std::array<double, 3> delta = { dcell, dcell, dcell };
+    auto lcl = Cabana::createLinkedCellList( pos, delta, t.grid_min, t.grid_max, t.test_radius,
+                                             t.cell_size_ratio );
+    auto bin_data = lcl.binningData();
+    EXPECT_EQ( bin_data.numBin(), lcl.totalBins() );
+    EXPECT_EQ( bin_data.rangeBegin(), std::size_t( 0 ) );
+    EXPECT_EQ( bin_data.rangeEnd(), n );
+    k_check_lcl_view<<<( (int)n + 127 ) / 128, 128>>>( lcl.deviceView(), (int)n, d_bad );
+    // permute through the binning data == permute through the list
+    Cabana::permute( bin_data, pos2 );
+    Cabana::permute( lcl, pos );
+    k_check_lcl_view<<<( (int)n + 127 ) / 128, 128>>>( lcl.deviceView(), (int)n, d_bad );
+    std::vector<double> a( 3 * n ), b( 3 * n );
+    cudaMemcpy( a.data(), d_x, 3 * n * sizeof( double ), cudaMemcpyDeviceToHost );
+    cudaMemcpy( b.data(), d_y, 3 * n * sizeof( double ), cudaMemcpyDeviceToHost );
+    EXPECT_TRUE( a == b );
+    auto m = lcl.hostMirror();
+    bool ok = true;
+    for ( std::size_t p = 0; p < n; ++p )
+        for ( int d = 0; d < 3; ++d )
+            ok = ok && a[3 * p + d] == t.xyz[3 * m.permute[p] + d];
+    EXPECT_TRUE( ok );
+    int bad = -1;
+    cudaMemcpy( &bad, d_bad, sizeof( int ), cudaMemcpyDeviceToHost );
+    EXPECT_EQ( bad, 0 );
+    cudaFree( d_x );
+    cudaFree( d_y );
+    cudaFree( d_bad );
+}
+
 // neighbor_parallel_for directly on a LinkedCellList (tstLinkedCellList.hpp:704-780,
 // checkLinkedCellNeighborPar): the functor applies the cutoff; counts must equal the N^2
 // list's, Serial and Team, before and after permute.
@@ -599,6 +669,7 @@ int main()
     testNeighborParallelFor<Cabana::VerletLayoutCSR>();
     testNeighborParallelFor<Cabana::VerletLayout2D>();
     testLinkedCellParallelFor();
+    testBinningData();
     cudaDeviceSynchronize();
     if ( g_fail == 0 )
         std::printf( "ALL CABANA API TESTS PASSED\n" );
