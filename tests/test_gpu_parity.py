@@ -421,3 +421,30 @@ def test_binned_row_placement_same_sets(cb, orc, algo, case):
     a1, a2 = f1.to_array().cpu().numpy(), f2.to_array().cpu().numpy()
     scale = np.abs(a2).max() + 1.0
     assert np.max(np.abs(a1 - a2)) <= 1e-12 * scale
+
+
+def test_binned_placement_2d_is_reference_and_host_copy(cb, orc):
+    """CB_ROWS_BINNED only applies to CSR: a 2D list is laid out as always; the host copy of a
+    binned CSR list carries `extent` ids and the same rows."""
+    ps = datasets.uniform_box(20000, 97)
+    x = cb.slice_from_array(ps.xyz, vlen=32)
+    ref = orc.verlet_build(orc.view_from_xyz(ps.xyz), 0, ps.n, ps.radius, 1.0, ps.grid_min, ps.grid_max,
+                           algo=orc.FULL, layout=orc.LAYOUT_2D)
+    l2d = cb.VerletList(x, 0, ps.n, ps.radius, 1.0, ps.grid_min, ps.grid_max, algorithm=cb.FULL,
+                        layout=cb.LAYOUT_2D, row_placement=cb.ROWS_BINNED)
+    _assert_list_equal(orc, l2d, ref)
+    # end-to-end entry points with the binned placement
+    lst = cb.VerletList(algorithm=cb.FULL, layout=cb.CSR, row_placement=cb.ROWS_BINNED)
+    lst.build_host(ps.xyz, 0, ps.n, ps.radius, 1.0, ps.grid_min, ps.grid_max)
+    counts_h = torch.empty(ps.n, dtype=torch.int32).pin_memory()
+    offsets_h = torch.empty(ps.n, dtype=torch.int32).pin_memory()
+    nb_h = torch.empty(lst.extent, dtype=torch.int32).pin_memory()
+    lst.copy_to_host(counts_h, offsets_h, nb_h)
+    torch.cuda.synchronize()
+    refc = orc.verlet_build(orc.view_from_xyz(ps.xyz), 0, ps.n, ps.radius, 1.0, ps.grid_min, ps.grid_max,
+                            algo=orc.FULL)
+    got, _ = orc.sorted_rows_flat(orc.CSR, counts_h.numpy(), offsets_h.numpy(), nb_h.numpy(), 0)
+    assert np.array_equal(counts_h.numpy(), refc.counts)
+    assert np.array_equal(got, refc.sorted_rows_flat()[0])
+    with pytest.raises(Exception):
+        lst.copy_to_host(counts_h, offsets_h, torch.empty(lst.total - 1, dtype=torch.int32).pin_memory())
