@@ -187,10 +187,6 @@ constexpr int kHaloItems = 4;
 constexpr int kHaloTile = kHaloThreads * kHaloItems;
 
 using ull = unsigned long long;
-CB_D ull halo_pack( unsigned flag, unsigned lo, unsigned hi )
-{
-    return ( (ull)flag << 62 ) | ( (ull)hi << 31 ) | (ull)lo;
-}
 
 __global__ void __launch_bounds__( kHaloThreads )
     k_halo_compact( PosAccess x, long long n, double lo_thresh, double hi_thresh, int has_lo,

@@ -104,11 +104,10 @@ struct Packed
     {
         // one 256-bit load (sm_100 LDG.E.256): ONE sector lookup per gathered particle --
         // the traversal is bound by L1 tag lookups of the gathers, not by bytes
-        double pad;
+        [[maybe_unused]] double pad;
         asm( "ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
              : "=d"( x ), "=d"( y ), "=d"( z ), "=d"( pad )
              : "l"( p + 2 * j ) );
-        (void)pad;
     }
 };
 

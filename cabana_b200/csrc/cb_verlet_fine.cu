@@ -45,7 +45,6 @@ namespace
 
 constexpr int kGroup = 4;      // home particles per register group
 constexpr int kReserve = 4096; // ids a warp reserves in the temporary buffer per atomic
-constexpr int kRowBuf = 128;   // ids compacted through shared memory per row (general kernel)
 constexpr int kGroupBuf = 512; // list positions (u16) of all hits of one group of home particles
 constexpr int kIdBuf = 384;    // candidate ids of the current home cell kept in shared memory
 
