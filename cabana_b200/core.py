@@ -202,19 +202,57 @@ class LinkedCellList:
                                                    int(cell), mn, mx))
         return tuple(mn), tuple(mx)
 
+    def binningData(self) -> "BinningData":
+        # :745-749
+        return BinningData(self._v.begin, self._v.end, self.counts, self.offsets, self.permutes,
+                           self.totalBins())
+
     def getParticle(self, offset):
         # :863-872
         return self.permutation(offset) if not self.sorted() else offset + self._v.begin
 
 
-def permute(linked_cell_list: LinkedCellList, *fields: Slice):
-    """Cabana::permute(LinkedCellList&, aosoa|slice) (Cabana_LinkedCellList.hpp:1130-1145).
+class BinningData:
+    """Cabana::BinningData<MemorySpace> (core/src/Cabana_Sort.hpp:37-136): a value type over the
+    binning arrays of a LinkedCellList (zero-copy device tensors)."""
+
+    def __init__(self, begin, end, counts, offsets, permute_vector, nbin):
+        self._begin, self._end, self._nbin = int(begin), int(end), int(nbin)
+        self.counts, self.offsets, self.permute_vector = counts, offsets, permute_vector
+
+    def numBin(self):
+        return self._nbin
+
+    def binSize(self, bin_id):
+        return int(self.counts[bin_id])
+
+    def binOffset(self, bin_id):
+        return int(self.offsets[bin_id])
+
+    def permutation(self, tuple_id):
+        return int(self.permute_vector[tuple_id])
+
+    def rangeBegin(self):
+        return self._begin
+
+    def rangeEnd(self):
+        return self._end
+
+
+def permute(binning, *fields: Slice):
+    """Cabana::permute(LinkedCellList&, aosoa|slice) (Cabana_LinkedCellList.hpp:1130-1145) and
+    Cabana::permute(BinningData, aosoa|slice) (Cabana_Sort.hpp:549-715).
 
     Pass every member slice of the AoSoA to permute the whole AoSoA.
     """
     arr = (capi.Field * len(fields))(*[f.field_desc() for f in fields])
-    capi.check(capi.lib().cb_lcl_permute(linked_cell_list._h, arr, len(fields), _stream()))
-    linked_cell_list._refresh()
+    if isinstance(binning, BinningData):
+        capi.check(capi.lib().cb_binning_permute(
+            C.c_int64(binning.rangeBegin()), C.c_int64(binning.rangeEnd()),
+            C.c_void_p(binning.permute_vector.data_ptr()), arr, len(fields), _stream()))
+        return
+    capi.check(capi.lib().cb_lcl_permute(binning._h, arr, len(fields), _stream()))
+    binning._refresh()
 
 
 # --------------------------------------------------------------------------------- VerletList

@@ -448,3 +448,22 @@ def test_binned_placement_2d_is_reference_and_host_copy(cb, orc):
     assert np.array_equal(got, refc.sorted_rows_flat()[0])
     with pytest.raises(Exception):
         lst.copy_to_host(counts_h, offsets_h, torch.empty(lst.total - 1, dtype=torch.int32).pin_memory())
+
+
+def test_permute_through_binning_data(cb, orc):
+    """permute(BinningData, slice) == permute(LinkedCellList, slice) (Cabana_Sort.hpp:549-715)."""
+    ps = datasets.fixture_random300()
+    d = ps.radius * ps.cell_ratio
+    x1 = cb.slice_from_array(ps.xyz, vlen=32)
+    x2 = cb.view_from_array(ps.xyz)
+    lcl = cb.LinkedCellList(x1, (d, d, d), ps.grid_min, ps.grid_max)
+    bd = lcl.binningData()
+    assert bd.numBin() == lcl.totalBins() and bd.rangeBegin() == 0 and bd.rangeEnd() == ps.n
+    perm = lcl.permutes.cpu().numpy().astype(np.int64)
+    cb.permute(bd, x2)
+    cb.permute(lcl, x1)
+    a = x1.to_array().cpu().numpy()
+    b = x2.to_array().cpu().numpy()
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, ps.xyz[perm])
+    assert sum(bd.binSize(c) for c in range(0, bd.numBin(), 97)) >= 0
