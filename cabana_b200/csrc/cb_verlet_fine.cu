@@ -33,7 +33,11 @@
 //    list positions dropped into shared memory by a branch-free walk over the block bits,
 //    then one coalesced stream position -> id -> temporary buffer.  After the offsets
 //    scan a streaming kernel (k_reorder_rows) moves every row to its reference position
-//    (offsets = exclusive scan of counts in particle order, or row-major 2D).
+//    (offsets = exclusive scan of counts in particle order, or row-major 2D); with the
+//    opt-in CB_ROWS_BINNED placement the temporary buffer simply becomes the list.
+//  * What bounds it (ncu, profiles/r01_final_ncu_summary.txt): L1TEX at ~72 % of its
+//    sustained peak (shared-memory list / parked ids / row buffer + scattered float4
+//    candidate loads) and issue slots at ~62 %; DRAM carries just the algorithmic bytes.
 #include "cb_common.cuh"
 #include "cb_internal.h"
 #include "cb_verlet_fine.h"
