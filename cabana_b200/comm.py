@@ -191,13 +191,73 @@ class CommunicationPlan:
                 w.wait()
 
 
+def exports_from_imports(import_ids: torch.Tensor, import_ranks: torch.Tensor, group=None,
+                         device=None):
+    """The Import build of a plan (CommunicationPlan::createWithTopology( Import, ... ) /
+    createWithoutTopology( Import, ... ), impl/Cabana_CommunicationPlan_Mpi.hpp:480-960).
+
+    Every rank lists what it wants: import_ids[i] is a LOCAL id on rank import_ranks[i].  The
+    requests are delivered to their owners (counts with one all_gather, ids with grouped
+    point-to-point -- the reference sends one MPI message per id) and come back as the
+    (export_ids, export_ranks) pair an Export-built plan is constructed from.  Requests keep
+    their order per (requester, owner) pair and are grouped by requester in ascending rank
+    order, so after `gather` the ghosts of this rank sit in neighbour order and, inside one
+    neighbour's block, in the order this rank asked for them.
+    """
+    rank, world = _world(group)
+    dev = device if device is not None else import_ids.device
+    ids = import_ids.to(torch.int32)
+    ranks = import_ranks.to(torch.int64)
+    if ranks.numel() and (int(ranks.min()) < 0 or int(ranks.max()) >= world):
+        raise ValueError("an import rank of -1 (or out of range) is not supported")
+    want = torch.bincount(ranks.cpu(), minlength=world).to(torch.int64)
+    if world > 1:
+        allw = torch.empty(world * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allw, want.to(dev), group=group)
+        allw = allw.view(world, world).cpu()     # [requester, owner]
+    else:
+        allw = want.view(1, 1)
+    order = torch.argsort(ranks.cpu(), stable=True).to(ids.device)
+    sorted_ids = ids[order]
+    starts = torch.cumsum(want, 0) - want
+    sends = {r: sorted_ids[int(starts[r]): int(starts[r]) + int(want[r])].contiguous()
+             for r in range(world) if int(want[r]) > 0}
+    recvs = {r: torch.empty(int(allw[r, rank]), dtype=torch.int32, device=ids.device)
+             for r in range(world) if int(allw[r, rank]) > 0}
+    ops = [dist.P2POp(dist.irecv, recvs[r], r, group=group) for r in recvs if r != rank]
+    ops += [dist.P2POp(dist.isend, sends[r], r, group=group) for r in sends if r != rank]
+    if rank in sends:
+        recvs[rank].copy_(sends[rank])
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    requesters = sorted(recvs)
+    if requesters:
+        export_ids = torch.cat([recvs[r] for r in requesters])
+        export_ranks = torch.cat([torch.full((recvs[r].numel(),), r, dtype=torch.int32,
+                                             device=ids.device) for r in requesters])
+    else:
+        export_ids = torch.empty(0, dtype=torch.int32, device=ids.device)
+        export_ranks = torch.empty(0, dtype=torch.int32, device=ids.device)
+    return export_ids, export_ranks
+
+
 class Halo(CommunicationPlan):
-    """Cabana::Halo<MemorySpace, Export, Nccl> (core/src/Cabana_Halo.hpp:59-268)."""
+    """Cabana::Halo<MemorySpace, Export|Import, Nccl> (core/src/Cabana_Halo.hpp:59-268)."""
 
     def __init__(self, num_local: int, export_ids: torch.Tensor | None,
                  export_ranks: torch.Tensor | None, group=None, kernels=None, plan=None):
         super().__init__(export_ranks, export_ids, group, kernels, plan)
         self._num_local = int(num_local)
+
+    @classmethod
+    def from_imports(cls, num_local: int, import_ids: torch.Tensor, import_ranks: torch.Tensor,
+                     group=None, kernels=None):
+        """Halo<MemorySpace, Import> (Cabana_Halo.hpp:174-330): built from the ghosts this rank
+        wants (local ids on their owners) instead of from what it sends."""
+        k = kernels if kernels is not None else CudaCommKernels()
+        export_ids, export_ranks = exports_from_imports(import_ids, import_ranks, group, k.device)
+        return cls(num_local, export_ids, export_ranks, group, k)
 
     def numLocal(self):
         return self._num_local

@@ -172,3 +172,57 @@ def test_slab_migrate_gloo(world):
 
 def test_ring_distributor_gloo():
     _spawn(_case_ring_distributor, 2)
+
+
+def _case_import_halo(rank, world):
+    """Halo built from imports (tstHalo.hpp import-built variants; Cabana_Halo.hpp:174-330):
+    every rank asks its neighbours for specific local ids; the ghosts must be exactly those
+    elements, grouped by owner in neighbour order and, inside a block, in request order."""
+    from _comm_double import CpuCommKernels, CpuSlice
+    from cabana_b200 import comm
+
+    num_local = 50 + 7 * rank
+    nl = [50 + 7 * r for r in range(world)]
+    # field value encodes (owner, local id)
+    store = torch.zeros((num_local + 200, 2), dtype=torch.float64)
+    store[:num_local, 0] = rank
+    store[:num_local, 1] = torch.arange(num_local, dtype=torch.float64)
+    rng = np.random.Generator(np.random.Philox(key=100 + rank))
+    want_ranks, want_ids = [], []
+    for r in range(world):
+        if r == rank and world > 1:
+            continue
+        k = 5 + (rank + r) % 4
+        want_ranks += [r] * k
+        want_ids += rng.integers(0, nl[r], k).tolist()   # duplicates allowed, like a real halo
+    perm = rng.permutation(len(want_ranks))               # interleave the owners in the request list
+    want_ranks = [want_ranks[i] for i in perm]
+    want_ids = [want_ids[i] for i in perm]
+    halo = comm.Halo.from_imports(num_local, torch.tensor(want_ids, dtype=torch.int32),
+                                  torch.tensor(want_ranks, dtype=torch.int32),
+                                  kernels=CpuCommKernels())
+    assert halo.numLocal() == num_local and halo.numGhost() == len(want_ids)
+    assert halo.neighborRank(0) == rank and halo.neighbors[1:] == sorted(halo.neighbors[1:])
+    x = CpuSlice(store)
+    comm.gather(halo, x)
+    got = store[num_local:num_local + len(want_ids)].numpy()
+    # expected: neighbour order (self first, then ascending), request order inside a block
+    exp = []
+    for r in halo.neighbors:
+        exp += [(r, i) for rr, i in zip(want_ranks, want_ids) if rr == r]
+    assert got[:, 0].astype(int).tolist() == [e[0] for e in exp]
+    assert got[:, 1].astype(int).tolist() == [e[1] for e in exp]
+    # scatter sends ghost contributions back to the owners' elements (summed over duplicates)
+    f = torch.zeros((num_local + 200, 1), dtype=torch.float64)
+    f[num_local:num_local + len(want_ids)] = 1.0
+    comm.scatter(halo, CpuSlice(f))
+    total = torch.tensor([float(f[:num_local].sum())])
+    dist.all_reduce(total)
+    asked = torch.tensor([float(len(want_ids))])
+    dist.all_reduce(asked)
+    assert total.item() == asked.item()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_import_built_halo_gloo(world):
+    _spawn(_case_import_halo, world)

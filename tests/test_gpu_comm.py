@@ -221,6 +221,15 @@ def _rank_main(rank, world, port, ret):
                 peer_ok &= bool(np.array_equal(g2.to_array().cpu().numpy()[:nt], ref_g))
         ph.close()
         out["peer_halo_ok"] = peer_ok
+        # import-built halo over NCCL: ask the other rank for specific local ids
+        other = 1 - rank
+        want = torch.tensor([5, 17, 3, 17, 250], dtype=torch.int32, device="cuda")
+        ih = comm.Halo.from_imports(nl, want, torch.full((5,), other, dtype=torch.int32, device="cuda"))
+        gid2 = np.full((nl + 8, 1), -1, dtype=np.int32)
+        gid2[:nl, 0] = mine
+        g2 = cb.view_from_array(gid2)
+        comm.gather(ih, g2)
+        out["import_ghosts"] = g2.to_array().cpu().numpy()[nl:nl + 5, 0].tolist()
         ret[rank] = out
     except Exception:
         import traceback
@@ -243,6 +252,12 @@ def test_two_gpu_slab_build_equals_single_gpu(orc):
         assert isinstance(ret[r], dict), ret[r]
         assert ret[r]["peer_halo_ok"], "peer-memory halo differs from the send/recv halo"
     ps = datasets.fcc_lattice(24, jitter=0.03)
+    # import-built halo: rank r received the global ids of the OTHER rank's local 5,17,3,17,250
+    L = ps.grid_max[0]
+    owner = np.minimum((ps.xyz[:, 0] / (L / world)).astype(int), world - 1)
+    for r in range(world):
+        theirs = np.nonzero(owner == 1 - r)[0]
+        assert ret[r]["import_ghosts"] == [int(theirs[i]) for i in (5, 17, 3, 17, 250)]
     ox = orc.view_from_xyz(ps.xyz)
     for algo, oalgo in ((0, orc.FULL), (1, orc.HALF)):
         ref = orc.verlet_build(ox, 0, ps.n, ps.radius, 1.0, ps.grid_min, ps.grid_max, algo=oalgo)
