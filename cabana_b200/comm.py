@@ -307,6 +307,127 @@ def scatter(halo: Halo, field: Slice):
             k.scatter_add(field, halo.steering_for(r), ne, recvs[r])
 
 
+class _CommunicationData:
+    """Persistent send/receive buffers of a Gather / Scatter (CommunicationData,
+    Cabana_CommunicationPlanBase.hpp:700-960): sizes in TUPLES, grow-only on reserve(),
+    reallocated by shrinkToFit()."""
+
+    def __init__(self, halo: Halo, fields, overallocation: float, total_send, total_recv):
+        if overallocation < 1.0:
+            raise RuntimeError("Cabana::CommunicationPlan: Cannot allocate buffers with less space "
+                               "than data to communicate!")
+        self._overallocation = float(overallocation)
+        self._send = torch.empty(0, dtype=torch.uint8, device=halo.kernels.device)
+        self._recv = torch.empty(0, dtype=torch.uint8, device=halo.kernels.device)
+        self._reserve(halo, fields, total_send, total_recv)
+
+    def _reserve(self, halo, fields, total_send, total_recv):
+        self.halo, self.fields = halo, list(fields)
+        self._tb = halo.kernels.tuple_bytes(self.fields)
+        new_send = int(total_send * self._overallocation)
+        if new_send > self.sendCapacity():
+            self._send = torch.empty(new_send * self._tb, dtype=torch.uint8, device=halo.kernels.device)
+        new_recv = int(total_recv * self._overallocation)
+        if new_recv > self.receiveCapacity():
+            self._recv = torch.empty(new_recv * self._tb, dtype=torch.uint8, device=halo.kernels.device)
+        self._send_size, self._recv_size = int(total_send), int(total_recv)
+
+    def sendSize(self):
+        return self._send_size
+
+    def receiveSize(self):
+        return self._recv_size
+
+    def sendCapacity(self):
+        return self._send.numel() // max(self._tb, 1)
+
+    def receiveCapacity(self):
+        return self._recv.numel() // max(self._tb, 1)
+
+    def shrinkToFit(self, use_overallocation: bool = False):
+        f = self._overallocation if use_overallocation else 1.0
+        dev = self.halo.kernels.device
+        self._send = torch.empty(int(self._send_size * f) * self._tb, dtype=torch.uint8, device=dev)
+        self._recv = torch.empty(int(self._recv_size * f) * self._tb, dtype=torch.uint8, device=dev)
+
+    def _blocks(self, buf, counts):
+        out, at = {}, 0
+        for r, c in zip(self.halo.neighbors, counts):
+            out[r] = buf[at * self._tb:(at + c) * self._tb]
+            at += c
+        return out
+
+
+class Gather(_CommunicationData):
+    """Cabana::Gather<HaloType, AoSoA|Slice> (Cabana_Halo.hpp:392-640): a gather with persistent
+    buffers.  `apply()` = impl/Cabana_Halo_Mpi.hpp:41-125; reserve() re-targets the object at a
+    new halo / data and only grows the buffers."""
+
+    def __init__(self, halo: Halo, *fields: Slice, overallocation: float = 1.0):
+        super().__init__(halo, fields, overallocation, halo.totalNumExport(), halo.totalNumImport())
+
+    def reserve(self, halo: Halo, *fields: Slice, overallocation: float | None = None):
+        if overallocation is not None:
+            if overallocation < 1.0:
+                raise RuntimeError("Cabana::CommunicationPlan: Cannot allocate buffers with less "
+                                   "space than data to communicate!")
+            self._overallocation = float(overallocation)
+        self._reserve(halo, fields, halo.totalNumExport(), halo.totalNumImport())
+
+    def apply(self):
+        h, k = self.halo, self.halo.kernels
+        sends = self._blocks(self._send, h.num_export)
+        recvs = self._blocks(self._recv, h.num_import)
+        for r, ne in zip(h.neighbors, h.num_export):
+            if ne > 0:
+                k.pack(self.fields, h.steering_for(r), ne, sends[r])
+        h.exchange(sends, recvs)
+        for r, ni in zip(h.neighbors, h.num_import):
+            if ni > 0:
+                k.unpack(self.fields, h.numLocal() + h.import_offset[r], ni, recvs[r])
+
+
+class Scatter(_CommunicationData):
+    """Cabana::Scatter<HaloType, Slice> (Cabana_Halo.hpp:700-870): ghost values go back to their
+    owners and are summed into them; persistent buffers (send = ghosts, receive = exports)."""
+
+    def __init__(self, halo: Halo, field: Slice, overallocation: float = 1.0):
+        super().__init__(halo, [field], overallocation, halo.totalNumImport(), halo.totalNumExport())
+
+    def reserve(self, halo: Halo, field: Slice, overallocation: float | None = None):
+        if overallocation is not None:
+            if overallocation < 1.0:
+                raise RuntimeError("Cabana::CommunicationPlan: Cannot allocate buffers with less "
+                                   "space than data to communicate!")
+            self._overallocation = float(overallocation)
+        self._reserve(halo, [field], halo.totalNumImport(), halo.totalNumExport())
+
+    def apply(self):
+        h, k = self.halo, self.halo.kernels
+        field = self.fields[0]
+        sends = self._blocks(self._send, h.num_import)
+        recvs = self._blocks(self._recv, h.num_export)
+        ghost = field.to_array()
+        for r, ni in zip(h.neighbors, h.num_import):
+            if ni > 0:
+                b = h.numLocal() + h.import_offset[r]
+                sends[r].copy_(ghost[b: b + ni].contiguous().view(torch.uint8).reshape(-1))
+        h.exchange(sends, recvs)
+        for r, ne in zip(h.neighbors, h.num_export):
+            if ne > 0:
+                k.scatter_add(field, h.steering_for(r), ne, recvs[r])
+
+
+def createGather(halo: Halo, *fields: Slice, overallocation: float = 1.0) -> Gather:
+    """Cabana::createGather (Cabana_Halo.hpp:653-664)."""
+    return Gather(halo, *fields, overallocation=overallocation)
+
+
+def createScatter(halo: Halo, field: Slice, overallocation: float = 1.0) -> Scatter:
+    """Cabana::createScatter (Cabana_Halo.hpp:833-843)."""
+    return Scatter(halo, field, overallocation)
+
+
 class Distributor(CommunicationPlan):
     """Cabana::Distributor<MemorySpace, Nccl> (core/src/Cabana_Distributor.hpp:62-146).
 

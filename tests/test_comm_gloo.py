@@ -101,6 +101,27 @@ def _case_slab_halo(rank, world):
     need = set(np.where((d2 <= r * r).any(axis=0) & (owner != rank))[0].tolist())
     assert need <= set(ghosts.tolist())
 
+    # persistent Gather object (Cabana_Halo.hpp:392-640): same ghosts, buffers kept and re-used
+    store2 = store.clone()
+    store2[num_local:] = 0.0
+    gid2 = gid.clone()
+    gid2[num_local:] = -1
+    g = comm.createGather(halo, CpuSlice(store2), CpuSlice(gid2), overallocation=1.5)
+    assert g.sendSize() == halo.totalNumExport() and g.receiveSize() == halo.totalNumImport()
+    assert g.sendCapacity() == int(halo.totalNumExport() * 1.5)
+    g.apply()
+    assert torch.equal(store2[:n_tot], store[:n_tot]) and torch.equal(gid2[:n_tot], gid[:n_tot])
+    cap = g.sendCapacity()
+    g.reserve(halo, CpuSlice(store2), CpuSlice(gid2))          # same sizes: no reallocation
+    assert g.sendCapacity() == cap
+    g.shrinkToFit()
+    assert g.sendCapacity() == halo.totalNumExport() and g.receiveCapacity() == halo.totalNumImport()
+    store2[num_local:] = 0.0
+    g.apply()
+    assert torch.equal(store2[:n_tot], store[:n_tot])
+    with pytest.raises(RuntimeError):
+        comm.createGather(halo, CpuSlice(store2), overallocation=0.5)
+
     # scatter: ghost contributions are summed into their owners (tstHalo.hpp:146-185)
     f = torch.zeros((num_local + 2000, 3), dtype=torch.float64)
     f[num_local:n_tot] = 1.0 + rank
@@ -112,6 +133,13 @@ def _case_slab_halo(rank, world):
     expect += np.where(sent_lo, 1.0 + (rank - 1), 0.0)
     expect += np.where(sent_hi, 1.0 + (rank + 1), 0.0)
     assert np.array_equal(f[:num_local, 0].numpy(), expect)
+    # persistent Scatter object: same sums
+    f2 = torch.zeros((num_local + 2000, 3), dtype=torch.float64)
+    f2[num_local:n_tot] = 1.0 + rank
+    sc = comm.createScatter(halo, CpuSlice(f2))
+    assert sc.sendSize() == halo.totalNumImport() and sc.receiveSize() == halo.totalNumExport()
+    sc.apply()
+    assert np.array_equal(f2[:num_local, 0].numpy(), expect)
 
 
 def _case_migrate(rank, world):

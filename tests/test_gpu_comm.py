@@ -221,6 +221,21 @@ def _rank_main(rank, world, port, ret):
                 peer_ok &= bool(np.array_equal(g2.to_array().cpu().numpy()[:nt], ref_g))
         ph.close()
         out["peer_halo_ok"] = peer_ok
+        # persistent Gather / Scatter objects (Cabana_Halo.hpp:392-870) over NCCL
+        xg = cb.slice_from_array(np.where(np.arange(cap)[:, None] < nl, store, 0.0), vlen=32)
+        gg = cb.view_from_array(gid)
+        gobj = comm.createGather(halo, cb.Slice(xg.data, nt, xg.outer_stride, xg.vlen, xg.comp_stride, 3),
+                                 cb.Slice(gg.data, nt, 1, 1, 1, 1), overallocation=1.25)
+        gobj.apply()
+        gobj.apply()   # buffers are re-used
+        out["gather_obj_ok"] = bool(
+            np.array_equal(xg.to_array().cpu().numpy()[:nt], ref_x) and
+            np.array_equal(gg.to_array().cpu().numpy()[:nt], ref_g))
+        fs1 = cb.view_from_array(np.ones((cap, 3)))
+        fs2 = cb.view_from_array(np.ones((cap, 3)))
+        comm.scatter(halo, cb.Slice(fs1.data, nt, 3, 1, 1, 3))
+        comm.createScatter(halo, cb.Slice(fs2.data, nt, 3, 1, 1, 3)).apply()
+        out["scatter_obj_ok"] = bool(np.array_equal(fs1.to_array().cpu().numpy(), fs2.to_array().cpu().numpy()))
         # import-built halo over NCCL: ask the other rank for specific local ids
         other = 1 - rank
         want = torch.tensor([5, 17, 3, 17, 250], dtype=torch.int32, device="cuda")
@@ -251,6 +266,7 @@ def test_two_gpu_slab_build_equals_single_gpu(orc):
     for r in range(world):
         assert isinstance(ret[r], dict), ret[r]
         assert ret[r]["peer_halo_ok"], "peer-memory halo differs from the send/recv halo"
+        assert ret[r]["gather_obj_ok"] and ret[r]["scatter_obj_ok"]
     ps = datasets.fcc_lattice(24, jitter=0.03)
     # import-built halo: rank r received the global ids of the OTHER rank's local 5,17,3,17,250
     L = ps.grid_max[0]
