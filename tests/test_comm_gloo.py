@@ -254,3 +254,35 @@ def _case_import_halo(rank, world):
 @pytest.mark.parametrize("world", [2, 3])
 def test_import_built_halo_gloo(world):
     _spawn(_case_import_halo, world)
+
+
+def _case_import_edge(rank, world):
+    """Import build corner cases: a rank that imports nothing, self-imports (allowed: the
+    calling rank may be in the neighbour list), and a rejected rank of -1."""
+    from _comm_double import CpuCommKernels, CpuSlice
+    from cabana_b200 import comm
+
+    num_local = 20
+    store = torch.zeros((num_local + 40, 1), dtype=torch.float64)
+    store[:num_local, 0] = 100.0 * rank + torch.arange(num_local, dtype=torch.float64)
+    if rank == 0:
+        ids, ranks = [3, 4, 19], [0, world - 1, 0]          # two self-imports and one remote
+    else:
+        ids, ranks = [], []                                  # imports nothing
+    halo = comm.Halo.from_imports(num_local, torch.tensor(ids, dtype=torch.int32),
+                                  torch.tensor(ranks, dtype=torch.int32), kernels=CpuCommKernels())
+    assert halo.numGhost() == len(ids)
+    comm.gather(halo, CpuSlice(store))
+    if rank == 0:
+        got = store[num_local:num_local + 3, 0].tolist()
+        if world == 1:
+            assert got == [3.0, 4.0, 19.0]
+        else:   # self block first, then the remote owner
+            assert got == [3.0, 19.0, 100.0 * (world - 1) + 4.0]
+    with pytest.raises(ValueError):
+        comm.exports_from_imports(torch.tensor([1], dtype=torch.int32), torch.tensor([-1], dtype=torch.int32))
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_import_built_halo_edge_cases_gloo(world):
+    _spawn(_case_import_edge, world)
