@@ -403,7 +403,15 @@ def run_ours(args):
         tr = {"plan": 0.0, "gather": 0.0, "build": 0.0, "n": 0}
         # ghost exchange: peer-memory windows over NVLink (default) or NCCL send/recv
         halo_impl = os.environ.get("CB_BENCH_HALO", "peer")
-        peer = slab.create_peer_halo([x_all], cap - num_local) if halo_impl == "peer" else None
+        peer = None
+        if halo_impl == "peer":
+            try:
+                peer = slab.create_peer_halo([x_all], cap - num_local)
+            except RuntimeError as e:   # raised on EVERY rank (the outcome is agreed collectively)
+                if rank == 0:
+                    sys.stderr.write(f"bench.py: {e}; falling back to the NCCL send/recv halo\n")
+                halo_impl = "nccl"
+                os.environ["CB_BENCH_HALO"] = "nccl"   # (named in config.workload)
 
         def step():
             t0 = time.perf_counter()

@@ -532,24 +532,39 @@ class PeerHalo:
         arr = (capi.Field * len(fields))(*[f.field_desc() for f in fields])
         self.tuple_bytes = int(L.cb_comm_tuple_bytes(arr, len(fields)))
         self._win = [C.c_void_p(), C.c_void_p()]      # from_lo, from_hi
-        handles = []
-        for w in self._win:
-            capi.check(L.cb_p2p_window_create(C.byref(w), C.c_int64(self.capacity),
-                                              C.c_int64(self.tuple_bytes)))
-            h = (C.c_ubyte * 64)()
-            capi.check(L.cb_p2p_window_get_handle(w, h))
-            handles.append(bytes(h))
+        self._peer = [C.c_void_p(), C.c_void_p()]     # where I push my lo / hi face
+        handles, err = [], None
+        try:
+            for w in self._win:
+                capi.check(L.cb_p2p_window_create(C.byref(w), C.c_int64(self.capacity),
+                                                  C.c_int64(self.tuple_bytes)))
+                h = (C.c_ubyte * 64)()
+                capi.check(L.cb_p2p_window_get_handle(w, h))
+                handles.append(bytes(h))
+        except Exception as e:
+            handles, err = None, str(e)
         everyone = [None] * slab.world
         dist.all_gather_object(everyone, handles, group=slab.group)
-        self._peer = [C.c_void_p(), C.c_void_p()]     # where I push my lo / hi face
-        if slab.lo_rank >= 0:   # my low face lands in the lower neighbour's "from_hi" window
-            h = (C.c_ubyte * 64).from_buffer_copy(everyone[slab.lo_rank][1])
-            capi.check(L.cb_p2p_window_open(h, C.byref(self._peer[0])))
-        if slab.hi_rank >= 0:
-            h = (C.c_ubyte * 64).from_buffer_copy(everyone[slab.hi_rank][0])
-            capi.check(L.cb_p2p_window_open(h, C.byref(self._peer[1])))
+        try:
+            if err is None and any(h is None for h in everyone):
+                err = "a neighbour could not export its window"
+            if err is None and slab.lo_rank >= 0:   # my low face lands in the lower neighbour's "from_hi" window
+                h = (C.c_ubyte * 64).from_buffer_copy(everyone[slab.lo_rank][1])
+                capi.check(L.cb_p2p_window_open(h, C.byref(self._peer[0])))
+            if err is None and slab.hi_rank >= 0:
+                h = (C.c_ubyte * 64).from_buffer_copy(everyone[slab.hi_rank][0])
+                capi.check(L.cb_p2p_window_open(h, C.byref(self._peer[1])))
+        except Exception as e:   # e.g. CUDA IPC not permitted between these processes
+            err = str(e)
+        # all ranks agree on the outcome before anyone pushes (and nobody is left in a barrier)
+        errs = [None] * slab.world
+        dist.all_gather_object(errs, err, group=slab.group)
         self._seq = 0
         self._steer = None
+        if any(e is not None for e in errs):
+            self._release()
+            raise RuntimeError("PeerHalo: peer-memory windows unavailable: " +
+                               "; ".join(f"rank {r}: {e}" for r, e in enumerate(errs) if e))
         dist.barrier(group=slab.group)   # every window is mapped before anyone pushes
 
     def gather(self, x: Slice, fields, num_local: int):
@@ -590,10 +605,13 @@ class PeerHalo:
         return n_lo, n_hi
 
     def close(self):
-        L = capi.lib()
         torch.cuda.synchronize()
         if dist.is_initialized():
             dist.barrier(group=self.slab.group)
+        self._release()
+
+    def _release(self):
+        L = capi.lib()
         for p in self._peer:
             if p:
                 L.cb_p2p_window_close(p)
