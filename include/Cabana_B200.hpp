@@ -28,6 +28,7 @@
 #ifndef CABANA_B200_HPP
 #define CABANA_B200_HPP
 
+#include <algorithm>
 #include <array>
 #include <cstddef>
 #include <cstdint>
@@ -846,6 +847,43 @@ class NeighborList<VerletListView<MemorySpace, AlgorithmTag, LayoutTag>>
         return list._data.get( particle_index, neighbor_index );
     }
 };
+
+//---------------------------------------------------------------------------//
+// neighborHistogram (core/src/Cabana_NeighborList.hpp:283-332): histogram of neighbours per
+// particle.  Row b = { upper bin edge, particles in the bin }.  The reference bins the counts with
+// Cabana::binByKey (Kokkos::BinOp1D: mul = nbin/(max-min), bin = int(mul*(key-min))); this is
+// set-up / diagnostics code, so the counts are brought to the host and binned there.
+//---------------------------------------------------------------------------//
+template <class ListType>
+std::vector<std::array<int, 2>> neighborHistogram( const std::size_t num_particles,
+                                                   const ListType& list, const int num_bin )
+{
+    std::vector<int> num_neigh( num_particles );
+    if ( num_particles > 0 )
+    {
+        cb_memcpy_d2h( num_neigh.data(), list._data.counts, num_particles * sizeof( int ),
+                       nullptr );
+        Impl::check( cb_stream_synchronize( nullptr ), "Cabana::neighborHistogram" );
+    }
+    int kmin = 0, kmax = 0;
+    if ( num_particles > 0 )
+    {
+        kmin = *std::min_element( num_neigh.begin(), num_neigh.end() );
+        kmax = *std::max_element( num_neigh.begin(), num_neigh.end() );
+    }
+    std::vector<int> bin_size( num_bin + 1, 0 );
+    const double mul = kmax > kmin ? (double)num_bin / (double)( kmax - kmin ) : 0.0;
+    for ( int c : num_neigh )
+        ++bin_size[(int)( mul * (double)( c - kmin ) )];
+    const int max_neigh = (int)NeighborList<ListType>::maxNeighbor( list );
+    double bin_width = (double)max_neigh / (double)num_bin;
+    if ( num_bin > max_neigh )
+        bin_width = 1;
+    std::vector<std::array<int, 2>> histogram( num_bin );
+    for ( int b = 0; b < num_bin; ++b )
+        histogram[b] = { (int)( ( b + 1 ) * bin_width ), bin_size[b] };
+    return histogram;
+}
 
 //---------------------------------------------------------------------------//
 // Pre-compiled consumers (C ABI): the Lennard-Jones functor of the benchmark.

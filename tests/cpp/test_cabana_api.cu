@@ -582,6 +582,52 @@ static void testBinningData()
     cudaFree( d_bad );
 }
 
+// testNeighborHistogram (tstNeighborList.hpp:328-381): 10^3 lattice, r = 3 dx + 1e-7; the
+// histogram values are the reference's literal known answers.
+static void testNeighborHistogram()
+{
+    const int np = 10;
+    const std::size_t n = np * np * np;
+    const double dx = 5.0 / np;
+    std::vector<double> xyz( 3 * n );
+    for ( std::size_t pid = 0; pid < n; ++pid )
+    {
+        xyz[3 * pid + 0] = dx / 2 + dx * ( pid / ( np * np ) );
+        xyz[3 * pid + 1] = dx / 2 + dx * ( ( pid / np ) % np );
+        xyz[3 * pid + 2] = dx / 2 + dx * ( pid % np );
+    }
+    double* d_x = nullptr;
+    cudaMalloc( &d_x, xyz.size() * sizeof( double ) );
+    cudaMemcpy( d_x, xyz.data(), xyz.size() * sizeof( double ), cudaMemcpyHostToDevice );
+    Cabana::View2D<double, 3> pos( d_x, n );
+    std::array<double, 3> mn = { 0, 0, 0 }, mx = { 5, 5, 5 };
+    using ListType =
+        Cabana::VerletList<Cabana::DeviceSpace, Cabana::FullNeighborTag, Cabana::VerletLayoutCSR>;
+    ListType nlist( pos, 0, n, 3 * dx + 1e-7, 0.5, mn, mx );
+    EXPECT_EQ( Cabana::NeighborList<ListType>::maxNeighbor( nlist ), std::size_t( 122 ) );
+    {
+        auto h = Cabana::neighborHistogram( n, nlist, 10 );
+        const int bin_max[10] = { 12, 24, 36, 48, 61, 73, 85, 97, 109, 122 };
+        const int bin_count[10] = { 32, 72, 24, 152, 120, 168, 0, 216, 0, 152 };
+        for ( int i = 0; i < 10; ++i )
+        {
+            EXPECT_EQ( h[i][0], bin_max[i] );
+            EXPECT_EQ( h[i][1], bin_count[i] );
+        }
+    }
+    {
+        auto h = Cabana::neighborHistogram( n, nlist, 5 );
+        const int bin_max[5] = { 24, 48, 73, 97, 122 };
+        const int bin_count[5] = { 104, 176, 288, 216, 152 };
+        for ( int i = 0; i < 5; ++i )
+        {
+            EXPECT_EQ( h[i][0], bin_max[i] );
+            EXPECT_EQ( h[i][1], bin_count[i] );
+        }
+    }
+    cudaFree( d_x );
+}
+
 // neighbor_parallel_for directly on a LinkedCellList (tstLinkedCellList.hpp:704-780,
 // checkLinkedCellNeighborPar): the functor applies the cutoff; counts must equal the N^2
 // list's, Serial and Team, before and after permute.
@@ -670,6 +716,7 @@ int main()
     testNeighborParallelFor<Cabana::VerletLayout2D>();
     testLinkedCellParallelFor();
     testBinningData();
+    testNeighborHistogram();
     cudaDeviceSynchronize();
     if ( g_fail == 0 )
         std::printf( "ALL CABANA API TESTS PASSED\n" );
