@@ -848,6 +848,68 @@ class NeighborList<VerletListView<MemorySpace, AlgorithmTag, LayoutTag>>
     }
 };
 
+//! NeighborList traits of a LinkedCellList (Cabana_LinkedCellList.hpp:1149-1303): the
+//! "neighbours" of a particle are ALL particles of the stencil cells of its bin (itself
+//! included, no cutoff) in stencil order; device code takes the list as its device view.
+template <>
+class NeighborList<LinkedCellListView>
+{
+  public:
+    using list_type = LinkedCellListView;
+    static constexpr std::size_t num_space_dim = 3;
+
+    CABANA_B200_FUNCTION static std::size_t numNeighbor( const list_type& list,
+                                                         const std::size_t particle_index )
+    {
+        int imin, imax, jmin, jmax, kmin, kmax;
+        list.getStencilCells( list.getParticleBin( (int)particle_index ), imin, imax, jmin,
+                              jmax, kmin, kmax );
+        int total_count = 0;
+        for ( int i = imin; i < imax; ++i )
+            for ( int j = jmin; j < jmax; ++j )
+                for ( int k = kmin; k < kmax; ++k )
+                    total_count += list.binSize( i, j, k );
+        return (std::size_t)total_count;
+    }
+    CABANA_B200_FUNCTION static std::size_t getNeighbor( const list_type& list,
+                                                         const std::size_t particle_index,
+                                                         const std::size_t neighbor_index )
+    {
+        int imin, imax, jmin, jmax, kmin, kmax;
+        list.getStencilCells( list.getParticleBin( (int)particle_index ), imin, imax, jmin,
+                              jmax, kmin, kmax );
+        std::size_t total_count = 0, previous_count = 0;
+        for ( int i = imin; i < imax; ++i )
+            for ( int j = jmin; j < jmax; ++j )
+                for ( int k = kmin; k < kmax; ++k )
+                {
+                    total_count += (std::size_t)list.binSize( i, j, k );
+                    if ( total_count > neighbor_index ) // this neighbour is in this bin
+                        return list.getParticle( (int)( list.binOffset( i, j, k ) +
+                                                        ( neighbor_index - previous_count ) ) );
+                    previous_count = total_count;
+                }
+        return 0; // (never reached for neighbor_index < numNeighbor)
+    }
+    CABANA_B200_FUNCTION static std::size_t totalNeighbor( const list_type& list )
+    {
+        std::size_t total_n = 0;
+        for ( std::size_t p = list.rangeBegin(); p < list.rangeEnd(); ++p )
+            total_n += numNeighbor( list, p );
+        return total_n;
+    }
+    CABANA_B200_FUNCTION static std::size_t maxNeighbor( const list_type& list )
+    {
+        std::size_t max_n = 0;
+        for ( std::size_t p = list.rangeBegin(); p < list.rangeEnd(); ++p )
+        {
+            const std::size_t c = numNeighbor( list, p );
+            max_n = c > max_n ? c : max_n;
+        }
+        return max_n;
+    }
+};
+
 //---------------------------------------------------------------------------//
 // neighborHistogram (core/src/Cabana_NeighborList.hpp:283-332): histogram of neighbours per
 // particle.  Row b = { upper bin edge, particles in the bin }.  The reference bins the counts with

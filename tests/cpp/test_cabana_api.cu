@@ -538,6 +538,21 @@ __global__ void k_check_lcl_view( Cabana::LinkedCellListView l, int n, int* bad 
         atomicAdd( bad, 1 );
 }
 
+// NeighborList<LinkedCellList> traits on the device (Cabana_LinkedCellList.hpp:1149-1303)
+__global__ void k_lcl_traits( Cabana::LinkedCellListView l, int n, long long* nn, long long* idsum )
+{
+    using traits = Cabana::NeighborList<Cabana::LinkedCellListView>;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( p >= n )
+        return;
+    const std::size_t c = traits::numNeighbor( l, p );
+    long long sum = 0;
+    for ( std::size_t k = 0; k < c; ++k )
+        sum += (long long)traits::getNeighbor( l, p, k );
+    nn[p] = (long long)c;
+    idsum[p] = sum;
+}
+
 static void testBinningData()
 {
     TestData t;
@@ -577,6 +592,40 @@ static void testBinningData()
     int bad = -1;
     cudaMemcpy( &bad, d_bad, sizeof( int ), cudaMemcpyDeviceToHost );
     EXPECT_EQ( bad, 0 );
+    // traits: every particle "sees" all particles of its stencil cells (itself included)
+    {
+        long long *d_nn = nullptr, *d_sum = nullptr;
+        cudaMalloc( &d_nn, n * sizeof( long long ) );
+        cudaMalloc( &d_sum, n * sizeof( long long ) );
+        k_lcl_traits<<<( (int)n + 127 ) / 128, 128>>>( lcl.deviceView(), (int)n, d_nn, d_sum );
+        std::vector<long long> nn( n ), sum( n );
+        cudaMemcpy( nn.data(), d_nn, n * sizeof( long long ), cudaMemcpyDeviceToHost );
+        cudaMemcpy( sum.data(), d_sum, n * sizeof( long long ), cudaMemcpyDeviceToHost );
+        // host replay from the mirror (the list is sorted now: slot p holds particle p)
+        bool ok2 = true;
+        long long total = 0;
+        for ( std::size_t p = 0; p < n; ++p )
+        {
+            int imin, imax, jmin, jmax, kmin, kmax;
+            lcl.getStencilCells( m.particle_bins[p], imin, imax, jmin, jmax, kmin, kmax );
+            long long c = 0, sid = 0;
+            for ( int i = imin; i < imax; ++i )
+                for ( int j = jmin; j < jmax; ++j )
+                    for ( int k = kmin; k < kmax; ++k )
+                    {
+                        const auto cell = lcl.cardinalBinIndex( i, j, k );
+                        for ( int q = 0; q < m.counts[cell]; ++q )
+                            sid += (long long)( m.offsets[cell] + q ); // sorted: id = slot
+                        c += m.counts[cell];
+                    }
+            ok2 = ok2 && nn[p] == c && sum[p] == sid;
+            total += c;
+        }
+        EXPECT_TRUE( ok2 );
+        EXPECT_TRUE( total > (long long)n );
+        cudaFree( d_nn );
+        cudaFree( d_sum );
+    }
     cudaFree( d_x );
     cudaFree( d_y );
     cudaFree( d_bad );
