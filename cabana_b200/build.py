@@ -18,8 +18,8 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcabana_b200.so")
 STAMP = os.path.join(LIB_DIR, "build.stamp")
 
-SOURCES = ["cb_core.cu", "cb_scan.cu", "cb_lcl.cu", "cb_verlet.cu", "cb_verlet_fine.cu", "cb_traverse.cu", "cb_comm.cu"]
-HEADERS = ["cb_common.cuh", "cb_internal.h", "cb_verlet_fine.h", os.path.join(ROOT, "include", "cabana_b200.h")]
+SOURCES = ["cb_core.cu", "cb_scan.cu", "cb_lcl.cu", "cb_verlet.cu", "cb_verlet_fine.cu", "cb_verlet_tile.cu", "cb_traverse.cu", "cb_comm.cu"]
+HEADERS = ["cb_common.cuh", "cb_internal.h", "cb_verlet_fine.h", "cb_verlet_tile.h", os.path.join(ROOT, "include", "cabana_b200.h")]
 
 NVCC = os.environ.get("CB_NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"  # the image's $CXX wrapper lacks libgomp.spec; use the system g++

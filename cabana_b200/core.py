@@ -321,6 +321,16 @@ class VerletList:
             C.c_int(self.algorithm), C.c_int(self.layout), C.c_int(self.build_tag), _stream()))
         self._refresh()
 
+    def filter_selftest(self, x: Slice, neighborhood_radius, grid_min, grid_max):
+        """cb_verlet_filter_selftest: (largest |tensor-core filter - exact FP64| seen over every
+        tested pair, the bound the build's decisions assume)."""
+        d = x.positions_desc()
+        out = (C.c_double * 2)()
+        capi.check(capi.lib().cb_verlet_filter_selftest(
+            self._h, C.byref(d), C.c_double(neighborhood_radius), capi.d3(grid_min), capi.d3(grid_max),
+            C.c_int(self.algorithm), out, _stream()))
+        return float(out[0]), float(out[1])
+
     def copy_to_host(self, counts_h: torch.Tensor, offsets_h: torch.Tensor | None, neighbors_h: torch.Tensor):
         capi.check(capi.lib().cb_verlet_copy_to_host(
             self._h, C.c_void_p(counts_h.data_ptr()),

@@ -27,6 +27,7 @@
 #include "cb_common.cuh"
 #include "cb_internal.h"
 #include "cb_verlet_fine.h"
+#include "cb_verlet_tile.h"
 
 namespace cb
 {
@@ -263,6 +264,8 @@ struct cb_verlet
     // workspace
     DeviceBuffer cell_counts, cell_off, permute, cell_of, rank, scan, xs, ys, zs, q, stats;
     DeviceBuffer worklist, tmp, tmp_off, ctrl;
+    // v2 (tile) workspace
+    DeviceBuffer block_tiles, tile_base, recs, tile_chunks, chunk_off, masks;
     DeviceBuffer host_stage; // device copy of host positions (build_host)
     PinnedScalars pinned;
     // optional phase timing
@@ -302,6 +305,209 @@ extern "C" int cb_verlet_create( cb_verlet** out )
 extern "C" int cb_verlet_destroy( cb_verlet* v )
 {
     delete v;
+    return CB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// v2 build: internal pencil grid -> bin -> gather q -> plan tiles -> count pass (tensor-core
+// distance tiles, hit masks) -> processCounts (:507-562) -> fill pass.  diag != nullptr runs
+// the filter self-test instead of the count pass: diag[0] = max |c_mma - c_exact| seen,
+// diag[1] = the bound tau/2 the decisions rely on.
+// ---------------------------------------------------------------------------------------
+static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, long long end,
+                       double radius, const cb_grid& ugrid, int cell_range,
+                       const double* grid_min, const double* grid_max, long long max_neigh,
+                       int algorithm, int layout, cudaStream_t stream, double* diag )
+{
+    const long long n = x->n;
+    const size_t na = (size_t)( n > 0 ? n : 1 );
+    const bool half = algorithm == CB_NEIGHBOR_HALF;
+    const bool csr = layout == CB_LAYOUT_CSR;
+    const double rsqr = radius * radius; // :239
+
+    TileGrid tg;
+    make_tile_grid( tg, grid_min, grid_max, radius, n );
+    const long long rec_capacity = n / kTileHomes + tg.nblocks + 2;
+
+    CB_TRY( v->pinned.ensure() );
+    CB_TRY( v->stats.ensure( 4 * sizeof( long long ) ) );
+    CB_TRY( v->ctrl.ensure( 64 ) );
+    CB_TRY( v->counts.ensure( sizeof( int ) * na, 1.1 ) );
+    if ( csr )
+        CB_TRY( v->offsets.ensure( sizeof( int ) * ( na + 1 ), 1.1 ) );
+    CB_TRY( v->cell_counts.ensure( sizeof( int ) * (size_t)tg.ncells ) );
+    CB_TRY( v->cell_off.ensure( sizeof( unsigned ) * (size_t)( tg.ncells + 1 ) ) );
+    CB_TRY( v->permute.ensure( sizeof( unsigned ) * na, 1.1 ) );
+    CB_TRY( v->cell_of.ensure( sizeof( int ) * na, 1.1 ) );
+    CB_TRY( v->q.ensure( sizeof( float4 ) * ( na + 8 ), 1.1 ) );
+    CB_TRY( v->block_tiles.ensure( sizeof( int ) * (size_t)( tg.nblocks + 1 ) ) );
+    CB_TRY( v->tile_base.ensure( sizeof( int ) * (size_t)( tg.nblocks + 1 ) ) );
+    CB_TRY( v->recs.ensure( sizeof( uint4 ) * (size_t)rec_capacity, 1.1 ) );
+    CB_TRY( v->tile_chunks.ensure( sizeof( int ) * (size_t)rec_capacity, 1.1 ) );
+    CB_TRY( v->chunk_off.ensure( sizeof( int ) * (size_t)( rec_capacity + 1 ), 1.1 ) );
+
+    for ( auto& f : v->ev_valid )
+        f = false;
+    v->mark( 0, stream );
+    CB_CUDA( cudaMemsetAsync( v->counts.ptr, 0, sizeof( int ) * na, stream ) ); // :215-216
+
+    // LCL over ALL particles, not just [begin,end) (:229-235), on the internal grid
+    CB_TRY( bin_particles( tg.g, *x, 0, n, v->cell_counts.as<int>(),
+                           v->cell_off.as<unsigned>(), v->permute.as<unsigned>(),
+                           v->cell_of.as<int>(), v->rank, v->scan, stream, 1 ) );
+    v->mark( 1, stream );
+    CB_TRY( tile_gather_q( *x, n, v->permute.as<unsigned>(), v->q.as<float4>(), tg.g.min,
+                           stream ) );
+    CB_TRY( tile_plan( tg, v->cell_off.as<unsigned>(), half, v->block_tiles.as<int>(),
+                       v->tile_base.as<int>(), v->recs.as<uint4>(),
+                       v->tile_chunks.as<int>(), v->chunk_off.as<int>(), rec_capacity,
+                       v->scan, stream ) );
+    v->mark( 2, stream );
+
+    TileArgs a;
+    memset( &a, 0, sizeof( a ) );
+    a.q = v->q.as<float4>();
+    a.permute = v->permute.as<unsigned>();
+    a.cell_off = v->cell_off.as<unsigned>();
+    a.x = make_access( *x );
+    a.ncx = tg.ncx;
+    a.ncy = tg.ncy;
+    a.nz = tg.nz;
+    a.zb = tg.zb;
+    a.nzb = tg.nzb;
+    a.kz = tg.kz;
+    a.wx = (float)tg.g.dx[0];
+    a.wy = (float)tg.g.dx[1];
+    a.hz = (float)tg.g.dx[2];
+    a.recs = v->recs.as<uint4>();
+    a.chunk_off = v->chunk_off.as<int>();
+    a.ntiles_dev = v->tile_base.as<int>() + tg.nblocks;
+    a.ticket = reinterpret_cast<unsigned*>( v->ctrl.as<char>() );
+    a.overflow = reinterpret_cast<int*>( v->ctrl.as<char>() + 8 );
+    a.diag_maxerr = reinterpret_cast<unsigned*>( v->ctrl.as<char>() + 16 );
+    a.ug = to_grid( ugrid );
+    a.R = cell_range;
+    a.rsqr = rsqr;
+    {
+        double extent = 0.0, cmax = 0.0;
+        for ( int d = 0; d < 3; ++d )
+        {
+            extent = fmax( extent, grid_max[d] - grid_min[d] );
+            cmax = fmax( cmax, fmax( fabs( grid_min[d] ), fabs( grid_max[d] ) ) );
+        }
+        // Band in which the reference's cell prune can reject an in-range pair: its min
+        // distance is computed with O(ulp(coordinate)) error.
+        const double eta = ldexp( cmax + extent + radius, -46 );
+        a.band = 8.0 * radius * eta + 4.0 * eta * eta + ldexp( rsqr, -44 );
+        // tf32 split of r^2 (both parts exactly representable)
+        float hi = (float)rsqr;
+        unsigned hb;
+        memcpy( &hb, &hi, 4 );
+        hb &= 0xffffe000u;
+        memcpy( &hi, &hb, 4 );
+        float lo = (float)( rsqr - (double)hi );
+        memcpy( &hb, &lo, 4 );
+        hb &= 0xffffe000u;
+        memcpy( &lo, &hb, 4 );
+        a.r2hi = hi;
+        a.r2lo = lo;
+        const double bound = tile_filter_bound( tg, radius );
+        a.tau = nextafterf( (float)( 2.0 * bound ), INFINITY );
+        if ( diag )
+            diag[1] = bound;
+    }
+    a.n = n;
+    a.begin = begin;
+    a.end = end;
+    a.counts = v->counts.as<int>();
+
+    long long* stats_dev = v->stats.as<long long>();
+    long long* stats_h = v->pinned.ptr;
+
+    if ( diag )
+    {
+        CB_CUDA( cudaMemsetAsync( v->ctrl.ptr, 0, 64, stream ) );
+        a.mask_capacity = 1ll << 40;
+        if ( n > 0 )
+            CB_TRY( tile_diag_pass( a, half, stream ) );
+        CB_CUDA( cudaMemcpyAsync( stats_h, v->ctrl.ptr, 32, cudaMemcpyDeviceToHost, stream ) );
+        CB_CUDA( cudaStreamSynchronize( stream ) );
+        float e;
+        memcpy( &e, reinterpret_cast<char*>( stats_h ) + 16, 4 );
+        diag[0] = (double)e;
+        return CB_OK;
+    }
+
+    // first guess of the mask buffer (~100 B per particle at liquid densities); the count
+    // pass reports the exact need if it does not fit
+    if ( v->masks.capacity == 0 )
+        CB_TRY( v->masks.ensure( (size_t)( 128.0 * (double)n ) + ( 1u << 20 ) ) );
+    for ( int attempt = 0;; ++attempt )
+    {
+        a.masks = v->masks.as<uint4>();
+        a.mask_capacity = (long long)( v->masks.capacity / ( kChunkWords * 4 ) );
+        CB_CUDA( cudaMemsetAsync( v->ctrl.ptr, 0, 64, stream ) );
+        if ( n > 0 )
+            CB_TRY( tile_count_pass( a, half, stream ) );
+        v->mark( 3, stream );
+        CB_TRY( max_and_sum_i32( v->counts.as<int>(), n, stats_dev, stream ) );
+        if ( csr )
+            CB_TRY( exclusive_scan_i32( v->counts.as<int>(), v->offsets.as<int>(), n, false,
+                                        nullptr, v->scan, stream ) );
+        CB_CUDA( cudaMemcpyAsync( stats_h, stats_dev, 2 * sizeof( long long ),
+                                  cudaMemcpyDeviceToHost, stream ) );
+        CB_CUDA( cudaMemcpyAsync( stats_h + 2, v->ctrl.ptr, 2 * sizeof( long long ),
+                                  cudaMemcpyDeviceToHost, stream ) );
+        CB_CUDA( cudaMemcpyAsync( stats_h + 4, v->chunk_off.as<int>() + rec_capacity,
+                                  sizeof( int ), cudaMemcpyDeviceToHost, stream ) );
+        v->mark( 4, stream );
+        CB_CUDA( cudaStreamSynchronize( stream ) ); // sizes the allocation (:518-528)
+        const int overflowed = (int)( stats_h[3] & 0xffffffffll );
+        if ( !overflowed )
+            break;
+        if ( attempt >= 1 )
+            return fail( CB_ERR_NOMEM, "cb_verlet_build: mask buffer kept overflowing" );
+        const long long chunks = (long long)( stats_h[4] & 0xffffffffll );
+        CB_TRY( v->masks.ensure( (size_t)( chunks + 16 ) * kChunkWords * 4, 1.05 ) );
+        CB_CUDA( cudaMemsetAsync( v->counts.ptr, 0, sizeof( int ) * na, stream ) );
+    }
+    v->max_n = stats_h[0];
+    v->total = stats_h[1];
+    v->extent = v->total;
+    if ( csr )
+    {
+        if ( v->total > 2147483647ll )
+            return fail( CB_ERR_OVERFLOW, "cb_verlet_build: total neighbours exceed INT_MAX" );
+        CB_TRY( v->neighbors.ensure( sizeof( int ) * (size_t)( v->total > 0 ? v->total : 1 ),
+                                     1.05 ) );
+        a.offsets = v->offsets.as<int>();
+        a.width = 0;
+    }
+    else
+    {
+        // initCounts / processCounts(2D) (:495-505, :536-562): keep max_neigh when it is
+        // enough, otherwise reallocate to exactly max_n ("refill")
+        if ( max_neigh > 0 && v->max_n <= max_neigh )
+            v->width = max_neigh;
+        else
+        {
+            v->width = v->max_n;
+            if ( max_neigh > 0 )
+                v->refilled = 1;
+        }
+        if ( (double)na * (double)v->width > 9.0e18 )
+            return fail( CB_ERR_OVERFLOW, "cb_verlet_build: 2D list too large" );
+        CB_TRY( v->neighbors.ensure( sizeof( int ) * na *
+                                     (size_t)( v->width > 0 ? v->width : 1 ) ) );
+        a.offsets = nullptr;
+        a.width = v->width;
+    }
+    a.neighbors = v->neighbors.as<int>();
+    if ( n > 0 && v->total > 0 )
+        CB_TRY( tile_fill_pass( a, half, csr, stream ) );
+    v->mark( 5, stream );
+    v->built = true;
     return CB_OK;
 }
 
@@ -352,9 +558,24 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
     const int cell_range = cb_stencil_cell_range( cell_size_ratio );
     const double rsqr = radius * radius; // :239
 
-    // Kernel generation: v1 (refined grid + FP32 filter, default) or v0 (CB_VERLET_IMPL=v0).
+    // Kernel generation: v2 (tile kernels, default), v1 (refined grid + FP32 SIMT filter,
+    // CB_VERLET_IMPL=v1) or v0 (reference-shaped exact FP64, CB_VERLET_IMPL=v0).
     const char* impl_env = getenv( "CB_VERLET_IMPL" );
     const bool use_v0 = impl_env && strcmp( impl_env, "v0" ) == 0;
+    const bool use_v1 = impl_env && strcmp( impl_env, "v1" ) == 0;
+    if ( !use_v0 && !use_v1 )
+    {
+        v->built = false;
+        v->layout = layout;
+        v->algorithm = algorithm;
+        v->n = n;
+        v->total = 0;
+        v->max_n = 0;
+        v->width = 0;
+        v->refilled = 0;
+        return build_tile( v, x, begin, end, radius, grid, cell_range, grid_min, grid_max,
+                           max_neigh, algorithm, layout, stream, nullptr );
+    }
     int refine = 1;
     if ( !use_v0 )
     {
@@ -714,6 +935,22 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
     }
     v->built = true;
     return CB_OK;
+}
+
+extern "C" int cb_verlet_filter_selftest( cb_verlet* v, const cb_positions* x, double radius,
+                                          const double* grid_min, const double* grid_max,
+                                          int algorithm, double* out_h, cb_stream_t stream_ )
+{
+    if ( !v || !x || !grid_min || !grid_max || !out_h )
+        return fail( CB_ERR_INVALID, "cb_verlet_filter_selftest: null argument" );
+    if ( !( radius > 0.0 ) || x->vlen < 1 || x->n >= 2147483647ll )
+        return fail( CB_ERR_INVALID, "cb_verlet_filter_selftest: bad argument" );
+    const double delta[3] = { radius, radius, radius };
+    cb_grid grid;
+    cb_grid_init( &grid, grid_min, grid_max, delta );
+    v->built = false;
+    return build_tile( v, x, 0, x->n, radius, grid, 1, grid_min, grid_max, 0, algorithm,
+                       CB_LAYOUT_CSR, (cudaStream_t)stream_, out_h );
 }
 
 extern "C" int cb_verlet_set_profiling( cb_verlet* v, int enable )

@@ -264,6 +264,15 @@ int cb_verlet_destroy(cb_verlet* list);
 int cb_verlet_set_profiling(cb_verlet* list, int enable);
 int cb_verlet_get_phase_times(const cb_verlet* list, double* ms_h);
 
+/* Self-test of the tensor-core distance filter the build relies on (tests only): runs the
+ * count pass over `x` with EVERY filter value compared with the exact FP64 arithmetic.
+ * out_h[0] = largest |filter - exact| observed, out_h[1] = the proven bound the in/out
+ * decisions assume (values closer than twice that to the cutoff go to the exact tier). */
+int cb_verlet_filter_selftest(cb_verlet* list, const cb_positions* x,
+                              double neighborhood_radius, const double* grid_min_h,
+                              const double* grid_max_h, int algorithm, double* out_h,
+                              cb_stream_t stream);
+
 /* Host-buffer entry points (the end-to-end path): positions live in HOST memory
  * (x_h->base is a host pointer; pinned memory makes the copies asynchronous), the
  * list is built on the device and copied back into caller-provided host arrays.

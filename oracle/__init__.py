@@ -30,8 +30,47 @@ def build(force: bool = False) -> str:
         or not os.path.exists(_LIB_PATH)
         or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)
     ):
-        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle_cabana.so"], check=True, capture_output=True)
     return _LIB_PATH
+
+
+_NATIVE_PATH = os.path.join(_HERE, "liboracle_cabana_native.so")
+_NATIVE_STAMP = _NATIVE_PATH + ".host"
+
+
+def _host_tag() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    import hashlib
+                    return hashlib.sha1(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def use_native_build() -> bool:
+    """Switch this process to the -march=native copy (bench.py's timed CPU legs).  It is compiled
+    on the host that runs it (the instruction set of the build container and of the GPU box's
+    host may differ); returns False and keeps the portable copy when that fails."""
+    global _lib
+    src = os.path.join(_HERE, "cabana_oracle.cpp")
+    tag = _host_tag()
+    try:
+        stale = (not os.path.exists(_NATIVE_PATH) or os.path.getmtime(_NATIVE_PATH) < os.path.getmtime(src)
+                 or not os.path.exists(_NATIVE_STAMP) or open(_NATIVE_STAMP).read() != tag)
+        if stale:
+            subprocess.run(["make", "-C", _HERE, "-B", "liboracle_cabana_native.so"], check=True,
+                           capture_output=True)
+            with open(_NATIVE_STAMP, "w") as f:
+                f.write(tag)
+        _lib = None
+        lib(_NATIVE_PATH)
+        return True
+    except Exception:
+        _lib = None
+        return False
 
 
 class _Positions(C.Structure):
@@ -75,11 +114,13 @@ class _VerletInfo(C.Structure):
 _lib = None
 
 
-def lib():
+def lib(path: str | None = None):
     global _lib
     if _lib is None:
-        build()
-        _lib = C.CDLL(_LIB_PATH)
+        if path is None:
+            build()
+            path = _LIB_PATH
+        _lib = C.CDLL(path)
         _lib.orc_grid_min_distance.restype = C.c_double
         _lib.orc_lj_energy.restype = C.c_double
         _lib.orc_grid_cardinal.restype = C.c_int
@@ -442,3 +483,24 @@ def num_threads() -> int:
 
 def set_num_threads(n: int) -> None:
     lib().orc_set_num_threads(C.c_int(n))
+
+
+def use_all_cores() -> int:
+    """torch.distributed.run exports OMP_NUM_THREADS=1: the timed CPU legs must not inherit it."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    set_num_threads(max(1, n))
+    return num_threads()
+
+
+def row_hashes(layout, counts, offsets, neighbors, width=0) -> np.ndarray:
+    """Order-independent 64-bit hash of every row (equal <=> equal sorted rows)."""
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    n = counts.shape[0]
+    nb = np.ascontiguousarray(neighbors, dtype=np.int32).reshape(-1)
+    off = np.ascontiguousarray(offsets, dtype=np.int32) if offsets is not None else None
+    out = np.empty(n, dtype=np.uint64)
+    lib().orc_row_hashes(
+        C.c_int(layout), C.c_int64(n), counts.ctypes.data_as(C.c_void_p),
+        off.ctypes.data_as(C.c_void_p) if off is not None else None,
+        nb.ctypes.data_as(C.c_void_p), C.c_int64(width), out.ctypes.data_as(C.c_void_p))
+    return out

@@ -48,8 +48,14 @@ typedef struct
 
 static inline double pos_at( const orc_positions* x, int64_t i, int d )
 {
-    return x->base[x->outer_stride * ( i / x->vlen ) + ( i % x->vlen ) +
-                   x->comp_stride * d];
+    // vlen is a power of two for every Cabana AoSoA (and 1 for views): shift/mask instead of
+    // a 64-bit divide per access (the reference's Impl::Index does the same at compile time,
+    // impl/Cabana_Index.hpp:62-80).
+    const int64_t v = x->vlen;
+    if ( ( v & ( v - 1 ) ) == 0 )
+        return x->base[x->outer_stride * ( i >> __builtin_ctzll( (unsigned long long)v ) ) +
+                       ( i & ( v - 1 ) ) + x->comp_stride * d];
+    return x->base[x->outer_stride * ( i / v ) + ( i % v ) + x->comp_stride * d];
 }
 
 // -----------------------------------------------------------------------------
@@ -171,6 +177,58 @@ void orc_stencil_cells( const orc_stencil* s, int cell, int* mn, int* mx )
 // here it is ascending particle id when `parallel` == 0 (what a serial backend
 // produces) and arbitrary when `parallel` != 0 (OpenMP atomics).
 // -----------------------------------------------------------------------------
+} // extern "C"
+
+// Exclusive prefix sum (Kokkos::parallel_scan in the reference); chunked two-level scan when
+// `parallel`.  Returns the total.
+template <class Out>
+static int64_t exclusive_scan_i64( const int* in, Out* out, int64_t n, int parallel )
+{
+    int nt = 1;
+#ifdef _OPENMP
+    if ( parallel )
+        nt = omp_get_max_threads();
+#endif
+    if ( nt <= 1 || n < 65536 )
+    {
+        int64_t update = 0;
+        for ( int64_t c = 0; c < n; ++c )
+        {
+            out[c] = (Out)update;
+            update += in[c];
+        }
+        return update;
+    }
+    std::vector<int64_t> part( nt + 1, 0 );
+    const int64_t chunk = ( n + nt - 1 ) / nt;
+#pragma omp parallel num_threads( nt )
+    {
+        int t = 0;
+#ifdef _OPENMP
+        t = omp_get_thread_num();
+#endif
+        const int64_t lo = std::min<int64_t>( n, chunk * t );
+        const int64_t hi = std::min<int64_t>( n, lo + chunk );
+        int64_t sum = 0;
+        for ( int64_t c = lo; c < hi; ++c )
+            sum += in[c];
+        part[t + 1] = sum;
+#pragma omp barrier
+#pragma omp single
+        for ( int k = 0; k < nt; ++k )
+            part[k + 1] += part[k];
+        int64_t update = part[t];
+        for ( int64_t c = lo; c < hi; ++c )
+        {
+            out[c] = (Out)update;
+            update += in[c];
+        }
+    }
+    return part[nt];
+}
+
+extern "C" {
+
 void orc_lcl_build( const orc_grid* g, const orc_positions* x, int64_t begin,
                     int64_t end, int* counts, int64_t* offsets,
                     int64_t* permute, int* particle_bins, int parallel )
@@ -197,12 +255,7 @@ void orc_lcl_build( const orc_grid* g, const orc_positions* x, int64_t begin,
     }
 
     // offset_scan (:701-712): exclusive prefix sum.
-    int64_t update = 0;
-    for ( int64_t c = 0; c < ncell; ++c )
-    {
-        offsets[c] = update;
-        update += counts[c];
-    }
+    exclusive_scan_i64( counts, offsets, ncell, parallel );
 
     // reset + create_permute (:715-731)
     std::fill( counts, counts + ncell, 0 );
@@ -451,8 +504,14 @@ int orc_verlet_build( const orc_positions* x, int64_t begin, int64_t end,
     b.lcl_offsets.resize( ncell );
     b.lcl_permute.resize( n );
     // LCL bins ALL particles (:229-235).
+    // (threaded like the reference's OpenMP backend whenever more than one thread is
+    // available: within-cell order is unspecified there, :726)
+    int par = 0;
+#ifdef _OPENMP
+    par = omp_get_max_threads() > 1 ? 1 : 0;
+#endif
     orc_lcl_build( &b.grid, x, 0, n, b.lcl_counts.data(), b.lcl_offsets.data(),
-                   b.lcl_permute.data(), nullptr, 0 );
+                   b.lcl_permute.data(), nullptr, par );
     b.rsqr = radius * radius; // :239
 
     info->refilled = 0;
@@ -466,12 +525,7 @@ int orc_verlet_build( const orc_positions* x, int64_t begin, int64_t end,
     // processCounts
     if ( layout == ORC_CSR ) // :507-532
     {
-        int64_t total = 0;
-        for ( int64_t i = 0; i < n; ++i )
-        {
-            offsets[i] = (int)total;
-            total += counts[i];
-        }
+        const int64_t total = exclusive_scan_i64( counts, offsets, n, par );
         b.neighbors =
             (int*)std::malloc( sizeof( int ) * (size_t)std::max<int64_t>( total, 1 ) );
         std::fill( counts, counts + n, 0 );
@@ -519,6 +573,32 @@ int orc_verlet_build( const orc_positions* x, int64_t begin, int64_t end,
 }
 
 void orc_free( void* p ) { std::free( p ); }
+
+// Order-independent 64-bit hash of every row (multiset of neighbour ids): equal hashes for
+// all rows <=> equal sorted rows, without sorting 1e9 ids.  Test infrastructure for the
+// full-size parity checks.  layout CSR: row i = neighbors[offsets[i] .. +counts[i]);
+// 2D: neighbors[i*width .. +counts[i]).
+static inline uint64_t mix64( uint64_t z )
+{
+    z += 0x9e3779b97f4a7c15ull;
+    z = ( z ^ ( z >> 30 ) ) * 0xbf58476d1ce4e5b9ull;
+    z = ( z ^ ( z >> 27 ) ) * 0x94d049bb133111ebull;
+    return z ^ ( z >> 31 );
+}
+void orc_row_hashes( int layout, int64_t n, const int* counts, const int* offsets,
+                     const int* neighbors, int64_t width, uint64_t* out )
+{
+#pragma omp parallel for schedule( static )
+    for ( int64_t i = 0; i < n; ++i )
+    {
+        const int* row =
+            neighbors + ( layout == ORC_CSR ? (int64_t)offsets[i] : i * width );
+        uint64_t h = 0x1234567ull * (uint64_t)counts[i];
+        for ( int k = 0; k < counts[i]; ++k )
+            h += mix64( (uint64_t)(uint32_t)row[k] );
+        out[i] = h;
+    }
+}
 
 // -----------------------------------------------------------------------------
 // Brute-force N^2 list  (core/unit_test/neighbor_unit_test.hpp:86-158).
