@@ -265,7 +265,7 @@ struct cb_verlet
     DeviceBuffer cell_counts, cell_off, permute, cell_of, rank, scan, xs, ys, zs, q, stats;
     DeviceBuffer worklist, tmp, tmp_off, ctrl;
     // v2 (tile) workspace
-    DeviceBuffer block_tiles, tile_base, recs, tile_chunks, chunk_off, masks;
+    DeviceBuffer block_tiles, tile_base, recs, spans, tile_chunks, chunk_off, masks;
     DeviceBuffer host_stage; // device copy of host positions (build_host)
     PinnedScalars pinned;
     // optional phase timing
@@ -338,12 +338,13 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
         CB_TRY( v->offsets.ensure( sizeof( int ) * ( na + 1 ), 1.1 ) );
     CB_TRY( v->cell_counts.ensure( sizeof( int ) * (size_t)tg.ncells ) );
     CB_TRY( v->cell_off.ensure( sizeof( unsigned ) * (size_t)( tg.ncells + 1 ) ) );
-    CB_TRY( v->permute.ensure( sizeof( unsigned ) * na, 1.1 ) );
+    CB_TRY( v->permute.ensure( sizeof( unsigned ) * ( na + 8 ), 1.1 ) );
     CB_TRY( v->cell_of.ensure( sizeof( int ) * na, 1.1 ) );
     CB_TRY( v->q.ensure( sizeof( float4 ) * ( na + 8 ), 1.1 ) );
     CB_TRY( v->block_tiles.ensure( sizeof( int ) * (size_t)( tg.nblocks + 1 ) ) );
     CB_TRY( v->tile_base.ensure( sizeof( int ) * (size_t)( tg.nblocks + 1 ) ) );
     CB_TRY( v->recs.ensure( sizeof( uint4 ) * (size_t)rec_capacity, 1.1 ) );
+    CB_TRY( v->spans.ensure( sizeof( uint2 ) * 9 * (size_t)rec_capacity, 1.1 ) );
     CB_TRY( v->tile_chunks.ensure( sizeof( int ) * (size_t)rec_capacity, 1.1 ) );
     CB_TRY( v->chunk_off.ensure( sizeof( int ) * (size_t)( rec_capacity + 1 ), 1.1 ) );
 
@@ -360,7 +361,7 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
     CB_TRY( tile_gather_q( *x, n, v->permute.as<unsigned>(), v->q.as<float4>(), tg.g.min,
                            stream ) );
     CB_TRY( tile_plan( tg, v->cell_off.as<unsigned>(), half, v->block_tiles.as<int>(),
-                       v->tile_base.as<int>(), v->recs.as<uint4>(),
+                       v->tile_base.as<int>(), v->recs.as<uint4>(), v->spans.as<uint2>(),
                        v->tile_chunks.as<int>(), v->chunk_off.as<int>(), rec_capacity,
                        v->scan, stream ) );
     v->mark( 2, stream );
@@ -381,6 +382,7 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
     a.wy = (float)tg.g.dx[1];
     a.hz = (float)tg.g.dx[2];
     a.recs = v->recs.as<uint4>();
+    a.spans = v->spans.as<uint2>();
     a.chunk_off = v->chunk_off.as<int>();
     a.ntiles_dev = v->tile_base.as<int>() + tg.nblocks;
     a.ticket = reinterpret_cast<unsigned*>( v->ctrl.as<char>() );
@@ -505,7 +507,7 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
     }
     a.neighbors = v->neighbors.as<int>();
     if ( n > 0 && v->total > 0 )
-        CB_TRY( tile_fill_pass( a, half, csr, stream ) );
+        CB_TRY( tile_fill_pass( a, csr, stream ) );
     v->mark( 5, stream );
     v->built = true;
     return CB_OK;

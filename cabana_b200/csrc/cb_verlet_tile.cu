@@ -30,6 +30,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 namespace cb
 {
 namespace
@@ -39,7 +41,7 @@ constexpr int kWarpsT = 8;
 constexpr int kBlockT = kWarpsT * 32;
 constexpr int kPieceEntries = kPieceTiles * kTileCands; // 128 candidates
 constexpr int kChunkEntries = kChunkTiles * kTileCands; // 256 candidates
-constexpr int kRowCap = 2048;                           // ids staged per tile in the fill pass
+constexpr int kRowCap = 1536;                           // ids staged per tile in the fill pass
 
 // ---------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + bulk copy (TMA engine) + tf32 mma
@@ -114,17 +116,19 @@ CB_D float trunc_tf32( float v )
 struct TileRec
 {
     unsigned first;
-    int block, np, zlo, zhi, ntile8;
+    int ca, cb, np, zlo, zhi, ntile8;
 };
+// {first slot, column a | b << 16, zlo | zhi << 16, np | #mma tiles << 8}
 CB_D TileRec unpack_rec( const uint4 r )
 {
     TileRec t;
     t.first = r.x;
-    t.block = (int)( r.y & 0x3ffffffu );
-    t.np = (int)( r.y >> 26 );
+    t.ca = (int)( r.y & 0xffffu );
+    t.cb = (int)( r.y >> 16 );
     t.zlo = (int)( r.z & 0xffffu );
     t.zhi = (int)( r.z >> 16 );
-    t.ntile8 = (int)r.w;
+    t.np = (int)( r.w & 0xffu );
+    t.ntile8 = (int)( r.w >> 8 );
     return t;
 }
 
@@ -254,7 +258,8 @@ __global__ void __launch_bounds__( 128 )
     k_plan_tiles( const unsigned* __restrict__ cell_off, GridInts gi, int zb, int nzb,
                   long long nblocks, int half, const int* __restrict__ block_tiles,
                   const int* __restrict__ tile_base, uint4* __restrict__ recs,
-                  int* __restrict__ tile_chunks, long long rec_capacity )
+                  uint2* __restrict__ spans, int* __restrict__ tile_chunks,
+                  long long rec_capacity )
 {
     for ( long long b = (long long)blockIdx.x * 128 + threadIdx.x; b < nblocks;
           b += (long long)gridDim.x * 128 )
@@ -284,17 +289,21 @@ __global__ void __launch_bounds__( 128 )
                 ++zz;
             const int zhi = zz;
             int T = 0;
+            const bool fits = tb + ti < rec_capacity;
             for ( int s = 0; s < 9; ++s )
             {
                 unsigned st, len;
                 span_of( gi, cell_off, ca, cb_, zlo, zhi, half != 0, s, st, len );
                 T += (int)( ( len + kTileCands - 1 ) / kTileCands );
+                if ( fits )
+                    spans[( tb + ti ) * 9 + s] = make_uint2( st, len );
             }
-            if ( tb + ti < rec_capacity )
+            if ( fits )
             {
                 recs[tb + ti] = make_uint4(
-                    first, (unsigned)b | ( ( last - first + 1u ) << 26 ),
-                    (unsigned)zlo | ( (unsigned)zhi << 16 ), (unsigned)T );
+                    first, (unsigned)ca | ( (unsigned)cb_ << 16 ),
+                    (unsigned)zlo | ( (unsigned)zhi << 16 ),
+                    ( last - first + 1u ) | ( (unsigned)T << 8 ) );
                 tile_chunks[tb + ti] = ( T + kChunkTiles - 1 ) / kChunkTiles;
             }
         }
@@ -304,69 +313,113 @@ __global__ void __launch_bounds__( 128 )
 // ---------------------------------------------------------------------------------------
 // count pass
 // ---------------------------------------------------------------------------------------
-struct __align__( 16 ) CountSmem
+constexpr int kTableTiles = 256; // mma tiles whose source slot is tabulated at a time
+
+// Shared memory of one warp.  TMA staging: candidates land in `raw` by cp.async.bulk.
+// LDG staging: every lane fetches its candidates itself through a per-tile source table.
+struct __align__( 16 ) CountSmemTma
 {
-    float4 raw[2][kPieceEntries]; // bulk-copy landing zone (q records), double buffered
     float4 f0[kPieceEntries];     // (hx, hy, hz, n_hi) of the staged candidates
     float4 f1[kPieceEntries];     // (lx, ly, lz, n_lo)
+    float4 raw[2][kPieceEntries]; // bulk-copy landing zone (q records), double buffered
     unsigned sp_start[16], sp_len[16], sp_pos[16];
+    float kscr[16]; // |x_i|^2 - r^2 of the home particles (accumulator init)
     unsigned long long mbar[2];
+    CB_D int cand_pid( int buf, int e ) const { return __float_as_int( raw[buf][e].w ); }
+};
+struct __align__( 16 ) CountSmemLdg
+{
+    float4 f0[kPieceEntries];
+    float4 f1[kPieceEntries];
+    int cpid[kPieceEntries];        // particle ids of the staged candidates (exact tier)
+    unsigned tsrc[kTableTiles];     // sorted slot of the first entry of every mma tile
+    unsigned char tval[kTableTiles]; // valid entries (1..8) of every mma tile
+    float kscr[16];
+    CB_D int cand_pid( int, int e ) const { return cpid[e]; }
 };
 
-// Stage piece `pc` (candidate list entries [128 pc, 128 pc + 128)) into raw[buf]: padding
-// is pre-filled with far-away sentinels, then every span that intersects the piece is one
-// bulk copy (16-byte records, 16-byte aligned on both sides).  All lanes call.
-CB_D void issue_piece( CountSmem& S, const float4* __restrict__ q, int pc, int buf,
-                       unsigned lane )
+// Stage piece `pc` (candidate list entries [128 pc, 128 pc + 128)) into raw[buf]: every span
+// that intersects the piece is one bulk copy (16-byte records, 16-byte aligned on both
+// sides); the <= 7 padding entries behind a span's end and the tail behind the last tile
+// are filled with far-away sentinels by ordinary stores (disjoint from what the copies
+// write, so no proxy fence is needed; the buffer's previous readers finished before the
+// __syncwarp that precedes this call).  All lanes call.
+CB_D void issue_piece( CountSmemTma& S, const float4* __restrict__ q, int pc, int buf,
+                       int total_entries, unsigned lane )
 {
     const float4 sent = make_float4( 1.0e18f, 1.0e18f, 1.0e18f, __int_as_float( -1 ) );
-#pragma unroll
-    for ( int j = 0; j < kPieceEntries / 32; ++j )
-        S.raw[buf][(int)lane + 32 * j] = sent;
-    fence_proxy_async(); // generic-proxy stores before the async-proxy writes
-    __syncwarp();
+    const unsigned p0 = (unsigned)( pc * kPieceEntries );
+    const unsigned p1 = p0 + kPieceEntries;
     unsigned lo = 0u, hi = 0u, p = 0u;
     if ( lane < 9u )
     {
         p = S.sp_pos[lane];
-        lo = max( p, (unsigned)( pc * kPieceEntries ) );
-        hi = min( p + S.sp_len[lane], (unsigned)( ( pc + 1 ) * kPieceEntries ) );
+        const unsigned end = p + S.sp_len[lane];
+        lo = max( p, p0 );
+        hi = min( end, p1 );
         if ( hi < lo )
             hi = lo;
+        // padding behind this span's end, if the end lies in this piece
+        if ( end > p0 && end <= p1 && S.sp_len[lane] != 0u )
+            for ( unsigned e = end; ( e & 7u ) != 0u; ++e )
+                S.raw[buf][e - p0] = sent;
     }
+    // tail behind the last tile (last piece only)
+    for ( unsigned e = max( (unsigned)total_entries, p0 ) + lane; e < p1; e += 32u )
+        S.raw[buf][e - p0] = sent;
     const unsigned bytes = ( hi - lo ) * 16u;
     const unsigned total = __reduce_add_sync( kFullMask, bytes );
     if ( lane == 0u )
         mbar_expect_tx( &S.mbar[buf], total );
     __syncwarp();
     if ( bytes )
-        bulk_g2s( &S.raw[buf][lo - (unsigned)( pc * kPieceEntries )],
-                  q + S.sp_start[lane] + ( lo - p ), bytes, &S.mbar[buf] );
+        bulk_g2s( &S.raw[buf][lo - p0], q + S.sp_start[lane] + ( lo - p ), bytes,
+                  &S.mbar[buf] );
 }
 
-template <bool HALF, bool DIAG>
-__global__ void __launch_bounds__( kBlockT, 2 )
+// Source table of the mma tiles [seg0, seg0 + kTableTiles): the lane that owns span s
+// writes the entries of its tiles (tile k of the span starts at sorted slot start + 8k).
+template <class SM>
+CB_D void build_tile_table( SM& S, int seg0, int tiles_before, int my_nt, unsigned sp_start,
+                            unsigned sp_len )
+{
+    const int i0 = max( 0, seg0 - tiles_before );
+    const int i1 = min( my_nt, seg0 + kTableTiles - tiles_before );
+    for ( int i = i0; i < i1; ++i )
+    {
+        const int k = tiles_before + i - seg0;
+        S.tsrc[k] = sp_start + (unsigned)( kTileCands * i );
+        S.tval[k] = (unsigned char)min( (unsigned)kTileCands,
+                                        sp_len - (unsigned)( kTileCands * i ) );
+    }
+}
+
+template <bool HALF, bool DIAG, bool TMA>
+__global__ void __launch_bounds__( kBlockT, 3 )
     k_tile_count( const __grid_constant__ TileArgs a )
 {
+    using SM = typename std::conditional<TMA, CountSmemTma, CountSmemLdg>::type;
     extern __shared__ __align__( 16 ) unsigned char s_dyn[];
     const unsigned lane = threadIdx.x & 31u;
     const int wib = threadIdx.x >> 5;
-    CountSmem& S = reinterpret_cast<CountSmem*>( s_dyn )[wib];
+    SM& S = reinterpret_cast<SM*>( s_dyn )[wib];
     const int g = (int)( lane >> 2 ), t = (int)( lane & 3u );
-    if ( lane == 0u )
-    {
-        mbar_init( &S.mbar[0], 1u );
-        mbar_init( &S.mbar[1], 1u );
-    }
-    fence_mbar_init();
-    fence_proxy_async();
-    __syncwarp();
     unsigned phase = 0u; // bit b: parity the next wait on mbar[b] uses
+    if constexpr ( TMA )
+    {
+        if ( lane == 0u )
+        {
+            mbar_init( &S.mbar[0], 1u );
+            mbar_init( &S.mbar[1], 1u );
+        }
+        fence_mbar_init();
+        fence_proxy_async();
+        __syncwarp();
+    }
     const int ntiles = *a.ntiles_dev;
-    const GridInts gi = { a.ncx, a.ncy, a.nz, a.kz };
-    const float zero4[4] = { 0.f, 0.f, 0.f, 0.f };
     float* f0w = reinterpret_cast<float*>( S.f0 );
     float* f1w = reinterpret_cast<float*>( S.f1 );
+    const float4 sent = make_float4( 1.0e18f, 1.0e18f, 1.0e18f, __int_as_float( -1 ) );
 
     for ( ;; )
     {
@@ -378,9 +431,6 @@ __global__ void __launch_bounds__( kBlockT, 2 )
             break;
         const TileRec rc = unpack_rec( a.recs[tile] );
         const int chunk0 = a.chunk_off[tile];
-        const int col = rc.block / a.nzb;
-        const int ca = col / a.ncy;
-        const int cb_ = col - ca * a.ncy;
 
         // ---- home particles (lanes 0..15) ------------------------------------------
         float4 hq = make_float4( -1.0e18f, -1.0e18f, -1.0e18f, __int_as_float( -1 ) );
@@ -398,41 +448,28 @@ __global__ void __launch_bounds__( kBlockT, 2 )
                 *a.overflow = 1; // the host grows the mask buffer and reruns
             continue;
         }
-        const float Ox = ( (float)ca + 0.5f ) * a.wx;
-        const float Oy = ( (float)cb_ + 0.5f ) * a.wy;
+        const float Ox = ( (float)rc.ca + 0.5f ) * a.wx;
+        const float Oy = ( (float)rc.cb + 0.5f ) * a.wy;
         const float Oz = ( 0.5f * (float)( rc.zlo + rc.zhi ) + 0.5f ) * a.hz;
         const float xh = hq.x - Ox, yh = hq.y - Oy, zh = hq.z - Oz;
+        // candidate spans (planned): lane s < 9 owns span s
+        uint2 sp = make_uint2( 0u, 0u );
+        if ( lane < 9u )
+            sp = a.spans[(size_t)tile * 9u + lane];
         __syncwarp();
         if ( lane < 16u )
         {
-            // A operands of the two MMAs, one row per home particle (see mma_tf32):
-            //   A1 = [-2H | -2H] with 1 in slot 3 and 7;  A2 = [-2L, 0 | N_hi, N_lo, -r2hi, -r2lo]
+            // A operands, one row per home particle (see mma_tf32):
+            //   A1 = [-2H, 1 | -2H, 1]   A2 = [-2L, 0 | -2L, 0]   C = |x_i|^2 - r^2
             const float Hx = trunc_tf32( xh ), Hy = trunc_tf32( yh ), Hz = trunc_tf32( zh );
             const float N = fmaf( zh, zh, fmaf( yh, yh, xh * xh ) );
-            const float Nh = trunc_tf32( N );
             S.f0[lane] = make_float4( -2.f * Hx, -2.f * Hy, -2.f * Hz, 1.f );
             S.f1[lane] = make_float4( -2.f * ( xh - Hx ), -2.f * ( yh - Hy ),
                                       -2.f * ( zh - Hz ), 0.f );
-            S.raw[1][lane] = make_float4( Nh, N - Nh, -a.r2hi, -a.r2lo );
+            // (N - r2hi) - r2lo: N and r2hi are close in magnitude, r2lo is the small part
+            S.kscr[lane] = ( N - a.r2hi ) - a.r2lo;
         }
-        __syncwarp();
-        const float a1_lo = f0w[4 * g + t], a1_hi = f0w[4 * ( g + 8 ) + t];
-        const float a2_lo = f1w[4 * g + t], a2_hi = f1w[4 * ( g + 8 ) + t];
-        const float a2p_lo = reinterpret_cast<float*>( S.raw[1] )[4 * g + t];
-        const float a2p_hi = reinterpret_cast<float*>( S.raw[1] )[4 * ( g + 8 ) + t];
-        const float hx_g = __shfl_sync( kFullMask, xh, g );
-        const float hx_g8 = __shfl_sync( kFullMask, xh, g + 8 );
-        const int pid_g = __shfl_sync( kFullMask, pid, g );
-        const int pid_g8 = __shfl_sync( kFullMask, pid, g + 8 );
-        const bool act_g = ( actmask >> g ) & 1u;
-        const bool act_g8 = ( actmask >> ( g + 8 ) ) & 1u;
-
-        // ---- candidate spans -------------------------------------------------------
-        unsigned sp_start = 0u, sp_len = 0u;
-        if ( lane < 9u )
-            span_of( gi, a.cell_off, ca, cb_, rc.zlo, rc.zhi, HALF, (int)lane, sp_start,
-                     sp_len );
-        const int my_nt = (int)( ( sp_len + kTileCands - 1 ) / kTileCands );
+        const int my_nt = (int)( ( sp.y + kTileCands - 1 ) / kTileCands );
         int incl = my_nt;
 #pragma unroll
         for ( int o = 1; o < 16; o <<= 1 )
@@ -443,22 +480,41 @@ __global__ void __launch_bounds__( kBlockT, 2 )
         }
         const int T = __shfl_sync( kFullMask, incl, 15 );
         const int T0 = __shfl_sync( kFullMask, incl, 2 ); // tiles of the da = 0 spans
-        const unsigned my_pos = (unsigned)( incl - my_nt ) * kTileCands;
-        __syncwarp();
-        if ( lane < 16u )
-        {
-            S.sp_start[lane] = sp_start;
-            S.sp_len[lane] = sp_len;
-            S.sp_pos[lane] = my_pos;
-        }
+        const int tiles_before = incl - my_nt;
         // list position of home particle h: selfbase + h (the home span is s = 1)
         const unsigned selfbase =
-            __shfl_sync( kFullMask, my_pos - sp_start, 1 ) + rc.first;
+            __shfl_sync( kFullMask, (unsigned)tiles_before * kTileCands - sp.x, 1 ) + rc.first;
         __syncwarp();
+        const float a1_lo = f0w[4 * g + t], a1_hi = f0w[4 * ( g + 8 ) + t];
+        const float a2_lo = f1w[4 * g + t], a2_hi = f1w[4 * ( g + 8 ) + t];
+        const float k_g = S.kscr[g], k_g8 = S.kscr[g + 8];
+        const float cinit[4] = { k_g, k_g, k_g8, k_g8 };
+        const float hx_g = __shfl_sync( kFullMask, xh, g );
+        const float hx_g8 = __shfl_sync( kFullMask, xh, g + 8 );
+        const int pid_g = __shfl_sync( kFullMask, pid, g );
+        const int pid_g8 = __shfl_sync( kFullMask, pid, g + 8 );
+        const bool act_g = ( actmask >> g ) & 1u;
+        const bool act_g8 = ( actmask >> ( g + 8 ) ) & 1u;
+        __syncwarp();
+        if constexpr ( TMA )
+        {
+            if ( lane < 16u )
+            {
+                S.sp_start[lane] = sp.x;
+                S.sp_len[lane] = sp.y;
+                S.sp_pos[lane] = (unsigned)tiles_before * kTileCands;
+            }
+            __syncwarp();
+            issue_piece( S, a.q, 0, 0, T * kTileCands, lane );
+        }
+        else
+        {
+            build_tile_table( S, 0, tiles_before, my_nt, sp.x, sp.y );
+            __syncwarp();
+        }
 
         // ---- pieces ----------------------------------------------------------------
         const int npieces = ( T + kPieceTiles - 1 ) / kPieceTiles;
-        issue_piece( S, a.q, 0, 0, lane );
         unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
         float ma = 3.0e38f;
         int cnt_g = 0, cnt_g8 = 0;
@@ -466,24 +522,50 @@ __global__ void __launch_bounds__( kBlockT, 2 )
         for ( int pc = 0; pc < npieces; ++pc )
         {
             const int buf = pc & 1;
-            if ( pc + 1 < npieces )
-                issue_piece( S, a.q, pc + 1, buf ^ 1, lane );
-            while ( !mbar_try_wait( &S.mbar[buf], ( phase >> buf ) & 1u ) )
+            if constexpr ( TMA )
             {
+                if ( pc + 1 < npieces )
+                    issue_piece( S, a.q, pc + 1, buf ^ 1, T * kTileCands, lane );
+                while ( !mbar_try_wait( &S.mbar[buf], ( phase >> buf ) & 1u ) )
+                {
+                }
+                phase ^= 1u << buf;
+                __syncwarp(); // the sentinel stores of other lanes
             }
-            phase ^= 1u << buf;
+            else if ( pc > 0 && ( pc * kPieceTiles ) % kTableTiles == 0 )
+            {
+                build_tile_table( S, pc * kPieceTiles, tiles_before, my_nt, sp.x, sp.y );
+                __syncwarp();
+            }
             // transform: tile-local coordinates, tf32 hi/lo split, squared norm
+            float4 r[kPieceEntries / 32];
 #pragma unroll
             for ( int j = 0; j < kPieceEntries / 32; ++j )
             {
                 const int e = (int)lane + 32 * j;
-                const float4 r = S.raw[buf][e];
-                const float x = r.x - Ox, y = r.y - Oy, z = r.z - Oz;
+                if constexpr ( TMA )
+                    r[j] = S.raw[buf][e];
+                else
+                {
+                    const int tl = pc * kPieceTiles + ( e >> 3 );
+                    const int k = tl & ( kTableTiles - 1 );
+                    r[j] = sent;
+                    if ( tl < T && ( e & 7 ) < (int)S.tval[k] )
+                        r[j] = a.q[S.tsrc[k] + (unsigned)( e & 7 )];
+                }
+            }
+#pragma unroll
+            for ( int j = 0; j < kPieceEntries / 32; ++j )
+            {
+                const int e = (int)lane + 32 * j;
+                const float x = r[j].x - Ox, y = r[j].y - Oy, z = r[j].z - Oz;
                 const float hx = trunc_tf32( x ), hy = trunc_tf32( y ), hz = trunc_tf32( z );
                 const float n = fmaf( z, z, fmaf( y, y, x * x ) );
                 const float nh = trunc_tf32( n );
                 S.f0[e] = make_float4( hx, hy, hz, nh );
                 S.f1[e] = make_float4( x - hx, y - hy, z - hz, n - nh );
+                if constexpr ( !TMA )
+                    S.cpid[e] = __float_as_int( r[j].w );
             }
             __syncwarp();
             const int nt_p = min( kPieceTiles, T - pc * kPieceTiles );
@@ -493,8 +575,8 @@ __global__ void __launch_bounds__( kBlockT, 2 )
                 const float b0 = f0w[32 * j + (int)lane];
                 const float b1 = f1w[32 * j + (int)lane];
                 float c1[4], c[4];
-                mma_tf32( c1, a1_lo, a1_hi, a1_lo, a1_hi, b0, b1, zero4 );
-                mma_tf32( c, a2_lo, a2_hi, a2p_lo, a2p_hi, b0, 1.0f, c1 );
+                mma_tf32( c1, a1_lo, a1_hi, a1_lo, a1_hi, b0, b1, cinit );
+                mma_tf32( c, a2_lo, a2_hi, a2_lo, a2_hi, b0, b1, c1 );
                 m0 = __funnelshift_l( __float_as_uint( c[0] ), m0, 1 );
                 m1 = __funnelshift_l( __float_as_uint( c[1] ), m1, 1 );
                 m2 = __funnelshift_l( __float_as_uint( c[2] ), m2, 1 );
@@ -510,8 +592,8 @@ __global__ void __launch_bounds__( kBlockT, 2 )
                     const float b0 = f0w[32 * j + (int)lane];
                     const float b1 = f1w[32 * j + (int)lane];
                     float c1[4], c[4];
-                    mma_tf32( c1, a1_lo, a1_hi, a1_lo, a1_hi, b0, b1, zero4 );
-                    mma_tf32( c, a2_lo, a2_hi, a2p_lo, a2p_hi, b0, 1.0f, c1 );
+                    mma_tf32( c1, a1_lo, a1_hi, a1_lo, a1_hi, b0, b1, cinit );
+                    mma_tf32( c, a2_lo, a2_hi, a2_lo, a2_hi, b0, b1, c1 );
                     const unsigned bit = 1u << ( nt_p - 1 - j );
 #pragma unroll
                     for ( int k = 0; k < 4; ++k )
@@ -520,7 +602,7 @@ __global__ void __launch_bounds__( kBlockT, 2 )
                         const int hp = k < 2 ? pid_g : pid_g8;
                         if ( DIAG )
                         {
-                            const int cp = __float_as_int( S.raw[buf][e].w );
+                            const int cp = S.cand_pid( buf, e );
                             if ( hp >= 0 && cp >= 0 )
                             {
                                 const float err =
@@ -530,8 +612,7 @@ __global__ void __launch_bounds__( kBlockT, 2 )
                         }
                         if ( fabsf( c[k] ) <= a.tau )
                         {
-                            const bool hit = exact_decide<HALF>(
-                                a, hp, __float_as_int( S.raw[buf][e].w ) );
+                            const bool hit = exact_decide<HALF>( a, hp, S.cand_pid( buf, e ) );
                             unsigned& m = k == 0 ? m0 : ( k == 1 ? m1 : ( k == 2 ? m2 : m3 ) );
                             m = hit ? ( m | bit ) : ( m & ~bit );
                         }
@@ -565,8 +646,7 @@ __global__ void __launch_bounds__( kBlockT, 2 )
                         else if ( cx < hx )
                             keep = false;
                         else
-                            keep = exact_decide<HALF>( a, hp,
-                                                       __float_as_int( S.raw[buf][e].w ) );
+                            keep = exact_decide<HALF>( a, hp, S.cand_pid( buf, e ) );
                         if ( !keep )
                             m &= ~( 1u << b );
                     }
@@ -584,30 +664,32 @@ __global__ void __launch_bounds__( kBlockT, 2 )
                     m2 <<= sh;
                     m3 <<= sh;
                 }
-                // j != i
-#pragma unroll
-                for ( int hh = 0; hh < 2; ++hh )
+                // j != i: the home particles sit at list entries selfbase .. selfbase + 15
+                if ( (int)( selfbase / kChunkEntries ) <= chunk_i &&
+                     (int)( ( selfbase + 15u ) / kChunkEntries ) >= chunk_i )
                 {
-                    const unsigned p = selfbase + (unsigned)( g + 8 * hh );
-                    if ( (int)( p / kChunkEntries ) == chunk_i )
+#pragma unroll
+                    for ( int hh = 0; hh < 2; ++hh )
                     {
+                        const unsigned p = selfbase + (unsigned)( g + 8 * hh );
                         const unsigned e = p % kChunkEntries;
-                        if ( (int)( ( e & 7u ) >> 1 ) == t )
+                        if ( (int)( p / kChunkEntries ) == chunk_i &&
+                             (int)( ( e & 7u ) >> 1 ) == t )
                         {
-                            const unsigned bit = 0x80000000u >> ( e >> 3 );
+                            const unsigned keep = ~( 0x80000000u >> ( e >> 3 ) );
                             if ( hh == 0 )
                             {
                                 if ( e & 1u )
-                                    m1 &= ~bit;
+                                    m1 &= keep;
                                 else
-                                    m0 &= ~bit;
+                                    m0 &= keep;
                             }
                             else
                             {
                                 if ( e & 1u )
-                                    m3 &= ~bit;
+                                    m3 &= keep;
                                 else
-                                    m2 &= ~bit;
+                                    m2 &= keep;
                             }
                         }
                     }
@@ -650,12 +732,34 @@ __global__ void __launch_bounds__( kBlockT, 2 )
 struct __align__( 16 ) FillSmem
 {
     int rows[kRowCap];
-    unsigned ids[kChunkEntries];
-    unsigned sp_start[16], sp_len[16], sp_pos[16];
+    unsigned ids[kChunkEntries]; // ids of the chunk's candidates, tiles in REVERSE order
+    unsigned tsrc[kTableTiles];
+    unsigned char tval[kTableTiles];
 };
 
-template <bool HALF, bool CSR>
-__global__ void __launch_bounds__( kBlockT, 2 )
+// Expand one mask word: tile i of the chunk is bit 31 - i, and its ids sit at
+// ids2[8 * (31 - i)], so the bit position indexes the table directly.
+CB_D void expand_word( unsigned mm, const unsigned* ids2, int* rows, int& w )
+{
+    while ( mm )
+    {
+        const int p = 31 - __clz( mm );
+        mm ^= 1u << p;
+        rows[w++] = (int)ids2[kTileCands * p];
+    }
+}
+CB_D void expand_word_global( unsigned mm, const unsigned* ids2, int*& out )
+{
+    while ( mm )
+    {
+        const int p = 31 - __clz( mm );
+        mm ^= 1u << p;
+        *out++ = (int)ids2[kTileCands * p];
+    }
+}
+
+template <bool CSR>
+__global__ void __launch_bounds__( kBlockT, 3 )
     k_tile_fill( const __grid_constant__ TileArgs a )
 {
     extern __shared__ __align__( 16 ) unsigned char s_dyn[];
@@ -664,7 +768,6 @@ __global__ void __launch_bounds__( kBlockT, 2 )
     FillSmem& S = reinterpret_cast<FillSmem*>( s_dyn )[wib];
     const int g = (int)( lane >> 2 ), t = (int)( lane & 3u );
     const int ntiles = *a.ntiles_dev;
-    const GridInts gi = { a.ncx, a.ncy, a.nz, a.kz };
 
     for ( ;; )
     {
@@ -676,9 +779,6 @@ __global__ void __launch_bounds__( kBlockT, 2 )
             break;
         const TileRec rc = unpack_rec( a.recs[tile] );
         const int chunk0 = a.chunk_off[tile];
-        const int col = rc.block / a.nzb;
-        const int ca = col / a.ncy;
-        const int cb_ = col - ca * a.ncy;
 
         int pid = -1, cnt = 0;
         long long dst = 0;
@@ -691,40 +791,32 @@ __global__ void __launch_bounds__( kBlockT, 2 )
                 dst = CSR ? (long long)a.offsets[pid] : (long long)pid * a.width;
             }
         }
-        // inclusive scan of the 16 row sizes
-        int inc = cnt;
-#pragma unroll
-        for ( int o = 1; o < 16; o <<= 1 )
-        {
-            const int y = __shfl_up_sync( kFullMask, inc, o );
-            if ( (int)lane >= o )
-                inc += y;
-        }
-        const int total = __shfl_sync( kFullMask, inc, 15 );
-        if ( total == 0 )
-            continue;
-
-        unsigned sp_start = 0u, sp_len = 0u;
+        uint2 sp = make_uint2( 0u, 0u );
         if ( lane < 9u )
-            span_of( gi, a.cell_off, ca, cb_, rc.zlo, rc.zhi, HALF, (int)lane, sp_start,
-                     sp_len );
-        const int my_nt = (int)( ( sp_len + kTileCands - 1 ) / kTileCands );
+            sp = a.spans[(size_t)tile * 9u + lane];
+        // inclusive scans: the 16 row sizes; the mma tiles of the 9 spans
+        int inc = cnt;
+        const int my_nt = (int)( ( sp.y + kTileCands - 1 ) / kTileCands );
         int incl = my_nt;
 #pragma unroll
         for ( int o = 1; o < 16; o <<= 1 )
         {
-            const int y = __shfl_up_sync( kFullMask, incl, o );
+            const int y = __shfl_up_sync( kFullMask, inc, o );
+            const int y2 = __shfl_up_sync( kFullMask, incl, o );
             if ( (int)lane >= o )
-                incl += y;
+            {
+                inc += y;
+                incl += y2;
+            }
         }
+        const int total = __shfl_sync( kFullMask, inc, 15 );
+        if ( total == 0 )
+            continue;
         const int T = __shfl_sync( kFullMask, incl, 15 );
+        const int tiles_before = incl - my_nt;
         __syncwarp();
-        if ( lane < 16u )
-        {
-            S.sp_start[lane] = sp_start;
-            S.sp_len[lane] = sp_len;
-            S.sp_pos[lane] = (unsigned)( incl - my_nt ) * kTileCands;
-        }
+        build_tile_table( S, 0, tiles_before, my_nt, sp.x, sp.y );
+        int table_seg = 0;
         __syncwarp();
         const int nchunks = ( T + kChunkTiles - 1 ) / kChunkTiles;
 
@@ -747,17 +839,13 @@ __global__ void __launch_bounds__( kBlockT, 2 )
             const int rowstart = inc - cnt - base; // valid for lanes in [ha, hb)
             const bool in_g = g >= ha && g < hb;
             const bool in_g8 = g + 8 >= ha && g + 8 < hb;
-            const int rs_g = __shfl_sync( kFullMask, rowstart, g );
-            const int rs_g8 = __shfl_sync( kFullMask, rowstart, g + 8 );
-            const long long dst_g = __shfl_sync( kFullMask, dst, g );
-            const long long dst_g8 = __shfl_sync( kFullMask, dst, g + 8 );
-            int* out_g = direct ? a.neighbors + dst_g : S.rows + rs_g;
-            int* out_g8 = direct ? a.neighbors + dst_g8 : S.rows + rs_g8;
-            int cur_g = 0, cur_g8 = 0;
             const int wtotal = __shfl_sync( kFullMask, inc, hb - 1 ) - base;
-
             if ( wtotal > 0 )
             {
+                int cur_g = __shfl_sync( kFullMask, rowstart, g );
+                int cur_g8 = __shfl_sync( kFullMask, rowstart, g + 8 );
+                int* gout_g = a.neighbors + __shfl_sync( kFullMask, dst, g );
+                int* gout_g8 = a.neighbors + __shfl_sync( kFullMask, dst, g + 8 );
                 for ( int ci = 0; ci < nchunks; ++ci )
                 {
                     uint4 m = a.masks[( (size_t)chunk0 + ci ) * 32u + lane];
@@ -768,16 +856,24 @@ __global__ void __launch_bounds__( kBlockT, 2 )
                     if ( !__any_sync( kFullMask, ( m.x | m.y | m.z | m.w ) != 0u ) )
                         continue;
                     __syncwarp();
-                    // ids of the chunk's candidates
-                    for ( int s = 0; s < 9; ++s )
+                    const int seg = ( ci * kChunkTiles ) / kTableTiles;
+                    if ( seg != table_seg )
                     {
-                        const unsigned p = S.sp_pos[s];
-                        const unsigned lo = max( p, (unsigned)( ci * kChunkEntries ) );
-                        const unsigned hi =
-                            min( p + S.sp_len[s], (unsigned)( ( ci + 1 ) * kChunkEntries ) );
-                        const unsigned src = S.sp_start[s] - p;
-                        for ( unsigned e = lo + lane; e < hi; e += 32u )
-                            S.ids[e - (unsigned)( ci * kChunkEntries )] = a.permute[src + e];
+                        build_tile_table( S, seg * kTableTiles, tiles_before, my_nt, sp.x, sp.y );
+                        table_seg = seg;
+                        __syncwarp();
+                    }
+                    // ids of the chunk's candidates.  Entries behind a span's end inside its
+                    // last tile read whatever follows in `permute` (padded by 8): their
+                    // mask bits are zero, the values are never used.
+#pragma unroll
+                    for ( int k = 0; k < kChunkEntries / 32; ++k )
+                    {
+                        const int e = (int)lane + 32 * k;
+                        const int tl = ci * kChunkTiles + ( e >> 3 );
+                        if ( tl < T )
+                            S.ids[( 31 - ( e >> 3 ) ) * kTileCands + ( e & 7 )] =
+                                a.permute[S.tsrc[tl & ( kTableTiles - 1 )] + (unsigned)( e & 7 )];
                     }
                     __syncwarp();
                     // where this thread's hits go: exclusive prefix over the quad
@@ -791,51 +887,44 @@ __global__ void __launch_bounds__( kBlockT, 2 )
                     if ( t >= 2 )
                         pk += y;
                     const int qt = __shfl_sync( kFullMask, pk, 3, 4 );
-                    int w_g = cur_g + ( pk & 0xffff ) - pg;
-                    int w_g8 = cur_g8 + ( pk >> 16 ) - pg8;
-                    cur_g += qt & 0xffff;
-                    cur_g8 += qt >> 16;
-                    // tile i of the chunk is bit 31 - i; candidate 2t (+1) of that tile
-                    unsigned mm = m.x;
-                    while ( mm )
+                    const unsigned* ids2 = S.ids + 2 * t;
+                    if ( !direct )
                     {
-                        const int i = __clz( mm );
-                        mm &= ~( 0x80000000u >> i );
-                        out_g[w_g++] = (int)S.ids[kTileCands * i + 2 * t];
+                        int w_g = cur_g + ( pk & 0xffff ) - pg;
+                        int w_g8 = cur_g8 + ( pk >> 16 ) - pg8;
+                        expand_word( m.x, ids2, S.rows, w_g );
+                        expand_word( m.y, ids2 + 1, S.rows, w_g );
+                        expand_word( m.z, ids2, S.rows, w_g8 );
+                        expand_word( m.w, ids2 + 1, S.rows, w_g8 );
+                        cur_g += qt & 0xffff;
+                        cur_g8 += qt >> 16;
                     }
-                    mm = m.y;
-                    while ( mm )
+                    else
                     {
-                        const int i = __clz( mm );
-                        mm &= ~( 0x80000000u >> i );
-                        out_g[w_g++] = (int)S.ids[kTileCands * i + 2 * t + 1];
-                    }
-                    mm = m.z;
-                    while ( mm )
-                    {
-                        const int i = __clz( mm );
-                        mm &= ~( 0x80000000u >> i );
-                        out_g8[w_g8++] = (int)S.ids[kTileCands * i + 2 * t];
-                    }
-                    mm = m.w;
-                    while ( mm )
-                    {
-                        const int i = __clz( mm );
-                        mm &= ~( 0x80000000u >> i );
-                        out_g8[w_g8++] = (int)S.ids[kTileCands * i + 2 * t + 1];
+                        int* w_g = gout_g + ( ( pk & 0xffff ) - pg );
+                        int* w_g8 = gout_g8 + ( ( pk >> 16 ) - pg8 );
+                        expand_word_global( m.x, ids2, w_g );
+                        expand_word_global( m.y, ids2 + 1, w_g );
+                        expand_word_global( m.z, ids2, w_g8 );
+                        expand_word_global( m.w, ids2 + 1, w_g8 );
+                        gout_g += qt & 0xffff;
+                        gout_g8 += qt >> 16;
                     }
                 }
                 __syncwarp();
                 if ( !direct )
                 {
                     // rows leave shared memory coalesced, each to its final place
+#pragma unroll 1
                     for ( int h = ha; h < hb; ++h )
                     {
                         const int c = __shfl_sync( kFullMask, cnt, h );
                         const int rs = __shfl_sync( kFullMask, rowstart, h );
-                        const long long d = __shfl_sync( kFullMask, dst, h );
-                        for ( int i = (int)lane; i < c; i += 32 )
-                            __stcs( a.neighbors + d + i, S.rows[rs + i] );
+                        int* d = a.neighbors + ( __shfl_sync( kFullMask, dst, h ) - rs );
+                        const int end = rs + c;
+#pragma unroll 1
+                        for ( int i = rs + (int)lane; i < end; i += 32 )
+                            __stcs( d + i, S.rows[i] );
                     }
                 }
                 __syncwarp();
@@ -940,8 +1029,7 @@ void make_tile_grid( TileGrid& tg, const double* grid_min, const double* grid_ma
         tg.zb = 16;
     tg.nzb = ( tg.nz + tg.zb - 1 ) / tg.zb;
     tg.ncols = (long long)tg.ncx * tg.ncy;
-    // block ids share a word with the tile's particle count (26 bits)
-    while ( tg.ncols * tg.nzb >= ( 1ll << 26 ) )
+    while ( tg.ncols * tg.nzb >= ( 1ll << 30 ) )
     {
         tg.zb *= 2;
         tg.nzb = ( tg.nz + tg.zb - 1 ) / tg.zb;
@@ -974,6 +1062,7 @@ double tile_filter_bound( const TileGrid& tg, double radius )
                12.0 * u * u * ( M * M + Dmax * Dmax );
     // (3) norms in fp32, hi/lo splits, dropped lo*lo, cutoff split, accumulation
     E += 3.0 * u * ( S + Sh ) + v * ( S + Sh ) + 6.0 * v * HD + v * rsqr;
+    E += 2.0 * u * ( Sh + rsqr ); // accumulator init fl(fl(N - r2hi) - r2lo)
     E += 2.0 * gam * ( 2.0 * HD * ( 1.0 + 1.0e-3 ) + S + Sh + rsqr );
     return E;
 }
@@ -988,7 +1077,7 @@ int tile_gather_q( const cb_positions& x, long long n, const unsigned* permute, 
 }
 
 int tile_plan( const TileGrid& tg, const unsigned* cell_off, bool half, int* block_tiles,
-               int* tile_base, uint4* recs, int* tile_chunks, int* chunk_off,
+               int* tile_base, uint4* recs, uint2* spans, int* tile_chunks, int* chunk_off,
                long long rec_capacity, DeviceBuffer& scan_scratch, cudaStream_t stream )
 {
     const GridInts gi = { tg.ncx, tg.ncy, tg.nz, tg.kz };
@@ -1000,35 +1089,50 @@ int tile_plan( const TileGrid& tg, const unsigned* cell_off, bool half, int* blo
     CB_CUDA( cudaMemsetAsync( tile_chunks, 0, sizeof( int ) * (size_t)rec_capacity, stream ) );
     k_plan_tiles<<<launch_grid_for( tg.nblocks, 128 ), 128, 0, stream>>>(
         cell_off, gi, tg.zb, tg.nzb, tg.nblocks, half ? 1 : 0, block_tiles, tile_base, recs,
-        tile_chunks, rec_capacity );
+        spans, tile_chunks, rec_capacity );
     CB_CHECK_LAUNCH();
     CB_TRY( exclusive_scan_i32( tile_chunks, chunk_off, rec_capacity, true, nullptr,
                                 scan_scratch, stream ) );
     return CB_OK;
 }
 
+static bool use_tma_staging()
+{
+    const char* e = getenv( "CB_TILE_STAGING" );
+    return e && strcmp( e, "tma" ) == 0;
+}
+
 int tile_count_pass( const TileArgs& a, bool half, cudaStream_t stream )
 {
-    const int smem = (int)sizeof( CountSmem ) * kWarpsT;
-    return half ? launch_persistent( k_tile_count<true, false>, smem, a, stream )
-                : launch_persistent( k_tile_count<false, false>, smem, a, stream );
+    if ( use_tma_staging() )
+    {
+        const int smem = (int)sizeof( CountSmemTma ) * kWarpsT;
+        return half ? launch_persistent( k_tile_count<true, false, true>, smem, a, stream )
+                    : launch_persistent( k_tile_count<false, false, true>, smem, a, stream );
+    }
+    const int smem = (int)sizeof( CountSmemLdg ) * kWarpsT;
+    return half ? launch_persistent( k_tile_count<true, false, false>, smem, a, stream )
+                : launch_persistent( k_tile_count<false, false, false>, smem, a, stream );
 }
 
 int tile_diag_pass( const TileArgs& a, bool half, cudaStream_t stream )
 {
-    const int smem = (int)sizeof( CountSmem ) * kWarpsT;
-    return half ? launch_persistent( k_tile_count<true, true>, smem, a, stream )
-                : launch_persistent( k_tile_count<false, true>, smem, a, stream );
+    if ( use_tma_staging() )
+    {
+        const int smem = (int)sizeof( CountSmemTma ) * kWarpsT;
+        return half ? launch_persistent( k_tile_count<true, true, true>, smem, a, stream )
+                    : launch_persistent( k_tile_count<false, true, true>, smem, a, stream );
+    }
+    const int smem = (int)sizeof( CountSmemLdg ) * kWarpsT;
+    return half ? launch_persistent( k_tile_count<true, true, false>, smem, a, stream )
+                : launch_persistent( k_tile_count<false, true, false>, smem, a, stream );
 }
 
-int tile_fill_pass( const TileArgs& a, bool half, bool csr, cudaStream_t stream )
+int tile_fill_pass( const TileArgs& a, bool csr, cudaStream_t stream )
 {
     const int smem = (int)sizeof( FillSmem ) * kWarpsT;
-    if ( half )
-        return csr ? launch_persistent( k_tile_fill<true, true>, smem, a, stream )
-                   : launch_persistent( k_tile_fill<true, false>, smem, a, stream );
-    return csr ? launch_persistent( k_tile_fill<false, true>, smem, a, stream )
-               : launch_persistent( k_tile_fill<false, false>, smem, a, stream );
+    return csr ? launch_persistent( k_tile_fill<true>, smem, a, stream )
+               : launch_persistent( k_tile_fill<false>, smem, a, stream );
 }
 
 } // namespace cb

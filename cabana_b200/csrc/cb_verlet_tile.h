@@ -39,7 +39,8 @@ struct TileArgs
     int ncx, ncy, nz, zb, nzb, kz;
     float wx, wy, hz;         // cell sizes (tile origins only; any float works)
     // tiles
-    const uint4* recs;         // {first slot, block | np << 26, zlo | zhi << 16, #mma tiles}
+    const uint4* recs;         // {first slot, col a | b << 16, zlo | zhi << 16, np | #mma tiles << 8}
+    const uint2* spans;        // [ntiles][9] candidate spans (start slot, length)
     const int* chunk_off;      // [ntiles+1] first mask chunk of every tile
     const int* ntiles_dev;     // tile_base[nblocks] (device)
     long long mask_capacity;   // chunks the mask buffer holds
@@ -76,11 +77,11 @@ int tile_gather_q( const cb_positions& x, long long n, const unsigned* permute, 
 // Tile records + mask chunk offsets.  block_tiles/tile_base: [nblocks+1] ints;
 // recs: capacity n/16 + nblocks + 1; chunk_off: same + 1.
 int tile_plan( const TileGrid& tg, const unsigned* cell_off, bool half, int* block_tiles,
-               int* tile_base, uint4* recs, int* tile_chunks, int* chunk_off,
+               int* tile_base, uint4* recs, uint2* spans, int* tile_chunks, int* chunk_off,
                long long rec_capacity, DeviceBuffer& scan_scratch, cudaStream_t stream );
 
 int tile_count_pass( const TileArgs& a, bool half, cudaStream_t stream );
-int tile_fill_pass( const TileArgs& a, bool half, bool csr, cudaStream_t stream );
+int tile_fill_pass( const TileArgs& a, bool csr, cudaStream_t stream );
 // Count pass with every filter value checked against the exact arithmetic (tests only).
 int tile_diag_pass( const TileArgs& a, bool half, cudaStream_t stream );
 
