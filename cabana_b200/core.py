@@ -325,11 +325,11 @@ class VerletList:
         """cb_verlet_filter_selftest: (largest |tensor-core filter - exact FP64| seen over every
         tested pair, the bound the build's decisions assume)."""
         d = x.positions_desc()
-        out = (C.c_double * 2)()
+        out = (C.c_double * 3)()
         capi.check(capi.lib().cb_verlet_filter_selftest(
             self._h, C.byref(d), C.c_double(neighborhood_radius), capi.d3(grid_min), capi.d3(grid_max),
             C.c_int(self.algorithm), out, _stream()))
-        return float(out[0]), float(out[1])
+        return float(out[0]), float(out[1]), int(out[2])
 
     def copy_to_host(self, counts_h: torch.Tensor, offsets_h: torch.Tensor | None, neighbors_h: torch.Tensor):
         capi.check(capi.lib().cb_verlet_copy_to_host(

@@ -19,6 +19,7 @@
 // reference's, so every in/out decision matches bit for bit by construction.
 #include <new>
 #include <utility>
+#include <vector>
 
 #include <math.h>
 #include <stdlib.h>
@@ -265,7 +266,8 @@ struct cb_verlet
     DeviceBuffer cell_counts, cell_off, permute, cell_of, rank, scan, xs, ys, zs, q, stats;
     DeviceBuffer worklist, tmp, tmp_off, ctrl;
     // v2 (tile) workspace
-    DeviceBuffer block_tiles, tile_base, recs, spans, tile_chunks, chunk_off, masks;
+    DeviceBuffer block_tiles, tile_base, recs, spans, tile_chunks, chunk_off, masks, cellslot,
+        pads, tau_tab, cnt_sorted, dst_sorted;
     DeviceBuffer host_stage; // device copy of host positions (build_host)
     PinnedScalars pinned;
     // optional phase timing
@@ -328,7 +330,8 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
 
     TileGrid tg;
     make_tile_grid( tg, grid_min, grid_max, radius, n );
-    const long long rec_capacity = n / kTileHomes + tg.nblocks + 2;
+    const long long ns_cap = sorted_capacity( tg, n ); // sorted slots incl. column pads
+    const long long rec_capacity = ns_cap / kTileHomes + tg.nblocks + 2;
 
     CB_TRY( v->pinned.ensure() );
     CB_TRY( v->stats.ensure( 4 * sizeof( long long ) ) );
@@ -338,9 +341,13 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
         CB_TRY( v->offsets.ensure( sizeof( int ) * ( na + 1 ), 1.1 ) );
     CB_TRY( v->cell_counts.ensure( sizeof( int ) * (size_t)tg.ncells ) );
     CB_TRY( v->cell_off.ensure( sizeof( unsigned ) * (size_t)( tg.ncells + 1 ) ) );
-    CB_TRY( v->permute.ensure( sizeof( unsigned ) * ( na + 8 ), 1.1 ) );
-    CB_TRY( v->cell_of.ensure( sizeof( int ) * na, 1.1 ) );
-    CB_TRY( v->q.ensure( sizeof( float4 ) * ( na + 8 ), 1.1 ) );
+    CB_TRY( v->permute.ensure( sizeof( unsigned ) * (size_t)( ns_cap + 8 ), 1.1 ) );
+    CB_TRY( v->q.ensure( sizeof( float4 ) * (size_t)( ns_cap + 8 ), 1.1 ) );
+    CB_TRY( v->cellslot.ensure( sizeof( uint2 ) * na, 1.1 ) );
+    CB_TRY( v->cnt_sorted.ensure( sizeof( int ) * (size_t)( ns_cap + 8 ), 1.1 ) );
+    if ( csr )
+        CB_TRY( v->dst_sorted.ensure( sizeof( int ) * (size_t)( ns_cap + 8 ), 1.1 ) );
+    CB_TRY( v->pads.ensure( (size_t)tg.ncols + 16 ) );
     CB_TRY( v->block_tiles.ensure( sizeof( int ) * (size_t)( tg.nblocks + 1 ) ) );
     CB_TRY( v->tile_base.ensure( sizeof( int ) * (size_t)( tg.nblocks + 1 ) ) );
     CB_TRY( v->recs.ensure( sizeof( uint4 ) * (size_t)rec_capacity, 1.1 ) );
@@ -354,12 +361,10 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
     CB_CUDA( cudaMemsetAsync( v->counts.ptr, 0, sizeof( int ) * na, stream ) ); // :215-216
 
     // LCL over ALL particles, not just [begin,end) (:229-235), on the internal grid
-    CB_TRY( bin_particles( tg.g, *x, 0, n, v->cell_counts.as<int>(),
-                           v->cell_off.as<unsigned>(), v->permute.as<unsigned>(),
-                           v->cell_of.as<int>(), v->rank, v->scan, stream, 1 ) );
+    CB_TRY( tile_bin( tg, *x, v->cell_counts.as<int>(), v->cell_off.as<unsigned>(),
+                      v->cellslot.as<uint2>(), v->pads.as<unsigned char>(), v->q.as<float4>(),
+                      v->permute.as<unsigned>(), v->scan, stream ) );
     v->mark( 1, stream );
-    CB_TRY( tile_gather_q( *x, n, v->permute.as<unsigned>(), v->q.as<float4>(), tg.g.min,
-                           stream ) );
     CB_TRY( tile_plan( tg, v->cell_off.as<unsigned>(), half, v->block_tiles.as<int>(),
                        v->tile_base.as<int>(), v->recs.as<uint4>(), v->spans.as<uint2>(),
                        v->tile_chunks.as<int>(), v->chunk_off.as<int>(), rec_capacity,
@@ -414,15 +419,28 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
         memcpy( &lo, &hb, 4 );
         a.r2hi = hi;
         a.r2lo = lo;
-        const double bound = tile_filter_bound( tg, radius );
-        a.tau = nextafterf( (float)( 2.0 * bound ), INFINITY );
+        // tau = twice the proven bound; one entry per number of z cells one origin serves
+        // (a tile: <= zb cells; the CTA kernel stages up to 8 tiles under one origin)
+        const int ntab = 8 * tg.zb + 2;
+        std::vector<float> tab( (size_t)ntab );
+        for ( int k = 0; k < ntab; ++k )
+            tab[(size_t)k] =
+                nextafterf( (float)( 2.0 * tile_filter_bound( tg, radius, k ) ), INFINITY );
+        CB_TRY( v->tau_tab.ensure( sizeof( float ) * (size_t)ntab ) );
+        CB_CUDA( cudaMemcpyAsync( v->tau_tab.ptr, tab.data(), sizeof( float ) * (size_t)ntab,
+                                  cudaMemcpyHostToDevice, stream ) );
+        CB_CUDA( cudaStreamSynchronize( stream ) ); // `tab` is a stack object
+        a.tau_tab = v->tau_tab.as<float>();
+        a.tau_tab_n = ntab;
+        a.tau = tab[(size_t)tg.zb];
         if ( diag )
-            diag[1] = bound;
+            diag[1] = tile_filter_bound( tg, radius, tg.zb );
     }
     a.n = n;
     a.begin = begin;
     a.end = end;
     a.counts = v->counts.as<int>();
+    a.cnt_sorted = v->cnt_sorted.as<int>();
 
     long long* stats_dev = v->stats.as<long long>();
     long long* stats_h = v->pinned.ptr;
@@ -436,8 +454,11 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
         CB_CUDA( cudaMemcpyAsync( stats_h, v->ctrl.ptr, 32, cudaMemcpyDeviceToHost, stream ) );
         CB_CUDA( cudaStreamSynchronize( stream ) );
         float e;
+        unsigned misses;
         memcpy( &e, reinterpret_cast<char*>( stats_h ) + 16, 4 );
+        memcpy( &misses, reinterpret_cast<char*>( stats_h ) + 20, 4 );
         diag[0] = (double)e;
+        diag[2] = (double)misses; // values whose error exceeded the bound of their staging
         return CB_OK;
     }
 
@@ -450,13 +471,21 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
         a.masks = v->masks.as<uint4>();
         a.mask_capacity = (long long)( v->masks.capacity / ( kChunkWords * 4 ) );
         CB_CUDA( cudaMemsetAsync( v->ctrl.ptr, 0, 64, stream ) );
+        CB_CUDA( cudaMemsetAsync( v->cnt_sorted.ptr, 0, sizeof( int ) * (size_t)( ns_cap + 8 ),
+                                  stream ) );
         if ( n > 0 )
             CB_TRY( tile_count_pass( a, half, stream ) );
         v->mark( 3, stream );
         CB_TRY( max_and_sum_i32( v->counts.as<int>(), n, stats_dev, stream ) );
         if ( csr )
+        {
             CB_TRY( exclusive_scan_i32( v->counts.as<int>(), v->offsets.as<int>(), n, false,
                                         nullptr, v->scan, stream ) );
+            a.offsets = v->offsets.as<int>();
+            if ( n > 0 )
+                CB_TRY( tile_sorted_dst( a, tg.ncells, ns_cap, v->dst_sorted.as<int>(), stream ) );
+            a.dst_sorted = v->dst_sorted.as<int>();
+        }
         CB_CUDA( cudaMemcpyAsync( stats_h, stats_dev, 2 * sizeof( long long ),
                                   cudaMemcpyDeviceToHost, stream ) );
         CB_CUDA( cudaMemcpyAsync( stats_h + 2, v->ctrl.ptr, 2 * sizeof( long long ),

@@ -41,7 +41,7 @@ constexpr int kWarpsT = 8;
 constexpr int kBlockT = kWarpsT * 32;
 constexpr int kPieceEntries = kPieceTiles * kTileCands; // 128 candidates
 constexpr int kChunkEntries = kChunkTiles * kTileCands; // 256 candidates
-constexpr int kRowCap = 1536;                           // ids staged per tile in the fill pass
+constexpr int kRowCap = 1280;                           // ids staged per tile in the fill pass
 
 // ---------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + bulk copy (TMA engine) + tf32 mma
@@ -82,6 +82,14 @@ CB_D void bulk_g2s( void* dst, const void* src, unsigned bytes, unsigned long lo
         "l"( src ), "r"( bytes ), "r"( smem_u32( b ) )
         : "memory" );
 }
+// Ampere-style per-lane asynchronous copy (LDGSTS): 16 bytes global -> shared, L1-cached.
+CB_D void cp_async16( void* dst, const void* src )
+{
+    asm volatile( "cp.async.ca.shared.global [%0], [%1], 16;" ::"r"( smem_u32( dst ) ), "l"( src )
+                  : "memory" );
+}
+CB_D void cp_async_commit() { asm volatile( "cp.async.commit_group;" ::: "memory" ); }
+CB_D void cp_async_wait_all() { asm volatile( "cp.async.wait_group 0;" ::: "memory" ); }
 CB_D void fence_proxy_async()
 {
     asm volatile( "fence.proxy.async.shared::cta;" ::: "memory" );
@@ -155,8 +163,10 @@ CB_D void span_of( const GridInts& gi, const unsigned* __restrict__ cell_off, in
     const int z0 = max( zlo - gi.kz, 0 );
     const int z1 = min( zhi + gi.kz, gi.nz - 1 );
     const long long c0 = ( (long long)aa * gi.ncy + bb ) * gi.nz;
-    start = cell_off[c0 + z0];
-    len = cell_off[c0 + z1 + 1] - start;
+    // the window is widened to multiples of 8 slots: what it gains are particles of cells
+    // the cutoff cannot reach, or the column's sentinel pad -- never a neighbour
+    start = cell_off[c0 + z0] & ~7u;
+    len = ( ( cell_off[c0 + z1 + 1] + 7u ) & ~7u ) - start;
 }
 
 // The reference's cell-level prune for the pair (p, n), evaluated exactly on the USER grid
@@ -211,27 +221,118 @@ __device__ __noinline__ double exact_c( const TileArgs& a, int pi, int pj )
 }
 
 // ---------------------------------------------------------------------------------------
-// gather: the FP32 origin-relative copy of the positions in cell-sorted order
+// binning on the internal grid (LinkedCellList::build semantics, Cabana_LinkedCellList.hpp
+// :651-739, fused for this consumer): positions are read from the user's slice TWICE in
+// coalesced order -- (1) locate + warp-aggregated atomic that both histograms and claims the
+// slot, (2) after the scan, scatter the FP32 origin-relative record straight to its sorted
+// slot -- instead of histogram, permute fill and a random gather.
+// Every column is padded with sentinel slots to a multiple of 8 plus 8, so 8-aligned windows
+// of the sorted array never leave their column.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__( 256 )
-    k_gather_q( PosAccess x, long long n, const unsigned* __restrict__ permute,
-                float4* __restrict__ q, double ox, double oy, double oz )
+    k_tbin_count( PosAccess x, Grid g, long long n, int* __restrict__ counts,
+                  uint2* __restrict__ cellslot )
 {
-    for ( long long s = (long long)blockIdx.x * 256 + threadIdx.x; s < n + 8;
-          s += (long long)gridDim.x * 256 )
+    const unsigned lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    for ( long long p0 = (long long)blockIdx.x * 256; p0 < n; p0 += (long long)gridDim.x * 256 )
     {
-        if ( s >= n )
+        const long long p = p0 + threadIdx.x;
+        const bool valid = p < n;
+        int c = -1 - (int)lane; // unique dummy key for idle lanes
+        if ( valid )
         {
-            q[s] = make_float4( 1.0e18f, 1.0e18f, 1.0e18f, __int_as_float( -1 ) );
-            continue;
+            const long long off = x.offset( p );
+            int ci = locate_1d( g, 0, x.base[off] );
+            int cj = locate_1d( g, 1, x.base[off + x.comp_stride] );
+            int ck = locate_1d( g, 2, x.base[off + 2 * x.comp_stride] );
+            // points outside [min,max] are undefined behaviour in the reference; clamp
+            ci = min( max( ci, 0 ), g.nx[0] - 1 );
+            cj = min( max( cj, 0 ), g.nx[1] - 1 );
+            ck = min( max( ck, 0 ), g.nx[2] - 1 );
+            c = cardinal_index( g, ci, cj, ck );
         }
-        const unsigned pid = permute[s];
-        const long long off = x.offset( (long long)pid );
+        const unsigned peers = __match_any_sync( kFullMask, c );
+        const int leader = __ffs( peers ) - 1;
+        int base = 0;
+        if ( valid && (int)lane == leader )
+            base = atomicAdd( &counts[c], __popc( peers ) );
+        base = __shfl_sync( peers, base, leader );
+        if ( valid )
+            cellslot[p] = make_uint2( (unsigned)c, (unsigned)( base + __popc( peers & lt ) ) );
+    }
+}
+
+// One warp per column: pad = slots added behind the column's last cell.
+__global__ void __launch_bounds__( 256 )
+    k_tbin_pad( int* __restrict__ counts, long long ncols, int nz,
+                unsigned char* __restrict__ pads )
+{
+    const unsigned lane = lane_id();
+    const long long warp = ( (long long)blockIdx.x * 256 + threadIdx.x ) >> 5;
+    const long long nwarps = ( (long long)gridDim.x * 256 ) >> 5;
+    for ( long long col = warp; col < ncols; col += nwarps )
+    {
+        int* cc = counts + col * nz;
+        int sum = 0;
+        for ( int k = (int)lane; k < nz; k += 32 )
+            sum += cc[k];
+        sum = warp_reduce_sum( sum );
+        if ( lane == 0 )
+        {
+            const int pad = ( ( 8 - ( sum & 7 ) ) & 7 ) + 8;
+            pads[col] = (unsigned char)pad;
+            cc[nz - 1] += pad;
+        }
+    }
+}
+
+__global__ void __launch_bounds__( 256 )
+    k_tbin_scatter( PosAccess x, long long n, const uint2* __restrict__ cellslot,
+                    const unsigned* __restrict__ cell_off, float4* __restrict__ q,
+                    unsigned* __restrict__ permute, double ox, double oy, double oz )
+{
+    for ( long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < n;
+          p += (long long)gridDim.x * 256 )
+    {
+        const long long off = x.offset( p );
         const double px = x.base[off];
         const double py = x.base[off + x.comp_stride];
         const double pz = x.base[off + 2 * x.comp_stride];
+        const uint2 cs = cellslot[p];
+        const unsigned s = cell_off[cs.x] + cs.y;
         q[s] = make_float4( __double2float_rn( px - ox ), __double2float_rn( py - oy ),
-                            __double2float_rn( pz - oz ), __int_as_float( (int)pid ) );
+                            __double2float_rn( pz - oz ), __int_as_float( (int)p ) );
+        permute[s] = (unsigned)p;
+    }
+}
+
+// Sentinels: the pad slots of every column and 8 slots behind the end of the array.
+__global__ void __launch_bounds__( 256 )
+    k_tbin_sentinels( const unsigned* __restrict__ cell_off, const unsigned char* __restrict__ pads,
+                      long long ncols, int nz, float4* __restrict__ q,
+                      unsigned* __restrict__ permute )
+{
+    const float4 sent = make_float4( 1.0e18f, 1.0e18f, 1.0e18f, __int_as_float( -1 ) );
+    for ( long long col = (long long)blockIdx.x * 256 + threadIdx.x; col <= ncols;
+          col += (long long)gridDim.x * 256 )
+    {
+        const unsigned end = cell_off[min( col + 1, ncols ) * nz];
+        const int pad = col < ncols ? (int)pads[col] : 0;
+        if ( col == ncols )
+        {
+            for ( int k = 0; k < 8; ++k )
+            {
+                q[end + k] = sent;
+                permute[end + k] = 0xffffffffu;
+            }
+            continue;
+        }
+        for ( int k = 1; k <= pad; ++k )
+        {
+            q[end - k] = sent;
+            permute[end - k] = 0xffffffffu;
+        }
     }
 }
 
@@ -315,58 +416,267 @@ __global__ void __launch_bounds__( 128 )
 // ---------------------------------------------------------------------------------------
 constexpr int kTableTiles = 256; // mma tiles whose source slot is tabulated at a time
 
+// Candidate features, as the B operand reads them: entry e, slot t -> (hi, lo) of
+// x, y, z (t = 0,1,2) and of |x|^2 (t = 3); thread (g,t) of tile j reads ONE 8-byte word
+// at feat[32 j + lane].
+CB_D void store_features( float2* feat, int e, float x, float y, float z )
+{
+    const float hx = trunc_tf32( x ), hy = trunc_tf32( y ), hz = trunc_tf32( z );
+    const float n = fmaf( z, z, fmaf( y, y, x * x ) );
+    const float nh = trunc_tf32( n );
+    float4* f = reinterpret_cast<float4*>( feat + 4 * e );
+    f[0] = make_float4( hx, x - hx, hy, y - hy );
+    f[1] = make_float4( hz, z - hz, nh, n - nh );
+}
+
+// Everything a warp keeps about its 16 home particles while it sweeps their candidates.
+struct HomeTile
+{
+    float a1[4], a2[4];               // A operands: (g,t) (g+8,t) (g,t+4) (g+8,t+4)
+    float cinit[4];                   // accumulator init: |x_i|^2 - r^2 of rows g, g+8
+    float hx_g, hx_g8;                // tile-local x of rows g, g+8 (half criterion)
+    int pid_g, pid_g8;
+    bool act_g, act_g8;
+    unsigned selfbase;                // list entry of home particle 0
+    unsigned m0, m1, m2, m3;          // hit bits of the current chunk
+    float ma;                         // min |c| since the last exact-tier check
+    int cnt_g, cnt_g8;
+};
+
+// Home operands from the tile-local coordinates of lanes 0..15 (scratch: 288 floats).
+//   A1 = [-2H, 1 | -2H, 1]   A2 = [-2L, 0 | -2L, 0]   C = |x_i|^2 - r^2
+CB_D void load_home_operands( HomeTile& H, float* scr, float xh, float yh, float zh, int pid,
+                              unsigned actmask, float r2hi, float r2lo, unsigned lane )
+{
+    const int g = (int)( lane >> 2 ), t = (int)( lane & 3u );
+    __syncwarp();
+    if ( lane < 16u )
+    {
+        const float Hx = trunc_tf32( xh ), Hy = trunc_tf32( yh ), Hz = trunc_tf32( zh );
+        const float N = fmaf( zh, zh, fmaf( yh, yh, xh * xh ) );
+        // (the two halves of A1 / A2 and the accumulator pairs hold equal values; they are
+        // kept in separate words so every operand register is loaded on its own instead of
+        // being re-copied inside the sweep loop)
+        float4* f = reinterpret_cast<float4*>( scr + 16 * lane );
+        f[0] = make_float4( -2.f * Hx, -2.f * Hy, -2.f * Hz, 1.f );
+        f[1] = f[0];
+        f[2] = make_float4( -2.f * ( xh - Hx ), -2.f * ( yh - Hy ), -2.f * ( zh - Hz ), 0.f );
+        f[3] = f[2];
+        // (N - r2hi) - r2lo: N and r2hi are close in magnitude, r2lo is the small part
+        scr[256 + 2 * lane] = scr[256 + 2 * lane + 1] = ( N - r2hi ) - r2lo;
+    }
+    __syncwarp();
+    H.a1[0] = scr[16 * g + t];
+    H.a1[1] = scr[16 * ( g + 8 ) + t];
+    H.a1[2] = scr[16 * g + 4 + t];
+    H.a1[3] = scr[16 * ( g + 8 ) + 4 + t];
+    H.a2[0] = scr[16 * g + 8 + t];
+    H.a2[1] = scr[16 * ( g + 8 ) + 8 + t];
+    H.a2[2] = scr[16 * g + 12 + t];
+    H.a2[3] = scr[16 * ( g + 8 ) + 12 + t];
+    H.cinit[0] = scr[256 + 2 * g];
+    H.cinit[1] = scr[256 + 2 * g + 1];
+    H.cinit[2] = scr[256 + 2 * ( g + 8 )];
+    H.cinit[3] = scr[256 + 2 * ( g + 8 ) + 1];
+    H.hx_g = __shfl_sync( kFullMask, xh, g );
+    H.hx_g8 = __shfl_sync( kFullMask, xh, g + 8 );
+    H.pid_g = __shfl_sync( kFullMask, pid, g );
+    H.pid_g8 = __shfl_sync( kFullMask, pid, g + 8 );
+    H.act_g = ( actmask >> g ) & 1u;
+    H.act_g8 = ( actmask >> ( g + 8 ) ) & 1u;
+    H.m0 = H.m1 = H.m2 = H.m3 = 0u;
+    H.ma = 3.0e38f;
+    H.cnt_g = H.cnt_g8 = 0;
+    __syncwarp();
+}
+
+// `seg` (<= 32) mma tiles whose features start at feat2 (tile j at feat2 + 32 j): the sign of
+// s - r^2 goes into the hit words (tile j ends up at bit seg-1-j), min |c| into H.ma; then
+// the exact tier for values inside the error band, and the x-major half criterion for the
+// first n_filter tiles (those of the home x column).  cpid: particle ids of the same entries.
+template <bool HALF, bool DIAG>
+CB_D void sweep_segment( const TileArgs& a, HomeTile& H, const float2* feat2, const int* cpid,
+                         int seg, int n_filter, float tau, unsigned lane )
+{
+    const int t = (int)( lane & 3u );
+    const float2* fp = feat2 + lane;
+#pragma unroll 4
+    for ( int j = 0; j < seg; ++j )
+    {
+        const float2 b = fp[32 * j];
+        float c1[4], c[4];
+        mma_tf32( c1, H.a1[0], H.a1[1], H.a1[2], H.a1[3], b.x, b.y, H.cinit );
+        mma_tf32( c, H.a2[0], H.a2[1], H.a2[2], H.a2[3], b.x, b.y, c1 );
+        H.m0 = __funnelshift_l( __float_as_uint( c[0] ), H.m0, 1 );
+        H.m1 = __funnelshift_l( __float_as_uint( c[1] ), H.m1, 1 );
+        H.m2 = __funnelshift_l( __float_as_uint( c[2] ), H.m2, 1 );
+        H.m3 = __funnelshift_l( __float_as_uint( c[3] ), H.m3, 1 );
+        H.ma = fminf( fminf( H.ma, fabsf( c[0] ) ), fabsf( c[1] ) );
+        H.ma = fminf( fminf( H.ma, fabsf( c[2] ) ), fabsf( c[3] ) );
+    }
+    // ---- exact tier: values inside the filter's error band ----------------------------
+    if ( DIAG || __any_sync( kFullMask, H.ma <= tau ) )
+    {
+        for ( int j = 0; j < seg; ++j )
+        {
+            const float2 b = fp[32 * j];
+            float c1[4], c[4];
+            mma_tf32( c1, H.a1[0], H.a1[1], H.a1[2], H.a1[3], b.x, b.y, H.cinit );
+            mma_tf32( c, H.a2[0], H.a2[1], H.a2[2], H.a2[3], b.x, b.y, c1 );
+            const unsigned bit = 1u << ( seg - 1 - j );
+#pragma unroll
+            for ( int k = 0; k < 4; ++k )
+            {
+                const int e = kTileCands * j + 2 * t + ( k & 1 );
+                const int hp = k < 2 ? H.pid_g : H.pid_g8;
+                if ( DIAG )
+                {
+                    const int cp = cpid[e];
+                    if ( hp >= 0 && cp >= 0 )
+                    {
+                        const float err = (float)fabs( (double)c[k] - exact_c( a, hp, cp ) );
+                        atomicMax( a.diag_maxerr, __float_as_uint( err ) );
+                        if ( err > tau * 0.5f )
+                            atomicAdd( a.diag_maxerr + 1, 1u );
+                    }
+                }
+                if ( fabsf( c[k] ) <= tau )
+                {
+                    const bool hit = exact_decide<HALF>( a, hp, cpid[e] );
+                    unsigned& m = k == 0 ? H.m0 : ( k == 1 ? H.m1 : ( k == 2 ? H.m2 : H.m3 ) );
+                    m = hit ? ( m | bit ) : ( m & ~bit );
+                }
+            }
+        }
+    }
+    H.ma = 3.0e38f;
+    // ---- half lists: x-major criterion on the windows of the home x column -----------
+    if ( HALF && n_filter > 0 )
+    {
+        const unsigned low = seg >= 32 ? 0xffffffffu : ( ( 1u << seg ) - 1u );
+#pragma unroll
+        for ( int k = 0; k < 4; ++k )
+        {
+            unsigned& m = k == 0 ? H.m0 : ( k == 1 ? H.m1 : ( k == 2 ? H.m2 : H.m3 ) );
+            const float hx = k < 2 ? H.hx_g : H.hx_g8;
+            const int hp = k < 2 ? H.pid_g : H.pid_g8;
+            unsigned mm = m & low;
+            while ( mm )
+            {
+                const int b = 31 - __clz( mm );
+                mm &= ~( 1u << b );
+                if ( seg - 1 - b >= n_filter )
+                    continue; // da = +1: a larger cell index means a larger x
+                const int e = kTileCands * ( seg - 1 - b ) + 2 * t + ( k & 1 );
+                const float2 fx = feat2[4 * e];
+                const float cx = fx.x + fx.y; // == x - Ox exactly
+                bool keep;
+                if ( cx > hx )
+                    keep = true; // float rounding is monotone
+                else if ( cx < hx )
+                    keep = false;
+                else
+                    keep = exact_decide<HALF>( a, hp, cpid[e] );
+                if ( !keep )
+                    m &= ~( 1u << b );
+            }
+        }
+    }
+}
+
+// End of a chunk of `in_chunk` (<= 32) tiles: normalise the words (tile i at bit 31 - i),
+// drop j == i, count, and store the 512-byte mask record.
+template <bool DIAG>
+CB_D void flush_chunk( const TileArgs& a, HomeTile& H, int in_chunk, int chunk_i, size_t chunk0,
+                       unsigned lane )
+{
+    const int g = (int)( lane >> 2 ), t = (int)( lane & 3u );
+    if ( in_chunk < kChunkTiles )
+    {
+        const int sh = kChunkTiles - in_chunk;
+        H.m0 <<= sh;
+        H.m1 <<= sh;
+        H.m2 <<= sh;
+        H.m3 <<= sh;
+    }
+    // j != i: the home particles sit at list entries selfbase .. selfbase + 15
+    if ( (int)( H.selfbase / kChunkEntries ) <= chunk_i &&
+         (int)( ( H.selfbase + 15u ) / kChunkEntries ) >= chunk_i )
+    {
+#pragma unroll
+        for ( int hh = 0; hh < 2; ++hh )
+        {
+            const unsigned p = H.selfbase + (unsigned)( g + 8 * hh );
+            const unsigned e = p % kChunkEntries;
+            if ( (int)( p / kChunkEntries ) == chunk_i && (int)( ( e & 7u ) >> 1 ) == t )
+            {
+                const unsigned keep = ~( 0x80000000u >> ( e >> 3 ) );
+                if ( hh == 0 )
+                {
+                    if ( e & 1u )
+                        H.m1 &= keep;
+                    else
+                        H.m0 &= keep;
+                }
+                else
+                {
+                    if ( e & 1u )
+                        H.m3 &= keep;
+                    else
+                        H.m2 &= keep;
+                }
+            }
+        }
+    }
+    if ( !H.act_g )
+        H.m0 = H.m1 = 0u;
+    if ( !H.act_g8 )
+        H.m2 = H.m3 = 0u;
+    H.cnt_g += __popc( H.m0 ) + __popc( H.m1 );
+    H.cnt_g8 += __popc( H.m2 ) + __popc( H.m3 );
+    if ( !DIAG )
+        a.masks[( chunk0 + (size_t)chunk_i ) * 32u + lane] = make_uint4( H.m0, H.m1, H.m2, H.m3 );
+    H.m0 = H.m1 = H.m2 = H.m3 = 0u;
+}
+
+// ---- per-warp kernel: every warp stages the candidates of its own tile ------------------
 // Shared memory of one warp.  TMA staging: candidates land in `raw` by cp.async.bulk.
 // LDG staging: every lane fetches its candidates itself through a per-tile source table.
 struct __align__( 16 ) CountSmemTma
 {
-    float4 f0[kPieceEntries];     // (hx, hy, hz, n_hi) of the staged candidates
-    float4 f1[kPieceEntries];     // (lx, ly, lz, n_lo)
+    float2 feat[kPieceEntries * 4];
     float4 raw[2][kPieceEntries]; // bulk-copy landing zone (q records), double buffered
+    int cpid[kPieceEntries];
     unsigned sp_start[16], sp_len[16], sp_pos[16];
-    float kscr[16]; // |x_i|^2 - r^2 of the home particles (accumulator init)
+    float scr[288];
     unsigned long long mbar[2];
-    CB_D int cand_pid( int buf, int e ) const { return __float_as_int( raw[buf][e].w ); }
 };
 struct __align__( 16 ) CountSmemLdg
 {
-    float4 f0[kPieceEntries];
-    float4 f1[kPieceEntries];
-    int cpid[kPieceEntries];        // particle ids of the staged candidates (exact tier)
-    unsigned tsrc[kTableTiles];     // sorted slot of the first entry of every mma tile
-    unsigned char tval[kTableTiles]; // valid entries (1..8) of every mma tile
-    float kscr[16];
-    CB_D int cand_pid( int, int e ) const { return cpid[e]; }
+    float2 feat[kPieceEntries * 4];
+    float4 raw[kPieceEntries];   // cp.async landing zone of the NEXT piece
+    int cpid[kPieceEntries];     // particle ids of the staged candidates (exact tier)
+    unsigned tsrc[kTableTiles];  // sorted slot of the first entry of every mma tile
+    float scr[288];
 };
 
-// Stage piece `pc` (candidate list entries [128 pc, 128 pc + 128)) into raw[buf]: every span
-// that intersects the piece is one bulk copy (16-byte records, 16-byte aligned on both
-// sides); the <= 7 padding entries behind a span's end and the tail behind the last tile
-// are filled with far-away sentinels by ordinary stores (disjoint from what the copies
-// write, so no proxy fence is needed; the buffer's previous readers finished before the
-// __syncwarp that precedes this call).  All lanes call.
+// Stage piece `pc` (candidate list entries [128 pc, 128 pc + 128)) into raw[buf]: every
+// window that intersects the piece is one bulk copy (16-byte records, 128-byte multiples).
+// All lanes call; the buffer's previous readers finished before the preceding __syncwarp.
 CB_D void issue_piece( CountSmemTma& S, const float4* __restrict__ q, int pc, int buf,
-                       int total_entries, unsigned lane )
+                       unsigned lane )
 {
-    const float4 sent = make_float4( 1.0e18f, 1.0e18f, 1.0e18f, __int_as_float( -1 ) );
     const unsigned p0 = (unsigned)( pc * kPieceEntries );
     const unsigned p1 = p0 + kPieceEntries;
     unsigned lo = 0u, hi = 0u, p = 0u;
     if ( lane < 9u )
     {
         p = S.sp_pos[lane];
-        const unsigned end = p + S.sp_len[lane];
         lo = max( p, p0 );
-        hi = min( end, p1 );
+        hi = min( p + S.sp_len[lane], p1 );
         if ( hi < lo )
             hi = lo;
-        // padding behind this span's end, if the end lies in this piece
-        if ( end > p0 && end <= p1 && S.sp_len[lane] != 0u )
-            for ( unsigned e = end; ( e & 7u ) != 0u; ++e )
-                S.raw[buf][e - p0] = sent;
     }
-    // tail behind the last tile (last piece only)
-    for ( unsigned e = max( (unsigned)total_entries, p0 ) + lane; e < p1; e += 32u )
-        S.raw[buf][e - p0] = sent;
     const unsigned bytes = ( hi - lo ) * 16u;
     const unsigned total = __reduce_add_sync( kFullMask, bytes );
     if ( lane == 0u )
@@ -377,21 +687,15 @@ CB_D void issue_piece( CountSmemTma& S, const float4* __restrict__ q, int pc, in
                   &S.mbar[buf] );
 }
 
-// Source table of the mma tiles [seg0, seg0 + kTableTiles): the lane that owns span s
-// writes the entries of its tiles (tile k of the span starts at sorted slot start + 8k).
-template <class SM>
-CB_D void build_tile_table( SM& S, int seg0, int tiles_before, int my_nt, unsigned sp_start,
-                            unsigned sp_len )
+// Source table of the mma tiles [seg0, seg0 + kTableTiles): the lane that owns window s
+// writes the entries of its tiles (tile k of the window starts at sorted slot start + 8k).
+CB_D void build_tile_table( unsigned* tsrc, int seg0, int tiles_before, int my_nt,
+                            unsigned sp_start )
 {
     const int i0 = max( 0, seg0 - tiles_before );
     const int i1 = min( my_nt, seg0 + kTableTiles - tiles_before );
     for ( int i = i0; i < i1; ++i )
-    {
-        const int k = tiles_before + i - seg0;
-        S.tsrc[k] = sp_start + (unsigned)( kTileCands * i );
-        S.tval[k] = (unsigned char)min( (unsigned)kTileCands,
-                                        sp_len - (unsigned)( kTileCands * i ) );
-    }
+        tsrc[tiles_before + i - seg0] = sp_start + (unsigned)( kTileCands * i );
 }
 
 template <bool HALF, bool DIAG, bool TMA>
@@ -403,7 +707,6 @@ __global__ void __launch_bounds__( kBlockT, 3 )
     const unsigned lane = threadIdx.x & 31u;
     const int wib = threadIdx.x >> 5;
     SM& S = reinterpret_cast<SM*>( s_dyn )[wib];
-    const int g = (int)( lane >> 2 ), t = (int)( lane & 3u );
     unsigned phase = 0u; // bit b: parity the next wait on mbar[b] uses
     if constexpr ( TMA )
     {
@@ -417,20 +720,37 @@ __global__ void __launch_bounds__( kBlockT, 3 )
         __syncwarp();
     }
     const int ntiles = *a.ntiles_dev;
-    float* f0w = reinterpret_cast<float*>( S.f0 );
-    float* f1w = reinterpret_cast<float*>( S.f1 );
-    const float4 sent = make_float4( 1.0e18f, 1.0e18f, 1.0e18f, __int_as_float( -1 ) );
 
-    for ( ;; )
+    // Tiles are handed out by a global ticket, two tickets ahead: the record of the next tile
+    // is in flight while the current one is swept.
+    auto grab = [&]() -> unsigned
     {
-        unsigned tile = 0u;
+        unsigned v = 0u;
         if ( lane == 0u )
-            tile = atomicAdd( a.ticket, 1u );
-        tile = __shfl_sync( kFullMask, tile, 0 );
+            v = atomicAdd( a.ticket, 1u );
+        return __shfl_sync( kFullMask, v, 0 );
+    };
+    unsigned tile = grab();
+    unsigned tile_next = grab();
+    uint4 rec_raw = make_uint4( 0u, 0u, 0u, 0u ), rec_next = rec_raw;
+    int chunk0 = 0, chunk0_next = 0;
+    if ( tile < (unsigned)ntiles )
+    {
+        rec_raw = a.recs[tile];
+        chunk0 = a.chunk_off[tile];
+    }
+    unsigned tile_nn = 0u;
+    for ( ;; tile = tile_next, tile_next = tile_nn, rec_raw = rec_next, chunk0 = chunk0_next )
+    {
         if ( tile >= (unsigned)ntiles )
             break;
-        const TileRec rc = unpack_rec( a.recs[tile] );
-        const int chunk0 = a.chunk_off[tile];
+        tile_nn = grab(); // needed only at the end of this iteration
+        if ( tile_next < (unsigned)ntiles )
+        {
+            rec_next = a.recs[tile_next];
+            chunk0_next = a.chunk_off[tile_next];
+        }
+        const TileRec rc = unpack_rec( rec_raw );
 
         // ---- home particles (lanes 0..15) ------------------------------------------
         float4 hq = make_float4( -1.0e18f, -1.0e18f, -1.0e18f, __int_as_float( -1 ) );
@@ -451,25 +771,14 @@ __global__ void __launch_bounds__( kBlockT, 3 )
         const float Ox = ( (float)rc.ca + 0.5f ) * a.wx;
         const float Oy = ( (float)rc.cb + 0.5f ) * a.wy;
         const float Oz = ( 0.5f * (float)( rc.zlo + rc.zhi ) + 0.5f ) * a.hz;
-        const float xh = hq.x - Ox, yh = hq.y - Oy, zh = hq.z - Oz;
-        // candidate spans (planned): lane s < 9 owns span s
+        // candidate windows (planned): lane s < 9 owns window s
         uint2 sp = make_uint2( 0u, 0u );
         if ( lane < 9u )
             sp = a.spans[(size_t)tile * 9u + lane];
-        __syncwarp();
-        if ( lane < 16u )
-        {
-            // A operands, one row per home particle (see mma_tf32):
-            //   A1 = [-2H, 1 | -2H, 1]   A2 = [-2L, 0 | -2L, 0]   C = |x_i|^2 - r^2
-            const float Hx = trunc_tf32( xh ), Hy = trunc_tf32( yh ), Hz = trunc_tf32( zh );
-            const float N = fmaf( zh, zh, fmaf( yh, yh, xh * xh ) );
-            S.f0[lane] = make_float4( -2.f * Hx, -2.f * Hy, -2.f * Hz, 1.f );
-            S.f1[lane] = make_float4( -2.f * ( xh - Hx ), -2.f * ( yh - Hy ),
-                                      -2.f * ( zh - Hz ), 0.f );
-            // (N - r2hi) - r2lo: N and r2hi are close in magnitude, r2lo is the small part
-            S.kscr[lane] = ( N - a.r2hi ) - a.r2lo;
-        }
-        const int my_nt = (int)( ( sp.y + kTileCands - 1 ) / kTileCands );
+        HomeTile H;
+        load_home_operands( H, S.scr, hq.x - Ox, hq.y - Oy, hq.z - Oz, pid, actmask, a.r2hi,
+                            a.r2lo, lane );
+        const int my_nt = (int)( sp.y / kTileCands );
         int incl = my_nt;
 #pragma unroll
         for ( int o = 1; o < 16; o <<= 1 )
@@ -479,23 +788,11 @@ __global__ void __launch_bounds__( kBlockT, 3 )
                 incl += y;
         }
         const int T = __shfl_sync( kFullMask, incl, 15 );
-        const int T0 = __shfl_sync( kFullMask, incl, 2 ); // tiles of the da = 0 spans
+        const int T0 = __shfl_sync( kFullMask, incl, 2 ); // tiles of the da = 0 windows
         const int tiles_before = incl - my_nt;
-        // list position of home particle h: selfbase + h (the home span is s = 1)
-        const unsigned selfbase =
+        // list entry of home particle h: selfbase + h (the home window is s = 1)
+        H.selfbase =
             __shfl_sync( kFullMask, (unsigned)tiles_before * kTileCands - sp.x, 1 ) + rc.first;
-        __syncwarp();
-        const float a1_lo = f0w[4 * g + t], a1_hi = f0w[4 * ( g + 8 ) + t];
-        const float a2_lo = f1w[4 * g + t], a2_hi = f1w[4 * ( g + 8 ) + t];
-        const float k_g = S.kscr[g], k_g8 = S.kscr[g + 8];
-        const float cinit[4] = { k_g, k_g, k_g8, k_g8 };
-        const float hx_g = __shfl_sync( kFullMask, xh, g );
-        const float hx_g8 = __shfl_sync( kFullMask, xh, g + 8 );
-        const int pid_g = __shfl_sync( kFullMask, pid, g );
-        const int pid_g8 = __shfl_sync( kFullMask, pid, g + 8 );
-        const bool act_g = ( actmask >> g ) & 1u;
-        const bool act_g8 = ( actmask >> ( g + 8 ) ) & 1u;
-        __syncwarp();
         if constexpr ( TMA )
         {
             if ( lane < 16u )
@@ -505,220 +802,110 @@ __global__ void __launch_bounds__( kBlockT, 3 )
                 S.sp_pos[lane] = (unsigned)tiles_before * kTileCands;
             }
             __syncwarp();
-            issue_piece( S, a.q, 0, 0, T * kTileCands, lane );
+            issue_piece( S, a.q, 0, 0, lane );
         }
         else
         {
-            build_tile_table( S, 0, tiles_before, my_nt, sp.x, sp.y );
+            build_tile_table( S.tsrc, 0, tiles_before, my_nt, sp.x );
             __syncwarp();
         }
+        // candidates of piece `pc` -> S.raw, asynchronously (per-lane cp.async: the loads of the
+        // next piece are in flight while the current one is swept, at no register cost)
+        auto prefetch_piece = [&]( int pc )
+        {
+            if constexpr ( !TMA )
+            {
+#pragma unroll
+                for ( int j = 0; j < kPieceEntries / 32; ++j )
+                {
+                    const int e = (int)lane + 32 * j;
+                    const int tl = min( pc * kPieceTiles + ( e >> 3 ), T - 1 );
+                    cp_async16( &S.raw[e],
+                                a.q + S.tsrc[tl & ( kTableTiles - 1 )] + (unsigned)( e & 7 ) );
+                }
+                cp_async_commit();
+            }
+        };
+        prefetch_piece( 0 );
 
-        // ---- pieces ----------------------------------------------------------------
+        // ---- pieces of 16 tiles; a mask chunk is two pieces ---------------------------
         const int npieces = ( T + kPieceTiles - 1 ) / kPieceTiles;
-        unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
-        float ma = 3.0e38f;
-        int cnt_g = 0, cnt_g8 = 0;
         int in_chunk = 0, chunk_i = 0;
         for ( int pc = 0; pc < npieces; ++pc )
         {
             const int buf = pc & 1;
+            float4 r[kPieceEntries / 32];
             if constexpr ( TMA )
             {
                 if ( pc + 1 < npieces )
-                    issue_piece( S, a.q, pc + 1, buf ^ 1, T * kTileCands, lane );
+                    issue_piece( S, a.q, pc + 1, buf ^ 1, lane );
                 while ( !mbar_try_wait( &S.mbar[buf], ( phase >> buf ) & 1u ) )
                 {
                 }
                 phase ^= 1u << buf;
-                __syncwarp(); // the sentinel stores of other lanes
+#pragma unroll
+                for ( int j = 0; j < kPieceEntries / 32; ++j )
+                    r[j] = S.raw[buf][(int)lane + 32 * j];
             }
-            else if ( pc > 0 && ( pc * kPieceTiles ) % kTableTiles == 0 )
+            else
             {
-                build_tile_table( S, pc * kPieceTiles, tiles_before, my_nt, sp.x, sp.y );
-                __syncwarp();
+                cp_async_wait_all();
+#pragma unroll
+                for ( int j = 0; j < kPieceEntries / 32; ++j )
+                    r[j] = S.raw[(int)lane + 32 * j]; // (each lane reads what it copied)
             }
             // transform: tile-local coordinates, tf32 hi/lo split, squared norm
-            float4 r[kPieceEntries / 32];
 #pragma unroll
             for ( int j = 0; j < kPieceEntries / 32; ++j )
             {
                 const int e = (int)lane + 32 * j;
-                if constexpr ( TMA )
-                    r[j] = S.raw[buf][e];
-                else
-                {
-                    const int tl = pc * kPieceTiles + ( e >> 3 );
-                    const int k = tl & ( kTableTiles - 1 );
-                    r[j] = sent;
-                    if ( tl < T && ( e & 7 ) < (int)S.tval[k] )
-                        r[j] = a.q[S.tsrc[k] + (unsigned)( e & 7 )];
-                }
-            }
-#pragma unroll
-            for ( int j = 0; j < kPieceEntries / 32; ++j )
-            {
-                const int e = (int)lane + 32 * j;
-                const float x = r[j].x - Ox, y = r[j].y - Oy, z = r[j].z - Oz;
-                const float hx = trunc_tf32( x ), hy = trunc_tf32( y ), hz = trunc_tf32( z );
-                const float n = fmaf( z, z, fmaf( y, y, x * x ) );
-                const float nh = trunc_tf32( n );
-                S.f0[e] = make_float4( hx, hy, hz, nh );
-                S.f1[e] = make_float4( x - hx, y - hy, z - hz, n - nh );
-                if constexpr ( !TMA )
-                    S.cpid[e] = __float_as_int( r[j].w );
+                store_features( S.feat, e, r[j].x - Ox, r[j].y - Oy, r[j].z - Oz );
+                S.cpid[e] = __float_as_int( r[j].w );
             }
             __syncwarp();
+            if constexpr ( !TMA )
+            {
+                if ( pc + 1 < npieces )
+                {
+                    if ( ( ( pc + 1 ) * kPieceTiles ) % kTableTiles == 0 )
+                    {
+                        build_tile_table( S.tsrc, ( pc + 1 ) * kPieceTiles, tiles_before, my_nt,
+                                          sp.x );
+                        __syncwarp();
+                    }
+                    prefetch_piece( pc + 1 );
+                }
+            }
             const int nt_p = min( kPieceTiles, T - pc * kPieceTiles );
-#pragma unroll 4
-            for ( int j = 0; j < nt_p; ++j )
-            {
-                const float b0 = f0w[32 * j + (int)lane];
-                const float b1 = f1w[32 * j + (int)lane];
-                float c1[4], c[4];
-                mma_tf32( c1, a1_lo, a1_hi, a1_lo, a1_hi, b0, b1, cinit );
-                mma_tf32( c, a2_lo, a2_hi, a2_lo, a2_hi, b0, b1, c1 );
-                m0 = __funnelshift_l( __float_as_uint( c[0] ), m0, 1 );
-                m1 = __funnelshift_l( __float_as_uint( c[1] ), m1, 1 );
-                m2 = __funnelshift_l( __float_as_uint( c[2] ), m2, 1 );
-                m3 = __funnelshift_l( __float_as_uint( c[3] ), m3, 1 );
-                ma = fminf( fminf( ma, fabsf( c[0] ) ), fabsf( c[1] ) );
-                ma = fminf( fminf( ma, fabsf( c[2] ) ), fabsf( c[3] ) );
-            }
-            // ---- exact tier: values inside the filter's error band --------------------
-            if ( DIAG || __any_sync( kFullMask, ma <= a.tau ) )
-            {
-                for ( int j = 0; j < nt_p; ++j )
-                {
-                    const float b0 = f0w[32 * j + (int)lane];
-                    const float b1 = f1w[32 * j + (int)lane];
-                    float c1[4], c[4];
-                    mma_tf32( c1, a1_lo, a1_hi, a1_lo, a1_hi, b0, b1, cinit );
-                    mma_tf32( c, a2_lo, a2_hi, a2_lo, a2_hi, b0, b1, c1 );
-                    const unsigned bit = 1u << ( nt_p - 1 - j );
-#pragma unroll
-                    for ( int k = 0; k < 4; ++k )
-                    {
-                        const int e = kTileCands * j + 2 * t + ( k & 1 );
-                        const int hp = k < 2 ? pid_g : pid_g8;
-                        if ( DIAG )
-                        {
-                            const int cp = S.cand_pid( buf, e );
-                            if ( hp >= 0 && cp >= 0 )
-                            {
-                                const float err =
-                                    (float)fabs( (double)c[k] - exact_c( a, hp, cp ) );
-                                atomicMax( a.diag_maxerr, __float_as_uint( err ) );
-                            }
-                        }
-                        if ( fabsf( c[k] ) <= a.tau )
-                        {
-                            const bool hit = exact_decide<HALF>( a, hp, S.cand_pid( buf, e ) );
-                            unsigned& m = k == 0 ? m0 : ( k == 1 ? m1 : ( k == 2 ? m2 : m3 ) );
-                            m = hit ? ( m | bit ) : ( m & ~bit );
-                        }
-                    }
-                }
-            }
-            ma = 3.0e38f;
-            // ---- half lists: x-major criterion on the spans of the home x column ------
-            if ( HALF && pc * kPieceTiles < T0 )
-            {
-                const unsigned low = ( 1u << nt_p ) - 1u; // nt_p <= 16
-#pragma unroll
-                for ( int k = 0; k < 4; ++k )
-                {
-                    unsigned& m = k == 0 ? m0 : ( k == 1 ? m1 : ( k == 2 ? m2 : m3 ) );
-                    const float hx = k < 2 ? hx_g : hx_g8;
-                    const int hp = k < 2 ? pid_g : pid_g8;
-                    unsigned mm = m & low;
-                    while ( mm )
-                    {
-                        const int b = 31 - __clz( mm );
-                        mm &= ~( 1u << b );
-                        const int j = nt_p - 1 - b;
-                        if ( pc * kPieceTiles + j >= T0 )
-                            continue; // da = +1: a larger cell index means a larger x
-                        const int e = kTileCands * j + 2 * t + ( k & 1 );
-                        const float cx = S.f0[e].x + S.f1[e].x; // == x - Ox exactly
-                        bool keep;
-                        if ( cx > hx )
-                            keep = true; // float rounding is monotone
-                        else if ( cx < hx )
-                            keep = false;
-                        else
-                            keep = exact_decide<HALF>( a, hp, S.cand_pid( buf, e ) );
-                        if ( !keep )
-                            m &= ~( 1u << b );
-                    }
-                }
-            }
+            sweep_segment<HALF, DIAG>( a, H, S.feat, S.cpid, nt_p,
+                                       min( max( T0 - pc * kPieceTiles, 0 ), nt_p ), a.tau, lane );
             in_chunk += nt_p;
             if ( in_chunk == kChunkTiles || pc == npieces - 1 )
             {
-                // normalise: tile i of the chunk sits at bit 31 - i
-                if ( in_chunk < kChunkTiles )
-                {
-                    const int sh = kChunkTiles - in_chunk;
-                    m0 <<= sh;
-                    m1 <<= sh;
-                    m2 <<= sh;
-                    m3 <<= sh;
-                }
-                // j != i: the home particles sit at list entries selfbase .. selfbase + 15
-                if ( (int)( selfbase / kChunkEntries ) <= chunk_i &&
-                     (int)( ( selfbase + 15u ) / kChunkEntries ) >= chunk_i )
-                {
-#pragma unroll
-                    for ( int hh = 0; hh < 2; ++hh )
-                    {
-                        const unsigned p = selfbase + (unsigned)( g + 8 * hh );
-                        const unsigned e = p % kChunkEntries;
-                        if ( (int)( p / kChunkEntries ) == chunk_i &&
-                             (int)( ( e & 7u ) >> 1 ) == t )
-                        {
-                            const unsigned keep = ~( 0x80000000u >> ( e >> 3 ) );
-                            if ( hh == 0 )
-                            {
-                                if ( e & 1u )
-                                    m1 &= keep;
-                                else
-                                    m0 &= keep;
-                            }
-                            else
-                            {
-                                if ( e & 1u )
-                                    m3 &= keep;
-                                else
-                                    m2 &= keep;
-                            }
-                        }
-                    }
-                }
-                if ( !act_g )
-                    m0 = m1 = 0u;
-                if ( !act_g8 )
-                    m2 = m3 = 0u;
-                cnt_g += __popc( m0 ) + __popc( m1 );
-                cnt_g8 += __popc( m2 ) + __popc( m3 );
-                if ( !DIAG )
-                    a.masks[( (size_t)chunk0 + chunk_i ) * 32u + lane] =
-                        make_uint4( m0, m1, m2, m3 );
-                m0 = m1 = m2 = m3 = 0u;
+                flush_chunk<DIAG>( a, H, in_chunk, chunk_i, (size_t)chunk0, lane );
                 in_chunk = 0;
                 ++chunk_i;
             }
             __syncwarp();
         }
-        cnt_g += __shfl_xor_sync( kFullMask, cnt_g, 1 );
-        cnt_g += __shfl_xor_sync( kFullMask, cnt_g, 2 );
-        cnt_g8 += __shfl_xor_sync( kFullMask, cnt_g8, 1 );
-        cnt_g8 += __shfl_xor_sync( kFullMask, cnt_g8, 2 );
+        H.cnt_g += __shfl_xor_sync( kFullMask, H.cnt_g, 1 );
+        H.cnt_g += __shfl_xor_sync( kFullMask, H.cnt_g, 2 );
+        H.cnt_g8 += __shfl_xor_sync( kFullMask, H.cnt_g8, 1 );
+        H.cnt_g8 += __shfl_xor_sync( kFullMask, H.cnt_g8, 2 );
         if ( !DIAG )
         {
-            if ( t == 0 && act_g )
-                a.counts[pid_g] = cnt_g;
-            if ( t == 1 && act_g8 )
-                a.counts[pid_g8] = cnt_g8;
+            // counts[] in particle order (the list's array) and in sorted order (fill pass)
+            const int t = (int)( lane & 3u ), g = (int)( lane >> 2 );
+            if ( t == 0 && H.act_g )
+            {
+                a.counts[H.pid_g] = H.cnt_g;
+                a.cnt_sorted[rc.first + g] = H.cnt_g;
+            }
+            if ( t == 1 && H.act_g8 )
+            {
+                a.counts[H.pid_g8] = H.cnt_g8;
+                a.cnt_sorted[rc.first + g + 8] = H.cnt_g8;
+            }
         }
     }
 }
@@ -734,7 +921,6 @@ struct __align__( 16 ) FillSmem
     int rows[kRowCap];
     unsigned ids[kChunkEntries]; // ids of the chunk's candidates, tiles in REVERSE order
     unsigned tsrc[kTableTiles];
-    unsigned char tval[kTableTiles];
 };
 
 // Expand one mask word: tile i of the chunk is bit 31 - i, and its ids sit at
@@ -759,7 +945,7 @@ CB_D void expand_word_global( unsigned mm, const unsigned* ids2, int*& out )
 }
 
 template <bool CSR>
-__global__ void __launch_bounds__( kBlockT, 3 )
+__global__ void __launch_bounds__( kBlockT, 4 )
     k_tile_fill( const __grid_constant__ TileArgs a )
 {
     extern __shared__ __align__( 16 ) unsigned char s_dyn[];
@@ -769,34 +955,57 @@ __global__ void __launch_bounds__( kBlockT, 3 )
     const int g = (int)( lane >> 2 ), t = (int)( lane & 3u );
     const int ntiles = *a.ntiles_dev;
 
-    for ( ;; )
+    // The kernel is bound by the latency of dependent global loads, so everything a tile needs
+    // is requested as early as its address is known: tickets two tiles ahead, the record of
+    // the next tile during the current one, row bookkeeping in sorted order (no gather through
+    // the permutation), masks and candidate ids one chunk ahead.
+    auto grab = [&]() -> unsigned
     {
-        unsigned tile = 0u;
+        unsigned v = 0u;
         if ( lane == 0u )
-            tile = atomicAdd( a.ticket + 1, 1u );
-        tile = __shfl_sync( kFullMask, tile, 0 );
+            v = atomicAdd( a.ticket + 1, 1u );
+        return __shfl_sync( kFullMask, v, 0 );
+    };
+    unsigned tile = grab();
+    unsigned tile_next = grab();
+    unsigned tile_nn = 0u;
+    uint4 rec_raw = make_uint4( 0u, 0u, 0u, 0u ), rec_next = rec_raw;
+    int chunk0 = 0, chunk0_next = 0;
+    if ( tile < (unsigned)ntiles )
+    {
+        rec_raw = a.recs[tile];
+        chunk0 = a.chunk_off[tile];
+    }
+    for ( ;; tile = tile_next, tile_next = tile_nn, rec_raw = rec_next, chunk0 = chunk0_next )
+    {
         if ( tile >= (unsigned)ntiles )
             break;
-        const TileRec rc = unpack_rec( a.recs[tile] );
-        const int chunk0 = a.chunk_off[tile];
-
+        tile_nn = grab();
+        if ( tile_next < (unsigned)ntiles )
+        {
+            rec_next = a.recs[tile_next];
+            chunk0_next = a.chunk_off[tile_next];
+        }
+        const TileRec rc = unpack_rec( rec_raw );
+        uint4 m_next = a.masks[(size_t)chunk0 * 32u + lane];
         int pid = -1, cnt = 0;
         long long dst = 0;
         if ( (int)lane < rc.np )
         {
-            pid = (int)a.permute[rc.first + lane];
-            if ( pid >= a.begin && pid < a.end )
-            {
-                cnt = a.counts[pid];
-                dst = CSR ? (long long)a.offsets[pid] : (long long)pid * a.width;
-            }
+            cnt = a.cnt_sorted[rc.first + lane];
+            if ( CSR )
+                dst = (long long)a.dst_sorted[rc.first + lane];
+            else
+                pid = (int)a.permute[rc.first + lane];
         }
         uint2 sp = make_uint2( 0u, 0u );
         if ( lane < 9u )
             sp = a.spans[(size_t)tile * 9u + lane];
-        // inclusive scans: the 16 row sizes; the mma tiles of the 9 spans
+        if ( !CSR )
+            dst = (long long)pid * a.width;
+        // inclusive scans: the 16 row sizes; the mma tiles of the 9 windows
         int inc = cnt;
-        const int my_nt = (int)( ( sp.y + kTileCands - 1 ) / kTileCands );
+        const int my_nt = (int)( sp.y / kTileCands );
         int incl = my_nt;
 #pragma unroll
         for ( int o = 1; o < 16; o <<= 1 )
@@ -815,10 +1024,31 @@ __global__ void __launch_bounds__( kBlockT, 3 )
         const int T = __shfl_sync( kFullMask, incl, 15 );
         const int tiles_before = incl - my_nt;
         __syncwarp();
-        build_tile_table( S, 0, tiles_before, my_nt, sp.x, sp.y );
+        build_tile_table( S.tsrc, 0, tiles_before, my_nt, sp.x );
         int table_seg = 0;
         __syncwarp();
         const int nchunks = ( T + kChunkTiles - 1 ) / kChunkTiles;
+        // ids of the candidates of chunk ci, one register per 32 entries (pad slots carry -1;
+        // their mask bits are zero)
+        unsigned idr[kChunkEntries / 32];
+        auto load_ids = [&]( int ci )
+        {
+            const int seg = ( ci * kChunkTiles ) / kTableTiles;
+            if ( seg != table_seg )
+            {
+                __syncwarp();
+                build_tile_table( S.tsrc, seg * kTableTiles, tiles_before, my_nt, sp.x );
+                table_seg = seg;
+                __syncwarp();
+            }
+#pragma unroll
+            for ( int k = 0; k < kChunkEntries / 32; ++k )
+            {
+                const int e = (int)lane + 32 * k;
+                const int tl = min( ci * kChunkTiles + ( e >> 3 ), T - 1 );
+                idr[k] = a.permute[S.tsrc[tl & ( kTableTiles - 1 )] + (unsigned)( e & 7 )];
+            }
+        };
 
         // Row windows [ha, hb): as many rows as fit the staging buffer (normally all 16);
         // a single row longer than the buffer goes straight to global memory.
@@ -846,36 +1076,29 @@ __global__ void __launch_bounds__( kBlockT, 3 )
                 int cur_g8 = __shfl_sync( kFullMask, rowstart, g + 8 );
                 int* gout_g = a.neighbors + __shfl_sync( kFullMask, dst, g );
                 int* gout_g8 = a.neighbors + __shfl_sync( kFullMask, dst, g + 8 );
+                if ( ha != 0 )
+                    m_next = a.masks[(size_t)chunk0 * 32u + lane];
+                load_ids( 0 );
                 for ( int ci = 0; ci < nchunks; ++ci )
                 {
-                    uint4 m = a.masks[( (size_t)chunk0 + ci ) * 32u + lane];
-                    if ( !in_g )
-                        m.x = m.y = 0u;
-                    if ( !in_g8 )
-                        m.z = m.w = 0u;
-                    if ( !__any_sync( kFullMask, ( m.x | m.y | m.z | m.w ) != 0u ) )
-                        continue;
-                    __syncwarp();
-                    const int seg = ( ci * kChunkTiles ) / kTableTiles;
-                    if ( seg != table_seg )
-                    {
-                        build_tile_table( S, seg * kTableTiles, tiles_before, my_nt, sp.x, sp.y );
-                        table_seg = seg;
-                        __syncwarp();
-                    }
-                    // ids of the chunk's candidates.  Entries behind a span's end inside its
-                    // last tile read whatever follows in `permute` (padded by 8): their
-                    // mask bits are zero, the values are never used.
+                    uint4 m = m_next;
+                    __syncwarp(); // the previous chunk's walk is done with S.ids
 #pragma unroll
                     for ( int k = 0; k < kChunkEntries / 32; ++k )
                     {
                         const int e = (int)lane + 32 * k;
-                        const int tl = ci * kChunkTiles + ( e >> 3 );
-                        if ( tl < T )
-                            S.ids[( 31 - ( e >> 3 ) ) * kTileCands + ( e & 7 )] =
-                                a.permute[S.tsrc[tl & ( kTableTiles - 1 )] + (unsigned)( e & 7 )];
+                        S.ids[( 31 - ( e >> 3 ) ) * kTileCands + ( e & 7 )] = idr[k];
+                    }
+                    if ( ci + 1 < nchunks )
+                    {
+                        m_next = a.masks[( (size_t)chunk0 + ci + 1 ) * 32u + lane];
+                        load_ids( ci + 1 );
                     }
                     __syncwarp();
+                    if ( !in_g )
+                        m.x = m.y = 0u;
+                    if ( !in_g8 )
+                        m.z = m.w = 0u;
                     // where this thread's hits go: exclusive prefix over the quad
                     const int pg = __popc( m.x ) + __popc( m.y );
                     const int pg8 = __popc( m.z ) + __popc( m.w );
@@ -914,23 +1137,47 @@ __global__ void __launch_bounds__( kBlockT, 3 )
                 __syncwarp();
                 if ( !direct )
                 {
-                    // rows leave shared memory coalesced, each to its final place
+                    // rows leave shared memory coalesced, each to its final place; up to
+                    // 96 ids per row without a loop
 #pragma unroll 1
                     for ( int h = ha; h < hb; ++h )
                     {
                         const int c = __shfl_sync( kFullMask, cnt, h );
                         const int rs = __shfl_sync( kFullMask, rowstart, h );
-                        int* d = a.neighbors + ( __shfl_sync( kFullMask, dst, h ) - rs );
-                        const int end = rs + c;
+                        int* d = a.neighbors + __shfl_sync( kFullMask, dst, h ) + lane;
+                        const int* src = S.rows + rs + lane;
+                        const int left = c - (int)lane;
+                        if ( left > 0 )
+                            __stcs( d, src[0] );
+                        if ( left > 32 )
+                            __stcs( d + 32, src[32] );
+                        if ( left > 64 )
+                            __stcs( d + 64, src[64] );
 #pragma unroll 1
-                        for ( int i = rs + (int)lane; i < end; i += 32 )
-                            __stcs( d + i, S.rows[i] );
+                        for ( int i = 96; i < left; i += 32 )
+                            __stcs( d + i, src[i] );
                     }
                 }
                 __syncwarp();
             }
             ha = hb;
         }
+    }
+}
+
+// dst_sorted[s] = offsets[permute[s]]: the CSR row start of the particle in sorted slot s, so
+// the fill pass reads its row bookkeeping coalesced instead of through the permutation.
+__global__ void __launch_bounds__( 256 )
+    k_sorted_dst( const unsigned* __restrict__ permute, const int* __restrict__ offsets,
+                  const unsigned* __restrict__ cell_off, long long ncells,
+                  int* __restrict__ dst_sorted )
+{
+    const long long ns = cell_off[ncells];
+    for ( long long s = (long long)blockIdx.x * 256 + threadIdx.x; s < ns;
+          s += (long long)gridDim.x * 256 )
+    {
+        const unsigned pid = permute[s];
+        dst_sorted[s] = pid == 0xffffffffu ? 0 : offsets[pid];
     }
 }
 
@@ -1038,10 +1285,11 @@ void make_tile_grid( TileGrid& tg, const double* grid_min, const double* grid_ma
     tg.ncells = tg.ncols * tg.nz;
 }
 
-double tile_filter_bound( const TileGrid& tg, double radius )
+double tile_filter_bound( const TileGrid& tg, double radius, int nzc )
 {
     // See DESIGN.md "Exactness (v2)".  u = 2^-24 (fp32 unit roundoff), v = 2^-20 (what the
     // hi/lo tf32 split drops), gam = 2^-21 per accumulated sum inside the tensor core.
+    // nzc = z cells the home particles of one staging span (tile-local origin at their centre).
     const double u = ldexp( 1.0, -24 ), v = ldexp( 1.0, -20 ), gam = ldexp( 1.0, -21 );
     double M = 0.0;
     for ( int d = 0; d < 3; ++d )
@@ -1049,9 +1297,9 @@ double tile_filter_bound( const TileGrid& tg, double radius )
     M *= 1.0 + 1.0e-9;
     const double sl = 1.0 + 1.0e-5;
     const double Dx = 1.5 * tg.g.dx[0] * sl, Dy = 1.5 * tg.g.dx[1] * sl;
-    const double Dz = ( 0.5 * tg.zb + tg.kz + 0.5 ) * tg.g.dx[2] * sl;
+    const double Dz = ( 0.5 * nzc + tg.kz + 1.0 ) * tg.g.dx[2] * sl;
     const double Hx = 0.5 * tg.g.dx[0] * sl, Hy = 0.5 * tg.g.dx[1] * sl;
-    const double Hz = ( 0.5 * tg.zb + 0.5 ) * tg.g.dx[2] * sl;
+    const double Hz = ( 0.5 * nzc + 0.5 ) * tg.g.dx[2] * sl;
     const double Dmax = fmax( Dx, fmax( Dy, Dz ) );
     const double S = Dx * Dx + Dy * Dy + Dz * Dz;
     const double Sh = Hx * Hx + Hy * Hy + Hz * Hz;
@@ -1060,18 +1308,39 @@ double tile_filter_bound( const TileGrid& tg, double radius )
     // (1)+(2) coordinate roundings (q = fl32(x - min), x' = fl32(q - O)), for s <= 4 r^2
     double E = 4.0 * sqrt( 3.0 ) * u * ( M + Dmax ) * ( 2.02 * radius ) +
                12.0 * u * u * ( M * M + Dmax * Dmax );
-    // (3) norms in fp32, hi/lo splits, dropped lo*lo, cutoff split, accumulation
+    // (3) norms in fp32, hi/lo splits, cutoff split, accumulation
     E += 3.0 * u * ( S + Sh ) + v * ( S + Sh ) + 6.0 * v * HD + v * rsqr;
     E += 2.0 * u * ( Sh + rsqr ); // accumulator init fl(fl(N - r2hi) - r2lo)
     E += 2.0 * gam * ( 2.0 * HD * ( 1.0 + 1.0e-3 ) + S + Sh + rsqr );
     return E;
 }
 
-int tile_gather_q( const cb_positions& x, long long n, const unsigned* permute, float4* q,
-                   const double* origin, cudaStream_t stream )
+int tile_bin( const TileGrid& tg, const cb_positions& x, int* cell_counts, unsigned* cell_off,
+              uint2* cellslot, unsigned char* pads, float4* q, unsigned* permute,
+              DeviceBuffer& scan_scratch, cudaStream_t stream )
 {
-    k_gather_q<<<launch_grid_for( n + 8, 256 ), 256, 0, stream>>>(
-        make_access( x ), n, permute, q, origin[0], origin[1], origin[2] );
+    const long long n = x.n;
+    CB_CUDA( cudaMemsetAsync( cell_counts, 0, sizeof( int ) * (size_t)tg.ncells, stream ) );
+    if ( n > 0 )
+    {
+        k_tbin_count<<<launch_grid_for( n, 256 ), 256, 0, stream>>>(
+            make_access( x ), to_grid( tg.g ), n, cell_counts, cellslot );
+        CB_CHECK_LAUNCH();
+    }
+    k_tbin_pad<<<launch_grid_for( tg.ncols * 32, 256 ), 256, 0, stream>>>( cell_counts, tg.ncols,
+                                                                           tg.nz, pads );
+    CB_CHECK_LAUNCH();
+    CB_TRY( exclusive_scan_i32( cell_counts, reinterpret_cast<int*>( cell_off ), tg.ncells,
+                                true, nullptr, scan_scratch, stream ) );
+    if ( n > 0 )
+    {
+        k_tbin_scatter<<<launch_grid_for( n, 256 ), 256, 0, stream>>>(
+            make_access( x ), n, cellslot, cell_off, q, permute, tg.g.min[0], tg.g.min[1],
+            tg.g.min[2] );
+        CB_CHECK_LAUNCH();
+    }
+    k_tbin_sentinels<<<launch_grid_for( tg.ncols + 1, 256 ), 256, 0, stream>>>(
+        cell_off, pads, tg.ncols, tg.nz, q, permute );
     CB_CHECK_LAUNCH();
     return CB_OK;
 }
@@ -1096,36 +1365,44 @@ int tile_plan( const TileGrid& tg, const unsigned* cell_off, bool half, int* blo
     return CB_OK;
 }
 
+// CB_TILE_STAGING = async (default: per-lane cp.async prefetch) | tma (cp.async.bulk spans).
 static bool use_tma_staging()
 {
     const char* e = getenv( "CB_TILE_STAGING" );
     return e && strcmp( e, "tma" ) == 0;
 }
 
-int tile_count_pass( const TileArgs& a, bool half, cudaStream_t stream )
+template <bool DIAG>
+static int launch_count( const TileArgs& a, bool half, cudaStream_t stream )
 {
     if ( use_tma_staging() )
     {
         const int smem = (int)sizeof( CountSmemTma ) * kWarpsT;
-        return half ? launch_persistent( k_tile_count<true, false, true>, smem, a, stream )
-                    : launch_persistent( k_tile_count<false, false, true>, smem, a, stream );
+        return half ? launch_persistent( k_tile_count<true, DIAG, true>, smem, a, stream )
+                    : launch_persistent( k_tile_count<false, DIAG, true>, smem, a, stream );
     }
     const int smem = (int)sizeof( CountSmemLdg ) * kWarpsT;
-    return half ? launch_persistent( k_tile_count<true, false, false>, smem, a, stream )
-                : launch_persistent( k_tile_count<false, false, false>, smem, a, stream );
+    return half ? launch_persistent( k_tile_count<true, DIAG, false>, smem, a, stream )
+                : launch_persistent( k_tile_count<false, DIAG, false>, smem, a, stream );
+}
+
+int tile_count_pass( const TileArgs& a, bool half, cudaStream_t stream )
+{
+    return launch_count<false>( a, half, stream );
 }
 
 int tile_diag_pass( const TileArgs& a, bool half, cudaStream_t stream )
 {
-    if ( use_tma_staging() )
-    {
-        const int smem = (int)sizeof( CountSmemTma ) * kWarpsT;
-        return half ? launch_persistent( k_tile_count<true, true, true>, smem, a, stream )
-                    : launch_persistent( k_tile_count<false, true, true>, smem, a, stream );
-    }
-    const int smem = (int)sizeof( CountSmemLdg ) * kWarpsT;
-    return half ? launch_persistent( k_tile_count<true, true, false>, smem, a, stream )
-                : launch_persistent( k_tile_count<false, true, false>, smem, a, stream );
+    return launch_count<true>( a, half, stream );
+}
+
+int tile_sorted_dst( const TileArgs& a, long long ncells, long long ns_cap, int* dst_sorted,
+                     cudaStream_t stream )
+{
+    k_sorted_dst<<<launch_grid_for( ns_cap, 256 ), 256, 0, stream>>>( a.permute, a.offsets,
+                                                                     a.cell_off, ncells, dst_sorted );
+    CB_CHECK_LAUNCH();
+    return CB_OK;
 }
 
 int tile_fill_pass( const TileArgs& a, bool csr, cudaStream_t stream )

@@ -52,14 +52,19 @@ struct TileArgs
     int R;                     // reference stencil range in user cells
     double rsqr, band;
     float r2hi, r2lo;          // tf32 split of r*r
-    float tau;                 // |c| <= tau: decided by the exact tier
+    float tau;                 // |c| <= tau: decided by the exact tier (one tile per origin)
+    const float* tau_tab;      // tau when the home particles of one origin span k z cells
+    int tau_tab_n;
     // rows
     long long n, begin, end;
     int* counts;
+    int* cnt_sorted;       // counts in sorted-slot order (0 for rows that are not built)
+    const int* dst_sorted; // CSR: offsets in sorted-slot order (fill pass)
     const int* offsets; // CSR row starts (fill pass); nullptr for 2D
     int* neighbors;
     long long width;    // 2D row width
-    // diagnostics (cb_verlet_tile_selftest): max |c_mma - c_exact| as float bits
+    // diagnostics (cb_verlet_filter_selftest): [0] max |c_mma - c_exact| as float bits,
+    // [1] number of values that missed the bound
     unsigned* diag_maxerr;
 };
 
@@ -68,11 +73,15 @@ void make_tile_grid( TileGrid& tg, const double* grid_min, const double* grid_ma
                      double radius, long long n );
 
 // Error bound of the tf32 filter for this grid (DESIGN.md "Exactness"); tau = 2 * bound.
-double tile_filter_bound( const TileGrid& tg, double radius );
+double tile_filter_bound( const TileGrid& tg, double radius, int nzc );
 
-// q[s] = float(x[permute[s]] - min), id; q[n .. n+8) = padding far away.
-int tile_gather_q( const cb_positions& x, long long n, const unsigned* permute, float4* q,
-                   const double* origin, cudaStream_t stream );
+// Fused binning on the internal grid: cell_off[ncells+1] (every column padded to a multiple
+// of 8 slots plus 8), q / permute in cell-sorted order (pad slots hold far-away sentinels and
+// id -1).  The sorted arrays need sorted_capacity(tg, n) + 8 slots.
+inline long long sorted_capacity( const TileGrid& tg, long long n ) { return n + 16 * tg.ncols; }
+int tile_bin( const TileGrid& tg, const cb_positions& x, int* cell_counts, unsigned* cell_off,
+              uint2* cellslot, unsigned char* pads, float4* q, unsigned* permute,
+              DeviceBuffer& scan_scratch, cudaStream_t stream );
 
 // Tile records + mask chunk offsets.  block_tiles/tile_base: [nblocks+1] ints;
 // recs: capacity n/16 + nblocks + 1; chunk_off: same + 1.
@@ -81,6 +90,8 @@ int tile_plan( const TileGrid& tg, const unsigned* cell_off, bool half, int* blo
                long long rec_capacity, DeviceBuffer& scan_scratch, cudaStream_t stream );
 
 int tile_count_pass( const TileArgs& a, bool half, cudaStream_t stream );
+int tile_sorted_dst( const TileArgs& a, long long ncells, long long ns_cap, int* dst_sorted,
+                     cudaStream_t stream );
 int tile_fill_pass( const TileArgs& a, bool csr, cudaStream_t stream );
 // Count pass with every filter value checked against the exact arithmetic (tests only).
 int tile_diag_pass( const TileArgs& a, bool half, cudaStream_t stream );

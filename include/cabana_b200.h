@@ -267,7 +267,8 @@ int cb_verlet_get_phase_times(const cb_verlet* list, double* ms_h);
 /* Self-test of the tensor-core distance filter the build relies on (tests only): runs the
  * count pass over `x` with EVERY filter value compared with the exact FP64 arithmetic.
  * out_h[0] = largest |filter - exact| observed, out_h[1] = the proven bound the in/out
- * decisions assume (values closer than twice that to the cutoff go to the exact tier). */
+ * decisions assume for one tile (values closer than twice the bound to the cutoff go to the
+ * exact tier), out_h[2] = number of values whose error exceeded the bound in force. */
 int cb_verlet_filter_selftest(cb_verlet* list, const cb_positions* x,
                               double neighborhood_radius, const double* grid_min_h,
                               const double* grid_max_h, int algorithm, double* out_h,
