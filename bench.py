@@ -34,7 +34,7 @@ UNIT = "neighbors/s"
 FCC_CELLS = 159          # 4 * 159^3 = 16 078 716 atoms
 RADIUS = 2.8             # 2.5 sigma cutoff + 0.3 sigma skin
 CELL_RATIO = 1.0
-CPU_SAMPLE_CELLS = int(os.environ.get("CB_BENCH_CPU_CELLS", "64"))  # FCC cells per side of the CPU sample
+CPU_SAMPLE_CELLS = int(os.environ.get("CB_BENCH_CPU_CELLS", "100"))  # cpu_baseline sample: 4 * 100^3 atoms
 
 
 def _peaks():
@@ -139,49 +139,75 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------- CPU arm
-def cpu_reference_run(steps: int, warmup: int, cells: int = CPU_SAMPLE_CELLS):
-    """Time the CPU port of the reference path (oracle/) on a bounded FCC sample."""
+def _cpu_setup():
+    """The timed CPU legs use the -march=native copy of the oracle (built on the host that runs
+    it) and EVERY host core: torch.distributed.run exports OMP_NUM_THREADS=1, which the oracle
+    must not inherit."""
     import oracle
+
+    native = oracle.use_native_build()
+    threads = oracle.use_all_cores()
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    assert threads > 1 or avail == 1, f"CPU arm would run on {threads} of {avail} cores"
+    return oracle, threads, native
+
+
+def cpu_reference_run(steps: int, warmup: int, cells: int = CPU_SAMPLE_CELLS):
+    """Time the CPU port of the reference path (oracle/) on an FCC lattice of `cells`^3 unit
+    cells (cells = 159 is the full cfg3 workload).  Returns the last build for parity checks."""
+    oracle, threads, native = _cpu_setup()
     from cabana_b200 import datasets
 
     ps = datasets.fcc_lattice(cells)
     x = oracle.slice_from_xyz(ps.xyz, vlen=16)  # host AoSoA vector length (PerformanceTraits)
-    threads = oracle.num_threads()
-    times, total = [], 0
+    times, res = [], None
     for it in range(warmup + steps):
+        res = None   # (one 5 GB list at a time)
         t0 = time.perf_counter()
         res = oracle.verlet_build(x, 0, ps.n, ps.radius, CELL_RATIO, ps.grid_min, ps.grid_max,
                                   algo=oracle.FULL, layout=oracle.CSR)
         dt = time.perf_counter() - t0
-        total = res.total
         if it >= warmup:
             times.append(dt)
     avg = float(np.mean(times))
+    what = ("the full workload" if cells == FCC_CELLS else
+            f"{ps.n}-atom FCC sub-lattice ({cells}^3 cells) of the same workload")
     return {
-        "value": total / avg,
+        "value": res.total / avg,
         "unit": UNIT,
         "cores": threads,
         "kind": "port",
-        "sample": f"{ps.n}-atom FCC sub-lattice ({cells}^3 cells) of the same workload, "
-                  f"{len(times)} timed builds, avg {avg*1e3:.1f} ms (min {min(times)*1e3:.1f}, "
-                  f"max {max(times)*1e3:.1f}); C++/OpenMP restatement of the reference "
-                  "(Kokkos is not installable here), -O3 -ffp-contract=off",
-    }, avg, total, ps.n
+        "sample": f"{what}, {ps.n} atoms, {len(times)} timed builds, avg {avg*1e3:.1f} ms "
+                  f"(min {min(times)*1e3:.1f}, max {max(times)*1e3:.1f}); C++/OpenMP restatement of the "
+                  "reference (Kokkos is not installable here), -O3 "
+                  + ("-march=native " if native else "") + "-ffp-contract=off, dynamic schedule over cells",
+    }, avg, res, ps
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps = max(1, min(args.steps, 5))
-    warmup = max(1, min(args.warmup, 2))
-    cpu, avg, total, n = cpu_reference_run(steps, warmup)
+    # the configuration the GPU arm names, in full (about 5 s per build on 16 cores);
+    # CB_BENCH_REF_CELLS=<cells per side> shrinks it and the line then says so
+    cells = int(os.environ.get("CB_BENCH_REF_CELLS", str(FCC_CELLS)))
+    steps = max(1, min(args.steps, 3))
+    warmup = max(1, min(args.warmup, 1))
+    cpu, avg, res, ps = cpu_reference_run(steps, warmup, cells)
+    cfg = _workload_config(args.gpus)
+    cfg["particles"] = int(ps.n)
+    if cells != FCC_CELLS:
+        cfg["workload"] += f" -- CPU arm ran a {ps.n}-atom sub-lattice ({cells}^3 cells) of it"
+        cfg["same_config"] = False
+    if args.gpus > 1:
+        cfg["workload"] += " (the CPU arm builds the undecomposed box on rank 0's host cores)"
     line = {
         "impl": "reference",
         "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": avg * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": _workload_config(args.gpus),
+        "config": cfg,
+        "neighbors_per_step": float(res.total),
         "cpu_baseline": cpu,
         "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -204,6 +230,46 @@ def _fcc_slab(rank, world):
     xyz = ps.xyz
     xyz[:, 0] += c0 * a
     return xyz, bounds, (FCC_CELLS * a,) * 3
+
+
+def _fcc_first_id(rank, world):
+    """Global index of a slab's first atom (lattice order: x cell slowest)."""
+    cuts = [round(FCC_CELLS * g / world) for g in range(world + 1)]
+    return cuts[rank] * 4 * FCC_CELLS * FCC_CELLS
+
+
+# ----------------------------------------------------------------------------------- parity
+def _lsr(z, k):
+    return (z >> k) & ((1 << (64 - k)) - 1)
+
+
+def _mix64(z):
+    """splitmix64 finaliser on int64 tensors (two's-complement wrap-around == uint64 arithmetic)."""
+    z = z + (-7046029254386353131)            # 0x9e3779b97f4a7c15
+    z = (z ^ _lsr(z, 30)) * (-4658895280553007687)   # 0xbf58476d1ce4e5b9
+    z = (z ^ _lsr(z, 27)) * (-7723592293110705685)   # 0x94d049bb133111eb
+    return z ^ _lsr(z, 31)
+
+
+def _row_hashes_gpu(torch, counts, offsets, neighbors, row0, row1, idmap=None, chunk=1 << 21):
+    """Order-independent 64-bit hash of rows [row0,row1) of a CSR list on the device: sum over the
+    row of mix64(global id).  Chunked so the temporaries stay small."""
+    out = torch.empty(row1 - row0, dtype=torch.int64, device=counts.device)
+    for r0 in range(row0, row1, chunk):
+        r1 = min(r0 + chunk, row1)
+        cnt = counts[r0:r1].to(torch.int64)
+        off = offsets[r0:r1].to(torch.int64)
+        lo = int(off[0])
+        hi = int(off[-1] + cnt[-1])
+        ids = neighbors[lo:hi].to(torch.int64)
+        if idmap is not None:
+            ids = idmap[ids]
+        cs = torch.cumsum(_mix64(ids), 0)
+        cs = torch.cat([torch.zeros(1, dtype=torch.int64, device=cs.device), cs])
+        out[r0 - row0:r1 - row0] = cs[off - lo + cnt] - cs[off - lo]
+    return out
+
+
 
 
 def run_cfg5(args):
@@ -491,48 +557,56 @@ def run_ours(args):
     ms_per_step = elapsed_ms / args.steps
     value = global_total / (ms_per_step * 1e-3)
 
-    # ---- per-kernel roofline for the dominant kernel, rank 0's numbers.  The dominant
-    # kernel is the single test pass (k_verlet_column: every pair tested once, rows written
-    # to the binned temporary, counts produced); the reorder kernel is timed separately.
+    # ---- per-kernel roofline, rank 0's numbers (CUDA events recorded inside the library on the
+    # launching stream around each phase of every timed build).  v2 kernels: fused binning on the
+    # internal pencil grid -> tile plan -> count pass (k_tile_count: tensor-core distance tiles,
+    # hit masks, counts) -> offsets scan -> fill pass (k_tile_fill: rows written once at
+    # offsets[i]).  Algorithmic bytes per particle follow SURVEY.md 8d: bin 32, build 36 + 4 K_s
+    # (count pass: positions 24 + permutation 4 + counts 4; fill pass: offsets 4 + ids 4 K_s).
     peak, peak_kind = _peaks()
-    phases = phase_sum / args.steps  # ms: bin, gather, test pass, scan, reorder, total
+    phases = phase_sum / args.steps  # ms: bin, plan, count pass, scan, fill pass, total
     n_rows = num_local
     k_s = local_total / max(n_rows, 1)
-    # test-pass algorithmic bytes per launch: read positions 24 + ids 4 + cell offsets ~4,
-    # write counts 4 + 4*K_s neighbour ids   (36 + 4 K_s per particle)
-    fill_bytes = n_rows * (36.0 + 4.0 * k_s)
-    fill_gbs = fill_bytes / (phases[2] * 1e-3) / 1e9 if phases[2] > 0 else 0.0
-    # whole step: bin 32 + build 36 + 4 K_s
-    step_bytes = n_rows * (68.0 + 4.0 * k_s)
-    step_gbs = step_bytes / (phases[5] * 1e-3) / 1e9 if phases[5] > 0 else 0.0
-    traffic, other_roofs = None, None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    alg = {"binning": 32.0 * n_rows, "tile_plan": 0.0, "count_pass": 32.0 * n_rows,
+           "offset_scan": 0.0, "fill_pass": n_rows * (4.0 + 4.0 * k_s)}
+    names = ["binning", "tile_plan", "count_pass", "offset_scan", "fill_pass"]
+    kernel_of = {"binning": "k_tbin_count + k_tbin_scatter", "tile_plan": "k_plan_blocks + k_plan_tiles + scans",
+                 "count_pass": "k_tile_count", "offset_scan": "k_exclusive_scan + k_max_and_sum + k_sorted_dst",
+                 "fill_pass": "k_tile_fill"}
+    tj = {}
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
                 tj = json.load(f)
-            traffic = tj.get("k_verlet_column_dram_bytes_per_launch")
-            # SURVEY.md 8d asks for the FP64 roof beside the HBM one: the pair tests run in FP32
-            # (tier 1), only the ambiguous band reaches the exact FP64 tier, so the FP64 pipe is
-            # idle; the unit that actually limits the kernel is L1TEX (ncu, profiles/)
-            other_roofs = {"fp64_pipe_active_pct": tj.get("k_verlet_column_fp64_pipe_active_pct"),
-                           "l1tex_throughput_pct": tj.get("k_verlet_column_l1tex_throughput_pct"),
-                           "issue_active_pct": tj.get("k_verlet_column_issue_active_pct"),
-                           "source": "ncu --set full, profiles/r01_final_ncu_summary.txt"}
         except Exception:
-            traffic = None
+            tj = {}
+    per_kernel = {}
+    for i, nm in enumerate(names):
+        ms_k = float(phases[i])
+        gbs = alg[nm] / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
+        per_kernel[nm] = {"kernels": kernel_of[nm], "ms": ms_k, "algorithmic_bytes": alg[nm],
+                          "achieved_gbs": gbs, "frac": gbs / peak,
+                          "dram_traffic_bytes": (tj.get("dram_bytes_per_launch") or {}).get(nm)}
+    dom = "count_pass" if phases[2] >= phases[4] else "fill_pass"
+    step_bytes = n_rows * (68.0 + 4.0 * k_s)
+    step_gbs = step_bytes / (phases[5] * 1e-3) / 1e9 if phases[5] > 0 else 0.0
     roofline = {
-        "bound": "hbm", "kernel": "k_verlet_column (single test pass; dominant kernel of the step)",
-        "achieved": fill_gbs, "peak": peak, "unit": "GB/s", "frac": fill_gbs / peak,
-        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "traffic": traffic,
-        "algorithmic_bytes_per_launch": fill_bytes,
-        "kernel_ms": float(phases[2]),
-        "other_units": other_roofs,
+        "bound": "hbm",
+        "kernel": f"{kernel_of[dom]} ({dom}: the longest kernel of the step)",
+        "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+        "frac": per_kernel[dom]["frac"],
+        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+        "traffic": per_kernel[dom]["dram_traffic_bytes"],
+        "traffic_source": tj.get("source"),
+        "algorithmic_bytes_per_launch": alg[dom],
+        "kernel_ms": per_kernel[dom]["ms"],
+        "other_units": tj.get("other_units"),
         "step": {"achieved": step_gbs, "frac": step_gbs / peak, "algorithmic_bytes": step_bytes,
-                 "note": "whole build (bin+gather+count+scan+fill) against the HBM roof"},
-        "phase_ms": {"binning": float(phases[0]), "gather_permute": float(phases[1]),
-                     "test_pass": float(phases[2]), "offset_scan": float(phases[3]),
-                     "row_reorder": float(phases[4]), "build_total": float(phases[5])},
+                 "ms": float(phases[5]),
+                 "dram_traffic_bytes": (tj.get("dram_bytes_per_launch") or {}).get("step"),
+                 "note": "whole build (bin + plan + count + scan + fill), N(68 + 4 K_s) bytes, against the HBM roof"},
+        "phases": per_kernel,
     }
 
     # ---- end-to-end: host buffers in, list back to host, copies inside the timed region
@@ -596,28 +670,6 @@ def run_ours(args):
                "api": "per rank: pinned host positions -> device, halo exchange, cb_verlet_build, "
                       "cb_verlet_copy_to_host (pinned); wall clock, max over ranks"}
 
-    # ---- informational: the same build with CB_ROWS_BINNED (rows stay in cell order; no
-    # offsets scan / reorder pass).  NOT the headline: `value` above is the reference layout.
-    binned = None
-    if world == 1 and layout == cb.CSR:
-        lst_b = cb.VerletList(algorithm=algo, layout=layout, row_placement=cb.ROWS_BINNED)
-        for _ in range(max(args.warmup, 2)):
-            lst_b.build(x, 0, num_local, radius, CELL_RATIO, gmin, gmax)
-        torch.cuda.synchronize()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b_steps = max(1, min(args.steps, 10))
-        b0.record()
-        for _ in range(b_steps):
-            lst_b.build(x, 0, num_local, radius, CELL_RATIO, gmin, gmax)
-        b1.record()
-        torch.cuda.synchronize()
-        b_ms = b0.elapsed_time(b1) / b_steps
-        assert lst_b.total == lst.total
-        binned = {"ms_per_step": b_ms, "value": lst_b.total / (b_ms * 1e-3), "unit": UNIT,
-                  "note": "opt-in cb_verlet_set_row_placement(CB_ROWS_BINNED): same neighbour sets, "
-                          "rows left in cell order inside `neighbors` (offsets not monotone)"}
-        del lst_b
-
     # ---- informational: LJ neighbor_parallel_for over the list just built (SURVEY.md 8d
     # "t_traverse"), thread-per-particle and warp-per-particle
     traverse = None
@@ -643,6 +695,51 @@ def run_ours(args):
                               "frac_of_hbm_peak": t_bytes / (t_ms * 1e-3) / 1e9 / peak}
         del f
 
+    # ---- parity, outside the timed region.  N > 1: every rank rebuilds the UNDECOMPOSED box on
+    # its own GPU and compares counts and a hash of every owned row (local ids mapped to global
+    # ids, ghosts through a gid field shipped by the NCCL halo) with its sharded list.
+    parity = None
+    if world > 1 and args.workload == "cfg3" and not args.no_parity_check:
+        local_total = step()            # the list under test: the timed path, once more
+        x_own = cb.Slice(x_all.data, num_local, x_all.outer_stride, x_all.vlen, x_all.comp_stride, 3)
+        halo = slab.create_halo(x_own, num_local)
+        n_tot = halo.numLocal() + halo.numGhost()
+        g0 = _fcc_first_id(rank, world)
+        gid_np = np.full((cap, 1), -1, dtype=np.int32)
+        gid_np[:num_local, 0] = g0 + np.arange(num_local)
+        gid = cb.view_from_array(gid_np)
+        x_chk = cb.slice_from_array(store, vlen=32)
+        comm.gather(halo, cb.Slice(x_chk.data, n_tot, x_chk.outer_stride, x_chk.vlen, x_chk.comp_stride, 3),
+                    cb.Slice(gid.data, n_tot, 1, 1, 1, 1))
+        x_cmp = cb.Slice(x_all.data, n_tot, x_all.outer_stride, x_all.vlen, x_all.comp_stride, 3)
+        x_ref = cb.Slice(x_chk.data, n_tot, x_chk.outer_stride, x_chk.vlen, x_chk.comp_stride, 3)
+        same_ghosts = bool(torch.equal(x_cmp.to_array(), x_ref.to_array()))
+        idmap = gid.data[:n_tot].to(torch.int64)
+        h_loc = _row_hashes_gpu(torch, lst._data.counts, lst._data.offsets, lst._data.neighbors,
+                                0, num_local, idmap)
+        c_loc = lst._data.counts[:num_local].clone()
+        full_xyz = np.concatenate([_fcc_slab(r, world)[0] for r in range(world)])
+        x_full = cb.slice_from_array(full_xyz, vlen=32)
+        lst_full = cb.VerletList(algorithm=algo, layout=layout)
+        lst_full.build(x_full, 0, full_xyz.shape[0], RADIUS, CELL_RATIO, gmin, gmax)
+        h_ref = _row_hashes_gpu(torch, lst_full._data.counts, lst_full._data.offsets,
+                                lst_full._data.neighbors, g0, g0 + num_local)
+        ok = (same_ghosts and bool(torch.equal(c_loc, lst_full._data.counts[g0:g0 + num_local]))
+              and bool(torch.equal(h_loc, h_ref)))
+        flag = torch.tensor([1.0 if ok else 0.0, float(local_total), 0.0], dtype=torch.float64, device="cuda")
+        flag[2] = float(lst_full.total) if rank == 0 else 0.0
+        fmin = flag.clone()
+        dist.all_reduce(fmin, op=dist.ReduceOp.MIN)
+        fsum = flag.clone()
+        dist.all_reduce(fsum, op=dist.ReduceOp.SUM)
+        ok_all = bool(fmin[0] == 1.0) and float(fsum[1]) == float(fsum[2])
+        parity = {"parity_check": "ok" if ok_all else "FAILED",
+                  "against": "the undecomposed 16 078 716-atom build on one GPU (every rank): counts and a "
+                             "64-bit hash of every owned row in global ids; ghost positions of the peer halo "
+                             "bit-equal to the NCCL halo's",
+                  "global_total": float(fsum[1]), "single_gpu_total": float(fsum[2])}
+        del lst_full, x_full, h_ref, h_loc
+
     if world > 1 and os.environ.get("CB_BENCH_TRACE") == "1":
         sys.stderr.write("rank %d trace (ms/step): plan %.3f gather %.3f build %.3f\n" % (
             rank, 1e3 * tr["plan"] / max(tr["n"], 1), 1e3 * tr["gather"] / max(tr["n"], 1),
@@ -654,7 +751,26 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu, _, _, _ = cpu_reference_run(steps=3, warmup=1)
+        cpu, _, res, ps_s = cpu_reference_run(steps=3, warmup=1)
+        if args.workload == "cfg3" and not args.no_parity_check:
+            # N = 1: the oracle's list of the cpu_baseline sample against the CUDA path's list of the
+            # same sample (counts, offsets, a hash of every row); the full-size comparison is
+            # tests/test_gpu_parity.py::test_fcc_16m_matches_oracle
+            import oracle
+            xs_ = cb.slice_from_array(ps_s.xyz, vlen=32)
+            ls_ = cb.VerletList(algorithm=cb.FULL, layout=cb.CSR)
+            ls_.build(xs_, 0, ps_s.n, ps_s.radius, CELL_RATIO, ps_s.grid_min, ps_s.grid_max)
+            c_ = ls_._data.counts.cpu().numpy()
+            o_ = ls_._data.offsets.cpu().numpy()
+            n_ = ls_._data.neighbors[: ls_.total].cpu().numpy()
+            ok = (ls_.total == res.total and np.array_equal(c_, res.counts) and np.array_equal(o_, res.offsets)
+                  and np.array_equal(oracle.row_hashes(oracle.CSR, c_, o_, n_),
+                                     oracle.row_hashes(oracle.CSR, res.counts, res.offsets, res.neighbors)))
+            parity = {"parity_check": "ok" if ok else "FAILED",
+                      "against": f"the CPU oracle on the cpu_baseline sample ({ps_s.n} atoms): counts, offsets "
+                                 "and a 64-bit hash of every row"}
+            del ls_, xs_, n_
+        del res
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -667,8 +783,9 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "e2e": e2e,
-        "binned_rows": binned,
         "lj_traverse": traverse,
+        "parity_check": parity["parity_check"] if parity else None,
+        "parity": parity,
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -704,6 +821,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
                     help="cfg3 (default) is the headline line; the others are the BASELINE.json "
                          "parity configurations, timed for DESIGN.md only (1 GPU)")

@@ -59,10 +59,25 @@ class CudaCommKernels:
         capi.check(capi.lib().cb_comm_unpack(arr, len(fields), C.c_int64(dst_begin), C.c_int64(count),
                                              C.c_void_p(buf.data_ptr()), _stream()))
 
+    _DTYPES = {torch.float64: 0, torch.float32: 1, torch.int32: 2, torch.int64: 3}
+
+    def scatter_dtype(self, field) -> int:
+        """Value types Cabana::scatter can sum (checked BEFORE any communication is posted)."""
+        code = self._DTYPES.get(field.data.dtype)
+        if code is None:
+            raise TypeError(f"scatter: unsupported slice value type {field.data.dtype}")
+        return code
+
     def scatter_add(self, field, steering: torch.Tensor, count: int, buf: torch.Tensor):
         fd = field.field_desc()
-        capi.check(capi.lib().cb_comm_scatter_add(C.byref(fd), C.c_void_p(steering.data_ptr()),
-                                                  C.c_int64(count), C.c_void_p(buf.data_ptr()), _stream()))
+        capi.check(capi.lib().cb_comm_scatter_add_typed(
+            C.byref(fd), C.c_void_p(steering.data_ptr()), C.c_int64(count), C.c_void_p(buf.data_ptr()),
+            C.c_int(self.scatter_dtype(field)), _stream()))
+
+    def pack_range(self, fields, src_begin: int, count: int, out: torch.Tensor):
+        arr = (capi.Field * len(fields))(*[f.field_desc() for f in fields])
+        capi.check(capi.lib().cb_comm_pack_range(arr, len(fields), C.c_int64(src_begin), C.c_int64(count),
+                                                 C.c_void_p(out.data_ptr()), _stream()))
 
     def slab_halo_select(self, x: Slice, num_local, lo_thresh, hi_thresh, lo_rank, hi_rank):
         ranks = torch.empty(2 * max(num_local, 1), dtype=torch.int32, device="cuda")
@@ -292,15 +307,17 @@ def scatter(halo: Halo, field: Slice):
     """Cabana::scatter(halo, slice) (impl/Cabana_Halo_Mpi.hpp:236-350): ghost values are sent
     back to their owners and atomically summed into them."""
     k = halo.kernels
+    k.scatter_dtype(field)             # reject unsupported value types before posting anything
+    es = field.data.element_size()
     nc = field.num_comp
     sends, recvs = {}, {}
-    ghost = field.to_array()  # (n, nc) dense copy of the field, ghosts at the tail
     for r, ne, ni in zip(halo.neighbors, halo.num_export, halo.num_import):
         if ni > 0:
-            b = halo.numLocal() + halo.import_offset[r]
-            sends[r] = ghost[b : b + ni].contiguous().view(torch.uint8).reshape(-1)
+            buf = torch.empty(ni * nc * es, dtype=torch.uint8, device=k.device)
+            k.pack_range([field], halo.numLocal() + halo.import_offset[r], ni, buf)
+            sends[r] = buf
         if ne > 0:
-            recvs[r] = torch.empty(ne * nc * 8, dtype=torch.uint8, device=k.device)
+            recvs[r] = torch.empty(ne * nc * es, dtype=torch.uint8, device=k.device)
     halo.exchange(sends, recvs)
     for r, ne in zip(halo.neighbors, halo.num_export):
         if ne > 0:
@@ -405,13 +422,12 @@ class Scatter(_CommunicationData):
     def apply(self):
         h, k = self.halo, self.halo.kernels
         field = self.fields[0]
+        k.scatter_dtype(field)
         sends = self._blocks(self._send, h.num_import)
         recvs = self._blocks(self._recv, h.num_export)
-        ghost = field.to_array()
         for r, ni in zip(h.neighbors, h.num_import):
             if ni > 0:
-                b = h.numLocal() + h.import_offset[r]
-                sends[r].copy_(ghost[b: b + ni].contiguous().view(torch.uint8).reshape(-1))
+                k.pack_range([field], h.numLocal() + h.import_offset[r], ni, sends[r])
         h.exchange(sends, recvs)
         for r, ne in zip(h.neighbors, h.num_export):
             if ne > 0:

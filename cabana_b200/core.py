@@ -322,14 +322,15 @@ class VerletList:
         self._refresh()
 
     def filter_selftest(self, x: Slice, neighborhood_radius, grid_min, grid_max):
-        """cb_verlet_filter_selftest: (largest |tensor-core filter - exact FP64| seen over every
-        tested pair, the bound the build's decisions assume)."""
+        """cb_verlet_filter_selftest: (largest |tensor-core filter - exact FP64| seen over the tested
+        pairs with s <= 4 r^2, the bound the build's decisions assume, pairs beyond the bound,
+        values outside the exact tier's band with the wrong sign)."""
         d = x.positions_desc()
-        out = (C.c_double * 3)()
+        out = (C.c_double * 4)()
         capi.check(capi.lib().cb_verlet_filter_selftest(
             self._h, C.byref(d), C.c_double(neighborhood_radius), capi.d3(grid_min), capi.d3(grid_max),
             C.c_int(self.algorithm), out, _stream()))
-        return float(out[0]), float(out[1]), int(out[2])
+        return float(out[0]), float(out[1]), int(out[2]), int(out[3])
 
     def copy_to_host(self, counts_h: torch.Tensor, offsets_h: torch.Tensor | None, neighbors_h: torch.Tensor):
         capi.check(capi.lib().cb_verlet_copy_to_host(

@@ -122,7 +122,9 @@ struct FieldSet
     int tuple_bytes;
 };
 
-template <int DIR> // 0 = pack (field -> buffer), 1 = unpack (buffer -> field)
+// DIR 0 = pack by steering (field -> buffer), 1 = unpack into a range (buffer -> field),
+// 2 = pack a contiguous range [dst_begin, dst_begin + count) (field -> buffer)
+template <int DIR>
 __global__ void __launch_bounds__( kBlock )
     k_pack_unpack( FieldSet fs, const unsigned* __restrict__ steering,
                    long long dst_begin, long long count, char* buffer )
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__( kBlock )
           j += (long long)gridDim.x * kBlock )
     {
         const long long elem = DIR == 0 ? (long long)steering[j] : dst_begin + j;
+        constexpr bool kToBuffer = DIR != 1;
         char* tuple = buffer + j * fs.tuple_bytes;
         for ( int k = 0; k < fs.num; ++k )
         {
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__( kBlock )
                     reinterpret_cast<unsigned long long*>( tuple + fs.byte_off[k] );
                 for ( int c = 0; c < f.num_comp; ++c )
                 {
-                    if ( DIR == 0 )
+                    if ( kToBuffer )
                         tb[c] = fb[off + f.comp_stride * c];
                     else
                         fb[off + f.comp_stride * c] = tb[c];
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__( kBlock )
                 unsigned* tb = reinterpret_cast<unsigned*>( tuple + fs.byte_off[k] );
                 for ( int c = 0; c < f.num_comp; ++c )
                 {
-                    if ( DIR == 0 )
+                    if ( kToBuffer )
                         tb[c] = fb[off + f.comp_stride * c];
                     else
                         fb[off + f.comp_stride * c] = tb[c];
@@ -165,11 +168,14 @@ __global__ void __launch_bounds__( kBlock )
     }
 }
 
+// Cabana::scatter sums ghost contributions into their owners for any arithmetic slice value type
+// (impl/Cabana_Halo_Mpi.hpp:334-347, Kokkos::atomic_add on the slice's value_type).
+template <class T>
 __global__ void __launch_bounds__( kBlock )
     k_scatter_add( FieldAccess f, const unsigned* __restrict__ steering, long long count,
-                   const double* __restrict__ recv )
+                   const T* __restrict__ recv )
 {
-    double* fb = reinterpret_cast<double*>( f.base );
+    T* fb = reinterpret_cast<T*>( f.base );
     for ( long long j = (long long)blockIdx.x * kBlock + threadIdx.x; j < count;
           j += (long long)gridDim.x * kBlock )
     {
@@ -518,18 +524,70 @@ extern "C" int cb_comm_unpack( const cb_field* fields, int num_fields, int64_t d
     return CB_OK;
 }
 
+extern "C" int cb_comm_scatter_add_typed( const cb_field* field, const uint32_t* steering,
+                                          int64_t count, const void* recv_buffer, int dtype,
+                                          cb_stream_t stream_ )
+{
+    static const int kBytes[4] = { 8, 4, 4, 8 };
+    if ( !field || dtype < CB_DTYPE_F64 || dtype > CB_DTYPE_I64 || field->vlen < 1 ||
+         field->num_comp < 1 || count < 0 || ( count > 0 && ( !steering || !recv_buffer ) ) )
+        return fail( CB_ERR_INVALID, "cb_comm_scatter_add: bad argument" );
+    if ( field->elem_bytes != kBytes[dtype] )
+        return fail( CB_ERR_INVALID, "cb_comm_scatter_add: element size does not match dtype" );
+    if ( count == 0 )
+        return CB_OK;
+    const int grid = launch_grid_for( count, kBlock );
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const FieldAccess f = make_access( *field );
+    switch ( dtype )
+    {
+    case CB_DTYPE_F64:
+        k_scatter_add<double><<<grid, kBlock, 0, stream>>>( f, steering, count,
+                                                            (const double*)recv_buffer );
+        break;
+    case CB_DTYPE_F32:
+        k_scatter_add<float><<<grid, kBlock, 0, stream>>>( f, steering, count,
+                                                           (const float*)recv_buffer );
+        break;
+    case CB_DTYPE_I32:
+        k_scatter_add<int><<<grid, kBlock, 0, stream>>>( f, steering, count,
+                                                         (const int*)recv_buffer );
+        break;
+    default: // two's complement: the unsigned 64-bit atomic adds signed values correctly
+        k_scatter_add<unsigned long long><<<grid, kBlock, 0, stream>>>(
+            f, steering, count, (const unsigned long long*)recv_buffer );
+        break;
+    }
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
 extern "C" int cb_comm_scatter_add( const cb_field* field, const uint32_t* steering,
                                     int64_t count, const void* recv_buffer,
                                     cb_stream_t stream_ )
 {
-    if ( !field || field->elem_bytes != 8 || field->vlen < 1 || field->num_comp < 1 ||
-         count < 0 || ( count > 0 && ( !steering || !recv_buffer ) ) )
-        return fail( CB_ERR_INVALID, "cb_comm_scatter_add: doubles only" );
+    if ( field && field->elem_bytes != 8 )
+        return fail( CB_ERR_INVALID, "cb_comm_scatter_add: doubles only (use "
+                                     "cb_comm_scatter_add_typed for other value types)" );
+    return cb_comm_scatter_add_typed( field, steering, count, recv_buffer, CB_DTYPE_F64,
+                                      stream_ );
+}
+
+extern "C" int cb_comm_pack_range( const cb_field* fields, int num_fields, int64_t src_begin,
+                                   int64_t count, void* send_buffer, cb_stream_t stream_ )
+{
+    FieldSet fs;
+    CB_TRY( make_field_set( fields, num_fields, fs ) );
+    if ( count < 0 || src_begin < 0 || ( count > 0 && !send_buffer ) )
+        return fail( CB_ERR_INVALID, "cb_comm_pack_range: bad argument" );
+    for ( int k = 0; k < num_fields; ++k )
+        if ( fields[k].n < src_begin + count )
+            return fail( CB_ERR_INVALID, "cb_comm_pack_range: range exceeds the field" );
     if ( count == 0 )
         return CB_OK;
-    k_scatter_add<<<launch_grid_for( count, kBlock ), kBlock, 0,
-                    (cudaStream_t)stream_>>>( make_access( *field ), steering, count,
-                                              (const double*)recv_buffer );
+    k_pack_unpack<2><<<launch_grid_for( count, kBlock ), kBlock, 0,
+                       (cudaStream_t)stream_>>>( fs, nullptr, src_begin, count,
+                                                 (char*)send_buffer );
     CB_CHECK_LAUNCH();
     return CB_OK;
 }

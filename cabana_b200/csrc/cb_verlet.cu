@@ -454,11 +454,13 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
         CB_CUDA( cudaMemcpyAsync( stats_h, v->ctrl.ptr, 32, cudaMemcpyDeviceToHost, stream ) );
         CB_CUDA( cudaStreamSynchronize( stream ) );
         float e;
-        unsigned misses;
+        unsigned misses, flips;
         memcpy( &e, reinterpret_cast<char*>( stats_h ) + 16, 4 );
         memcpy( &misses, reinterpret_cast<char*>( stats_h ) + 20, 4 );
+        memcpy( &flips, reinterpret_cast<char*>( stats_h ) + 24, 4 );
         diag[0] = (double)e;
-        diag[2] = (double)misses; // values whose error exceeded the bound of their staging
+        diag[2] = (double)misses; // pairs with s <= 4 r^2 whose error exceeded the bound
+        diag[3] = (double)flips;  // values outside +-tau with the wrong sign (any distance)
         return CB_OK;
     }
 

@@ -416,17 +416,21 @@ __global__ void __launch_bounds__( 128 )
 // ---------------------------------------------------------------------------------------
 constexpr int kTableTiles = 256; // mma tiles whose source slot is tabulated at a time
 
-// Candidate features, as the B operand reads them: entry e, slot t -> (hi, lo) of
-// x, y, z (t = 0,1,2) and of |x|^2 (t = 3); thread (g,t) of tile j reads ONE 8-byte word
-// at feat[32 j + lane].
+// Candidate features of one piece, in two planes so that both the stores (one float4 per lane
+// and plane: 512 contiguous bytes per instruction) and the B-operand loads are free of bank
+// conflicts:  plane A: entry e -> (x hi, x lo, y hi, y lo);  plane B: (z hi, z lo, |x|^2 hi, lo).
+// Thread (g,t) of mma tile j reads ONE 8-byte word: feature t of entry 8j + g, i.e.
+// plane (t >> 1), float2 index 2 (8j + g) + (t & 1).  Plane B starts 64 bytes past a multiple of
+// 128, so the two planes of a half-warp's words fall into different banks.
+constexpr int kFeatPlaneB = 2 * kPieceEntries + 8;      // float2 index of plane B
+constexpr int kFeatWords = 4 * kPieceEntries + 8;       // float2 words of one feature buffer
 CB_D void store_features( float2* feat, int e, float x, float y, float z )
 {
     const float hx = trunc_tf32( x ), hy = trunc_tf32( y ), hz = trunc_tf32( z );
     const float n = fmaf( z, z, fmaf( y, y, x * x ) );
     const float nh = trunc_tf32( n );
-    float4* f = reinterpret_cast<float4*>( feat + 4 * e );
-    f[0] = make_float4( hx, x - hx, hy, y - hy );
-    f[1] = make_float4( hz, z - hz, nh, n - nh );
+    *reinterpret_cast<float4*>( feat + 2 * e ) = make_float4( hx, x - hx, hy, y - hy );
+    *reinterpret_cast<float4*>( feat + kFeatPlaneB + 2 * e ) = make_float4( hz, z - hz, nh, n - nh );
 }
 
 // Everything a warp keeps about its 16 home particles while it sweeps their candidates.
@@ -499,11 +503,11 @@ CB_D void sweep_segment( const TileArgs& a, HomeTile& H, const float2* feat2, co
                          int seg, int n_filter, float tau, unsigned lane )
 {
     const int t = (int)( lane & 3u );
-    const float2* fp = feat2 + lane;
+    const float2* fp = feat2 + ( t >> 1 ) * kFeatPlaneB + 2 * (int)( lane >> 2 ) + ( t & 1 );
 #pragma unroll 4
     for ( int j = 0; j < seg; ++j )
     {
-        const float2 b = fp[32 * j];
+        const float2 b = fp[16 * j];
         float c1[4], c[4];
         mma_tf32( c1, H.a1[0], H.a1[1], H.a1[2], H.a1[3], b.x, b.y, H.cinit );
         mma_tf32( c, H.a2[0], H.a2[1], H.a2[2], H.a2[3], b.x, b.y, c1 );
@@ -519,7 +523,7 @@ CB_D void sweep_segment( const TileArgs& a, HomeTile& H, const float2* feat2, co
     {
         for ( int j = 0; j < seg; ++j )
         {
-            const float2 b = fp[32 * j];
+            const float2 b = fp[16 * j];
             float c1[4], c[4];
             mma_tf32( c1, H.a1[0], H.a1[1], H.a1[2], H.a1[3], b.x, b.y, H.cinit );
             mma_tf32( c, H.a2[0], H.a2[1], H.a2[2], H.a2[3], b.x, b.y, c1 );
@@ -534,10 +538,18 @@ CB_D void sweep_segment( const TileArgs& a, HomeTile& H, const float2* feat2, co
                     const int cp = cpid[e];
                     if ( hp >= 0 && cp >= 0 )
                     {
-                        const float err = (float)fabs( (double)c[k] - exact_c( a, hp, cp ) );
-                        atomicMax( a.diag_maxerr, __float_as_uint( err ) );
-                        if ( err > tau * 0.5f )
-                            atomicAdd( a.diag_maxerr + 1, 1u );
+                        // The bound is proven for s <= 4 r^2 (c <= 3 r^2); farther pairs only
+                        // need the right sign, and every value outside +-tau must have it.
+                        const double ce = exact_c( a, hp, cp );
+                        const float err = (float)fabs( (double)c[k] - ce );
+                        if ( ce <= 3.0 * a.rsqr )
+                        {
+                            atomicMax( a.diag_maxerr, __float_as_uint( err ) );
+                            if ( err > tau * 0.5f )
+                                atomicAdd( a.diag_maxerr + 1, 1u );
+                        }
+                        if ( fabsf( c[k] ) > tau && ( c[k] < 0.f ) != ( ce <= 0.0 ) )
+                            atomicAdd( a.diag_maxerr + 2, 1u );
                     }
                 }
                 if ( fabsf( c[k] ) <= tau )
@@ -568,7 +580,7 @@ CB_D void sweep_segment( const TileArgs& a, HomeTile& H, const float2* feat2, co
                 if ( seg - 1 - b >= n_filter )
                     continue; // da = +1: a larger cell index means a larger x
                 const int e = kTileCands * ( seg - 1 - b ) + 2 * t + ( k & 1 );
-                const float2 fx = feat2[4 * e];
+                const float2 fx = feat2[2 * e];
                 const float cx = fx.x + fx.y; // == x - Ox exactly
                 bool keep;
                 if ( cx > hx )
@@ -644,7 +656,7 @@ CB_D void flush_chunk( const TileArgs& a, HomeTile& H, int in_chunk, int chunk_i
 // LDG staging: every lane fetches its candidates itself through a per-tile source table.
 struct __align__( 16 ) CountSmemTma
 {
-    float2 feat[kPieceEntries * 4];
+    float2 feat[kFeatWords];
     float4 raw[2][kPieceEntries]; // bulk-copy landing zone (q records), double buffered
     int cpid[kPieceEntries];
     unsigned sp_start[16], sp_len[16], sp_pos[16];
@@ -653,7 +665,7 @@ struct __align__( 16 ) CountSmemTma
 };
 struct __align__( 16 ) CountSmemLdg
 {
-    float2 feat[kPieceEntries * 4];
+    float2 feat[kFeatWords];
     float4 raw[kPieceEntries];   // cp.async landing zone of the NEXT piece
     int cpid[kPieceEntries];     // particle ids of the staged candidates (exact tier)
     unsigned tsrc[kTableTiles];  // sorted slot of the first entry of every mma tile
@@ -1181,10 +1193,10 @@ __global__ void __launch_bounds__( 256 )
     }
 }
 
-int persistent_blocks( const void* func, int smem )
+int persistent_blocks( const void* func, int threads, int smem )
 {
     int nb = 0;
-    if ( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &nb, func, kBlockT, smem ) !=
+    if ( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &nb, func, threads, smem ) !=
              cudaSuccess ||
          nb < 1 )
     {
@@ -1198,13 +1210,14 @@ int persistent_blocks( const void* func, int smem )
 }
 
 template <class K>
-int launch_persistent( K kernel, int smem, const TileArgs& a, cudaStream_t stream )
+int launch_persistent( K kernel, int smem, const TileArgs& a, cudaStream_t stream,
+                       int threads = kBlockT )
 {
     // per device/context: set unconditionally (cheap) rather than caching per process
     CB_CUDA( cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    smem ) );
-    const int blocks = persistent_blocks( (const void*)kernel, smem );
-    kernel<<<blocks, kBlockT, smem, stream>>>( a );
+    const int blocks = persistent_blocks( (const void*)kernel, threads, smem );
+    kernel<<<blocks, threads, smem, stream>>>( a );
     CB_CHECK_LAUNCH();
     return CB_OK;
 }

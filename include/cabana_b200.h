@@ -266,9 +266,11 @@ int cb_verlet_get_phase_times(const cb_verlet* list, double* ms_h);
 
 /* Self-test of the tensor-core distance filter the build relies on (tests only): runs the
  * count pass over `x` with EVERY filter value compared with the exact FP64 arithmetic.
- * out_h[0] = largest |filter - exact| observed, out_h[1] = the proven bound the in/out
- * decisions assume for one tile (values closer than twice the bound to the cutoff go to the
- * exact tier), out_h[2] = number of values whose error exceeded the bound in force. */
+ * out_h[0] = largest |filter - exact| observed over pairs with s <= 4 r^2 (the range the bound
+ * is proven for), out_h[1] = the proven bound the in/out decisions assume for one tile (values
+ * closer than twice the bound to the cutoff go to the exact tier), out_h[2] = number of such
+ * pairs whose error exceeded the bound, out_h[3] = number of values at ANY distance that lie
+ * outside the exact tier's band and have the wrong sign (must be 0). out_h holds 4 doubles. */
 int cb_verlet_filter_selftest(cb_verlet* list, const cb_positions* x,
                               double neighborhood_radius, const double* grid_min_h,
                               const double* grid_max_h, int algorithm, double* out_h,
@@ -382,6 +384,16 @@ int cb_comm_unpack(const cb_field* fields_h, int num_fields, int64_t dst_begin,
 /* scatter: field(steering[j]) += recv_buffer[j]  (atomic add; doubles only) */
 int cb_comm_scatter_add(const cb_field* field_h, const uint32_t* steering,
                         int64_t count, const void* recv_buffer, cb_stream_t stream);
+/* The same for every arithmetic slice value type Cabana::scatter accepts
+ * (impl/Cabana_Halo_Mpi.hpp:334-347): recv_buffer holds count*num_comp values of `dtype`. */
+enum { CB_DTYPE_F64 = 0, CB_DTYPE_F32 = 1, CB_DTYPE_I32 = 2, CB_DTYPE_I64 = 3 };
+int cb_comm_scatter_add_typed(const cb_field* field_h, const uint32_t* steering,
+                              int64_t count, const void* recv_buffer, int dtype,
+                              cb_stream_t stream);
+/* send_buffer tuple j = fields(src_begin + j): packs a contiguous range, e.g. the ghost block
+ * a scatter sends home (impl/Cabana_Halo_Mpi.hpp:269-300) */
+int cb_comm_pack_range(const cb_field* fields_h, int num_fields, int64_t src_begin,
+                       int64_t count, void* send_buffer, cb_stream_t stream);
 /* bytes of one packed tuple */
 int64_t cb_comm_tuple_bytes(const cb_field* fields_h, int num_fields);
 

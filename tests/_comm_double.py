@@ -19,6 +19,10 @@ class CpuSlice:
         self.n = t.shape[0]
         self.num_comp = t.shape[1]
 
+    @property
+    def data(self):
+        return self.t
+
     def size(self):
         return self.n
 
@@ -57,9 +61,18 @@ class CpuCommKernels:
             f.t[dst_begin : dst_begin + count] = rows[:, at : at + w].contiguous().view(f.t.dtype).reshape(count, f.num_comp)
             at += w
 
+    def scatter_dtype(self, field):
+        if field.t.dtype not in (torch.float64, torch.float32, torch.int32, torch.int64):
+            raise TypeError(f"scatter: unsupported slice value type {field.t.dtype}")
+        return 0
+
     def scatter_add(self, field, steering, count, buf):
-        vals = buf.view(torch.float64).reshape(count, field.num_comp)
+        vals = buf.view(field.t.dtype).reshape(count, field.num_comp)
         field.t.index_add_(0, steering.long(), vals)
+
+    def pack_range(self, fields, src_begin, count, out):
+        cols = [f.t[src_begin:src_begin + count].contiguous().view(torch.uint8).reshape(count, -1) for f in fields]
+        out.copy_(torch.cat(cols, dim=1).reshape(-1))
 
     def slab_halo_select(self, x, num_local, lo_thresh, hi_thresh, lo_rank, hi_rank):
         px = x.t[:num_local, 0]

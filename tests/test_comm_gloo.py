@@ -140,6 +140,19 @@ def _case_slab_halo(rank, world):
     assert sc.sendSize() == halo.totalNumImport() and sc.receiveSize() == halo.totalNumExport()
     sc.apply()
     assert np.array_equal(f2[:num_local, 0].numpy(), expect)
+    # every arithmetic value type scatters (buffers sized by the element size); an unsupported
+    # one is rejected BEFORE any message is posted (mismatched send/recv sizes)
+    for dt in (torch.float32, torch.int32, torch.int64):
+        ft = torch.zeros((num_local + 2000, 2), dtype=dt)
+        ft[num_local:n_tot] = 1 + rank
+        comm.scatter(halo, CpuSlice(ft))
+        assert np.array_equal(ft[:num_local, 1].numpy().astype(np.float64), expect)
+        ft2 = torch.zeros((num_local + 2000, 2), dtype=dt)
+        ft2[num_local:n_tot] = 1 + rank
+        comm.createScatter(halo, CpuSlice(ft2)).apply()
+        assert torch.equal(ft2, ft)
+    with pytest.raises(TypeError):
+        comm.scatter(halo, CpuSlice(torch.zeros((num_local + 2000, 1), dtype=torch.int16)))
 
 
 def _case_migrate(rank, world):

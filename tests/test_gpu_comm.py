@@ -84,6 +84,24 @@ def test_pack_unpack_scatter(mods, layout):
     exp = np.zeros((n, 3))
     np.add.at(exp, st, contrib)
     assert np.allclose(f.to_array().cpu().numpy(), exp, rtol=1e-13, atol=1e-13)
+    # the other value types Cabana::scatter sums (typed atomic adds) and pack_range
+    for dt, tol in ((np.float32, 1e-5), (np.int32, 0), (np.int64, 0)):
+        ft = mk(np.zeros((n, 2), dtype=dt))
+        if dt == np.float32:
+            ct = rng.random((777, 2)).astype(dt)
+        else:
+            ct = rng.integers(-1000, 1000, (777, 2)).astype(dt)
+        k.scatter_add(ft, steering, 777, torch.from_numpy(ct).cuda().view(torch.uint8).reshape(-1))
+        et = np.zeros((n, 2), dtype=np.float64)
+        np.add.at(et, st, ct.astype(np.float64))
+        assert np.allclose(ft.to_array().cpu().numpy().astype(np.float64), et, rtol=tol, atol=tol)
+    buf2 = torch.zeros(300 * tb, dtype=torch.uint8, device="cuda")
+    k.pack_range([fx, fi, fv], 1234, 300, buf2)
+    raw2 = buf2.cpu().numpy().reshape(300, tb)
+    assert np.array_equal(raw2[:, :24].copy().view(np.float64).reshape(300, 3), x[1234:1534])
+    assert np.array_equal(raw2[:, 24:28].copy().view(np.int32)[:, 0], ident[1234:1534, 0])
+    with pytest.raises(TypeError):
+        k.scatter_dtype(mk(np.zeros((4, 1), dtype=np.int16)))
 
 
 def test_slab_select_and_destinations(mods):

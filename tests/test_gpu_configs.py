@@ -95,3 +95,12 @@ def test_cfg4_8m_clustered_properties(cb):
     torch.cuda.empty_cache()
     half = cb.VerletList(x, 0, ps.n, ps.radius, 1.0, ps.grid_min, ps.grid_max, algorithm=cb.HALF)
     assert 2 * half.total == total_full
+
+
+def test_cfg4_8m_clustered_matches_oracle(orc, cb):
+    """cfg4 at its full 8 M particles against the oracle: counts, offsets and a hash of every
+    row."""
+    from _parity_helpers import full_size_oracle_compare as _full_size_oracle_compare
+
+    ps = datasets.clustered(8_000_000)
+    _full_size_oracle_compare(orc, cb, ps, cb.FULL, orc.FULL)

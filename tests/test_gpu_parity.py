@@ -8,6 +8,7 @@ import pytest
 import torch
 
 from cabana_b200 import datasets
+from _parity_helpers import full_size_oracle_compare as _full_size_oracle_compare
 
 pytestmark = pytest.mark.gpu
 
@@ -379,6 +380,16 @@ def test_fcc_16m_properties(cb):
     half = cb.VerletList(x, 0, ps.n, ps.radius, 1.0, ps.grid_min, ps.grid_max,
                          algorithm=cb.HALF, layout=cb.CSR)
     assert 2 * half.total == total_full
+
+
+@pytest.mark.parametrize("algo", ["full", "half"])
+def test_fcc_16m_matches_oracle(orc, cb, algo):
+    """BASELINE config 3 (the headline configuration) at its full 16 078 716 atoms, compared
+    with the oracle row by row."""
+    ps = datasets.fcc_lattice(159)
+    assert ps.n == 16_078_716
+    _full_size_oracle_compare(orc, cb, ps, cb.FULL if algo == "full" else cb.HALF,
+                              orc.FULL if algo == "full" else orc.HALF)
 
 
 # ------------------------------------------------------------- CB_ROWS_BINNED (opt-in placement)
