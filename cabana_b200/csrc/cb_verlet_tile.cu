@@ -498,7 +498,7 @@ CB_D void load_home_operands( HomeTile& H, float* scr, float xh, float yh, float
 // s - r^2 goes into the hit words (tile j ends up at bit seg-1-j), min |c| into H.ma; then
 // the exact tier for values inside the error band, and the x-major half criterion for the
 // first n_filter tiles (those of the home x column).  cpid: particle ids of the same entries.
-template <bool HALF, bool DIAG>
+template <bool HALF, bool DIAG, int CSTRIDE>
 CB_D void sweep_segment( const TileArgs& a, HomeTile& H, const float2* feat2, const int* cpid,
                          int seg, int n_filter, float tau, unsigned lane )
 {
@@ -535,7 +535,7 @@ CB_D void sweep_segment( const TileArgs& a, HomeTile& H, const float2* feat2, co
                 const int hp = k < 2 ? H.pid_g : H.pid_g8;
                 if ( DIAG )
                 {
-                    const int cp = cpid[e];
+                    const int cp = cpid[CSTRIDE * e];
                     if ( hp >= 0 && cp >= 0 )
                     {
                         // The bound is proven for s <= 4 r^2 (c <= 3 r^2); farther pairs only
@@ -554,7 +554,7 @@ CB_D void sweep_segment( const TileArgs& a, HomeTile& H, const float2* feat2, co
                 }
                 if ( fabsf( c[k] ) <= tau )
                 {
-                    const bool hit = exact_decide<HALF>( a, hp, cpid[e] );
+                    const bool hit = exact_decide<HALF>( a, hp, cpid[CSTRIDE * e] );
                     unsigned& m = k == 0 ? H.m0 : ( k == 1 ? H.m1 : ( k == 2 ? H.m2 : H.m3 ) );
                     m = hit ? ( m | bit ) : ( m & ~bit );
                 }
@@ -588,7 +588,7 @@ CB_D void sweep_segment( const TileArgs& a, HomeTile& H, const float2* feat2, co
                 else if ( cx < hx )
                     keep = false;
                 else
-                    keep = exact_decide<HALF>( a, hp, cpid[e] );
+                    keep = exact_decide<HALF>( a, hp, cpid[CSTRIDE * e] );
                 if ( !keep )
                     m &= ~( 1u << b );
             }
@@ -656,20 +656,18 @@ CB_D void flush_chunk( const TileArgs& a, HomeTile& H, int in_chunk, int chunk_i
 // LDG staging: every lane fetches its candidates itself through a per-tile source table.
 struct __align__( 16 ) CountSmemTma
 {
-    float2 feat[kFeatWords];
-    float4 raw[2][kPieceEntries]; // bulk-copy landing zone (q records), double buffered
-    int cpid[kPieceEntries];
+    float2 feat[kFeatWords];      // (also the scratch of load_home_operands between tiles)
+    float4 raw[2][kPieceEntries]; // bulk-copy landing zone (q records), double buffered; the
+                                  // records' w words are the particle ids the exact tier reads
     unsigned sp_start[16], sp_len[16], sp_pos[16];
-    float scr[288];
     unsigned long long mbar[2];
 };
 struct __align__( 16 ) CountSmemLdg
 {
-    float2 feat[kFeatWords];
+    float2 feat[kFeatWords];     // (also the scratch of load_home_operands between tiles)
     float4 raw[kPieceEntries];   // cp.async landing zone of the NEXT piece
     int cpid[kPieceEntries];     // particle ids of the staged candidates (exact tier)
     unsigned tsrc[kTableTiles];  // sorted slot of the first entry of every mma tile
-    float scr[288];
 };
 
 // Stage piece `pc` (candidate list entries [128 pc, 128 pc + 128)) into raw[buf]: every
@@ -788,7 +786,7 @@ __global__ void __launch_bounds__( kBlockT, 3 )
         if ( lane < 9u )
             sp = a.spans[(size_t)tile * 9u + lane];
         HomeTile H;
-        load_home_operands( H, S.scr, hq.x - Ox, hq.y - Oy, hq.z - Oz, pid, actmask, a.r2hi,
+        load_home_operands( H, reinterpret_cast<float*>( S.feat ), hq.x - Ox, hq.y - Oy, hq.z - Oz, pid, actmask, a.r2hi,
                             a.r2lo, lane );
         const int my_nt = (int)( sp.y / kTileCands );
         int incl = my_nt;
@@ -872,7 +870,8 @@ __global__ void __launch_bounds__( kBlockT, 3 )
             {
                 const int e = (int)lane + 32 * j;
                 store_features( S.feat, e, r[j].x - Ox, r[j].y - Oy, r[j].z - Oz );
-                S.cpid[e] = __float_as_int( r[j].w );
+                if constexpr ( !TMA )
+                    S.cpid[e] = __float_as_int( r[j].w );
             }
             __syncwarp();
             if constexpr ( !TMA )
@@ -889,8 +888,13 @@ __global__ void __launch_bounds__( kBlockT, 3 )
                 }
             }
             const int nt_p = min( kPieceTiles, T - pc * kPieceTiles );
-            sweep_segment<HALF, DIAG>( a, H, S.feat, S.cpid, nt_p,
-                                       min( max( T0 - pc * kPieceTiles, 0 ), nt_p ), a.tau, lane );
+            const int n_filter = min( max( T0 - pc * kPieceTiles, 0 ), nt_p );
+            if constexpr ( TMA )
+                sweep_segment<HALF, DIAG, 4>( a, H, S.feat,
+                                              reinterpret_cast<const int*>( &S.raw[buf][0] ) + 3,
+                                              nt_p, n_filter, a.tau, lane );
+            else
+                sweep_segment<HALF, DIAG, 1>( a, H, S.feat, S.cpid, nt_p, n_filter, a.tau, lane );
             in_chunk += nt_p;
             if ( in_chunk == kChunkTiles || pc == npieces - 1 )
             {
@@ -1378,11 +1382,12 @@ int tile_plan( const TileGrid& tg, const unsigned* cell_off, bool half, int* blo
     return CB_OK;
 }
 
-// CB_TILE_STAGING = async (default: per-lane cp.async prefetch) | tma (cp.async.bulk spans).
+// CB_TILE_STAGING = tma (default: cp.async.bulk of every contiguous candidate span, mbarrier
+// completion, double buffered) | async (per-lane cp.async gather through a tile table).
 static bool use_tma_staging()
 {
     const char* e = getenv( "CB_TILE_STAGING" );
-    return e && strcmp( e, "tma" ) == 0;
+    return !( e && strcmp( e, "async" ) == 0 );
 }
 
 template <bool DIAG>
