@@ -306,6 +306,21 @@ class VerletList:
             C.c_int(self.algorithm), C.c_int(self.layout), C.c_int(self.build_tag), _stream()))
         self._refresh()
 
+    def build_radii(self, x: Slice, begin, end, background_radius, neighborhood_radius: Slice,
+                    cell_size_ratio, grid_min, grid_max, max_neigh=0):
+        """VerletList( x, begin, end, background_radius, neighborhood_radius (slice/view, one double
+        per particle), cell_size_ratio, grid_min, grid_max, max_neigh ) -- the per-particle cutoff
+        constructor (core/src/Cabana_VerletList.hpp:989-1017)."""
+        b = 0 if begin is None else int(begin)
+        e = x.size() if end is None else int(end)
+        d = x.positions_desc()
+        rd = neighborhood_radius.field_desc()
+        capi.check(capi.lib().cb_verlet_build_radii(
+            self._h, C.byref(d), C.byref(rd), C.c_int64(b), C.c_int64(e), C.c_double(background_radius),
+            C.c_double(cell_size_ratio), capi.d3(grid_min), capi.d3(grid_max), C.c_int64(max_neigh),
+            C.c_int(self.algorithm), C.c_int(self.layout), C.c_int(self.build_tag), _stream()))
+        self._refresh()
+
     def build_host(self, x_host, begin, end, neighborhood_radius, cell_size_ratio, grid_min, grid_max,
                    max_neigh=0):
         """End-to-end entry: positions in HOST memory (numpy / pinned torch CPU tensor, (n,3))."""

@@ -208,6 +208,176 @@ __global__ void __launch_bounds__( kBlock ) k_verlet_pass( const VerletArgs a )
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Per-particle cutoff radius (Cabana_VerletList.hpp:181-203, :244-305).  The linked cells and
+// the stencil come from the background radius; the cell prune (:401-403) and the pair test
+// (:254) use radius(i) of the particle whose row is built; a pair with dist_sqr >=
+// radius(j)^2 will not be found from j's side, so i is appended to j's row as well (:299-304).
+// Rows are the reference's FILL semantics and counts/offsets describe exactly those rows
+// (the reference's count pass books the extra entry on the wrong row, SURVEY.md Appendix B.6;
+// its own test checks the post-fill counts: 6 / 4 in tstNeighborList.hpp:244-252).
+// Reference-shaped kernel (warp per particle, exact FP64, count then fill): this is a
+// widening row, not the hot path of the benchmark.
+// ---------------------------------------------------------------------------------------
+struct RadiiArgs
+{
+    VerletArgs v;
+    FieldAccess radii;
+    int* cursor; // fill position of every row (atomic)
+};
+
+CB_D double radius_sq( const FieldAccess& r, long long i )
+{
+    const double v = reinterpret_cast<const double*>( r.base )[r.offset( i )];
+    return CB_MUL( v, v );
+}
+
+template <int MODE, bool HALF, bool CSR>
+__global__ void __launch_bounds__( kBlock ) k_verlet_radii_pass( const RadiiArgs ra )
+{
+    const VerletArgs& a = ra.v;
+    const unsigned lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    const long long warp = ( (long long)blockIdx.x * kBlock + threadIdx.x ) >> 5;
+    const long long nwarps = ( (long long)gridDim.x * kBlock ) >> 5;
+    const int R = a.cell_range;
+
+    for ( long long s = warp; s < a.n; s += nwarps )
+    {
+        const long long pid = (long long)a.ids[s];
+        if ( pid < a.begin || pid >= a.end )
+            continue;
+        const double xp = a.xs[s], yp = a.ys[s], zp = a.zs[s];
+        const double ri2 = radius_sq( ra.radii, pid );
+        int ci = locate_1d( a.g, 0, xp );
+        int cj = locate_1d( a.g, 1, yp );
+        int ck = locate_1d( a.g, 2, zp );
+        ci = min( max( ci, 0 ), a.g.nx[0] - 1 );
+        cj = min( max( cj, 0 ), a.g.nx[1] - 1 );
+        ck = min( max( ck, 0 ), a.g.nx[2] - 1 );
+        const int imin = HALF ? ci : max( ci - R, 0 );
+        const int imax = min( ci + R + 1, a.g.nx[0] );
+        const int jmin = max( cj - R, 0 );
+        const int jmax = min( cj + R + 1, a.g.nx[1] );
+        const int kmin = max( ck - R, 0 );
+        const int kmax = min( ck + R + 1, a.g.nx[2] );
+        const int nj = jmax - jmin;
+        const int nrow = ( imax - imin ) * nj;
+        const long long row_base = CSR ? ( MODE == kFill ? (long long)a.offsets[pid] : 0 )
+                                       : pid * a.width;
+        int total = 0;
+
+        for ( int rb = 0; rb < nrow; rb += 32 )
+        {
+            const int r = rb + (int)lane;
+            unsigned st = 0, en = 0;
+            if ( r < nrow )
+            {
+                const int ia = imin + r / nj;
+                const int jb = jmin + r % nj;
+                const double sxy = CB_ADD( min_dist_1d_sq( a.g, 0, xp, ia ),
+                                           min_dist_1d_sq( a.g, 1, yp, jb ) );
+                int k0 = -1, k1 = -1;
+                for ( int k = kmin; k < kmax; ++k )
+                {
+                    const double sq = CB_ADD( sxy, min_dist_1d_sq( a.g, 2, zp, k ) );
+                    if ( sq <= ri2 ) // withinCutoff( pid, minDistanceToPoint ) :401-403
+                    {
+                        if ( k0 < 0 )
+                            k0 = k;
+                        k1 = k;
+                    }
+                }
+                if ( k0 >= 0 )
+                {
+                    const int c0 = cardinal_index( a.g, ia, jb, k0 );
+                    st = a.cell_off[c0];
+                    en = a.cell_off[c0 + ( k1 - k0 ) + 1];
+                }
+            }
+            unsigned live = __ballot_sync( kFullMask, en > st );
+            while ( live )
+            {
+                const int rr = __ffs( live ) - 1;
+                live &= live - 1;
+                const unsigned rst = __shfl_sync( kFullMask, st, rr );
+                const unsigned ren = __shfl_sync( kFullMask, en, rr );
+                for ( unsigned j0 = rst; j0 < ren; j0 += 32 )
+                {
+                    const unsigned j = j0 + lane;
+                    bool hit = false, extra = false;
+                    int nid = -1;
+                    if ( j < ren )
+                    {
+                        const double xn = a.xs[j], yn = a.ys[j], zn = a.zs[j];
+                        nid = (int)a.ids[j];
+                        bool ok = ( (long long)j != s );
+                        if ( HALF )
+                            ok = ok && half_criterion( xp, yp, zp, xn, yn, zn );
+                        const double d2 = pair_dist_sq( xp, yp, zp, xn, yn, zn );
+                        hit = ok && ( d2 <= ri2 );                                 // :299
+                        extra = hit && ( d2 >= radius_sq( ra.radii, nid ) );       // :268
+                    }
+                    const unsigned m = __ballot_sync( kFullMask, hit );
+                    if ( MODE == kCount )
+                    {
+                        if ( extra )
+                            atomicAdd( a.counts + nid, 1 ); // the row the fill appends to (:304)
+                    }
+                    else
+                    {
+                        int base = 0;
+                        if ( m != 0u && lane == (unsigned)( __ffs( m ) - 1 ) )
+                            base = atomicAdd( ra.cursor + pid, __popc( m ) );
+                        base = __shfl_sync( kFullMask, base, m ? __ffs( m ) - 1 : 0 );
+                        if ( hit )
+                        {
+                            const int pos = base + __popc( m & lt );
+                            if ( CSR || pos < a.width )
+                                a.neighbors[row_base + pos] = nid;
+                        }
+                        if ( extra )
+                        {
+                            const int pos = atomicAdd( ra.cursor + nid, 1 );
+                            const long long nb = CSR ? (long long)a.offsets[nid]
+                                                     : (long long)nid * a.width;
+                            if ( CSR || pos < a.width )
+                                a.neighbors[nb + pos] = (int)pid;
+                        }
+                    }
+                    total += __popc( m );
+                }
+            }
+        }
+        if ( MODE == kCount && lane == 0 && total > 0 )
+            atomicAdd( a.counts + pid, total );
+    }
+}
+
+template <int MODE>
+int launch_radii_pass( const RadiiArgs& a, int algorithm, int layout, cudaStream_t stream )
+{
+    if ( a.v.n == 0 )
+        return CB_OK;
+    long long blocks = ( a.v.n * 32 + kBlock - 1 ) / kBlock;
+    const long long cap = (long long)kNumSMs * 64;
+    if ( blocks > cap )
+        blocks = cap;
+    const int grid = (int)blocks;
+    const bool half = algorithm == CB_NEIGHBOR_HALF;
+    const bool csr = layout == CB_LAYOUT_CSR;
+    if ( half && csr )
+        k_verlet_radii_pass<MODE, true, true><<<grid, kBlock, 0, stream>>>( a );
+    else if ( half )
+        k_verlet_radii_pass<MODE, true, false><<<grid, kBlock, 0, stream>>>( a );
+    else if ( csr )
+        k_verlet_radii_pass<MODE, false, true><<<grid, kBlock, 0, stream>>>( a );
+    else
+        k_verlet_radii_pass<MODE, false, false><<<grid, kBlock, 0, stream>>>( a );
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+}
+
 __global__ void k_set_neighbor( int* neighbors, const int* offsets, long long i,
                                 long long k, long long width, int value )
 {
@@ -268,6 +438,7 @@ struct cb_verlet
     // v2 (tile) workspace
     DeviceBuffer block_tiles, tile_base, recs, spans, tile_chunks, chunk_off, masks, cellslot,
         pads, tau_tab, cnt_sorted, dst_sorted;
+    DeviceBuffer row_cursor; // per-row fill positions (per-particle radius build)
     DeviceBuffer host_stage; // device copy of host positions (build_host)
     PinnedScalars pinned;
     // optional phase timing
@@ -966,6 +1137,145 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
         }
         v->mark( 5, stream );
     }
+    v->built = true;
+    return CB_OK;
+}
+
+extern "C" int cb_verlet_build_radii( cb_verlet* v, const cb_positions* x,
+                                      const cb_field* radii, int64_t begin, int64_t end,
+                                      double background_radius, double cell_size_ratio,
+                                      const double* grid_min, const double* grid_max,
+                                      int64_t max_neigh, int algorithm, int layout,
+                                      int build_op, cb_stream_t stream_ )
+{
+    if ( !v || !x || !radii || !grid_min || !grid_max )
+        return fail( CB_ERR_INVALID, "cb_verlet_build_radii: null argument" );
+    if ( begin < 0 || end < begin || end > x->n )
+        return fail( CB_ERR_INVALID, "cb_verlet_build_radii: bad particle range" );
+    if ( !( background_radius > 0.0 ) || !( cell_size_ratio > 0.0 ) || x->vlen < 1 ||
+         max_neigh < 0 )
+        return fail( CB_ERR_INVALID, "cb_verlet_build_radii: bad argument" );
+    // assert( size( positions ) == size( neighborhood_radius ) ) (:194)
+    if ( radii->n != x->n || radii->elem_bytes != 8 || radii->num_comp != 1 || radii->vlen < 1 )
+        return fail( CB_ERR_INVALID,
+                     "cb_verlet_build_radii: radii must be one double per particle" );
+    if ( ( algorithm != CB_NEIGHBOR_FULL && algorithm != CB_NEIGHBOR_HALF ) ||
+         ( layout != CB_LAYOUT_CSR && layout != CB_LAYOUT_2D ) ||
+         ( build_op != CB_OP_TEAM && build_op != CB_OP_TEAM_VECTOR ) )
+        return fail( CB_ERR_INVALID, "cb_verlet_build_radii: bad tag" );
+    if ( x->n >= 2147483647ll )
+        return fail( CB_ERR_UNSUPPORTED, "cb_verlet_build_radii: ids are 32-bit int" );
+    for ( int d = 0; d < 3; ++d )
+        if ( !( grid_max[d] > grid_min[d] ) )
+            return fail( CB_ERR_INVALID, "cb_verlet_build_radii: grid_max <= grid_min" );
+
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long n = x->n;
+    const size_t na = (size_t)( n > 0 ? n : 1 );
+    const double grid_size = cell_size_ratio * background_radius; // :224
+    const double delta[3] = { grid_size, grid_size, grid_size };
+    cb_grid grid;
+    cb_grid_init( &grid, grid_min, grid_max, delta );
+    const long long ncell = (long long)grid.nx[0] * grid.nx[1] * grid.nx[2];
+    if ( grid.nx[0] <= 0 || grid.nx[1] <= 0 || grid.nx[2] <= 0 || ncell >= 2147483647ll )
+        return fail( CB_ERR_INVALID, "cb_verlet_build_radii: cell count out of int range" );
+
+    CB_TRY( v->pinned.ensure() );
+    CB_TRY( v->stats.ensure( 4 * sizeof( long long ) ) );
+    CB_TRY( v->counts.ensure( sizeof( int ) * na, 1.1 ) );
+    CB_TRY( v->row_cursor.ensure( sizeof( int ) * na, 1.1 ) );
+    CB_TRY( v->cell_counts.ensure( sizeof( int ) * (size_t)ncell ) );
+    CB_TRY( v->cell_off.ensure( sizeof( unsigned ) * (size_t)( ncell + 1 ) ) );
+    CB_TRY( v->permute.ensure( sizeof( unsigned ) * na, 1.1 ) );
+    CB_TRY( v->cell_of.ensure( sizeof( int ) * na, 1.1 ) );
+    CB_TRY( v->xs.ensure( sizeof( double ) * na, 1.1 ) );
+    CB_TRY( v->ys.ensure( sizeof( double ) * na, 1.1 ) );
+    CB_TRY( v->zs.ensure( sizeof( double ) * na, 1.1 ) );
+    v->built = false;
+    v->layout = layout;
+    v->algorithm = algorithm;
+    v->n = n;
+    v->total = v->max_n = v->width = 0;
+    v->refilled = 0;
+    for ( auto& f : v->ev_valid )
+        f = false;
+
+    CB_CUDA( cudaMemsetAsync( v->counts.ptr, 0, sizeof( int ) * na, stream ) );
+    CB_CUDA( cudaMemsetAsync( v->row_cursor.ptr, 0, sizeof( int ) * na, stream ) );
+    CB_TRY( bin_particles( grid, *x, 0, n, v->cell_counts.as<int>(), v->cell_off.as<unsigned>(),
+                           v->permute.as<unsigned>(), v->cell_of.as<int>(), v->rank, v->scan,
+                           stream, 1 ) );
+    if ( n > 0 )
+    {
+        k_gather_sorted<<<launch_grid_for( n, kBlock ), kBlock, 0, stream>>>(
+            make_access( *x ), n, v->permute.as<unsigned>(), v->xs.as<double>(),
+            v->ys.as<double>(), v->zs.as<double>(), nullptr, grid.min[0], grid.min[1],
+            grid.min[2] );
+        CB_CHECK_LAUNCH();
+    }
+    RadiiArgs ra;
+    VerletArgs& a = ra.v;
+    a.xs = v->xs.as<double>();
+    a.ys = v->ys.as<double>();
+    a.zs = v->zs.as<double>();
+    a.ids = v->permute.as<unsigned>();
+    a.cell_off = v->cell_off.as<unsigned>();
+    a.g = to_grid( grid );
+    a.cell_range = cb_stencil_cell_range( cell_size_ratio );
+    a.rsqr = background_radius * background_radius;
+    a.n = n;
+    a.begin = begin;
+    a.end = end;
+    a.counts = v->counts.as<int>();
+    a.offsets = nullptr;
+    a.neighbors = nullptr;
+    a.width = 0;
+    ra.radii = make_access( *radii );
+    ra.cursor = v->row_cursor.as<int>();
+
+    CB_TRY( launch_radii_pass<kCount>( ra, algorithm, layout, stream ) );
+    long long* stats_dev = v->stats.as<long long>();
+    long long* stats_h = v->pinned.ptr;
+    CB_TRY( max_and_sum_i32( v->counts.as<int>(), n, stats_dev, stream ) );
+    if ( layout == CB_LAYOUT_CSR )
+    {
+        CB_TRY( v->offsets.ensure( sizeof( int ) * ( na + 1 ), 1.1 ) );
+        CB_TRY( exclusive_scan_i32( v->counts.as<int>(), v->offsets.as<int>(), n, false, nullptr,
+                                    v->scan, stream ) );
+    }
+    CB_CUDA( cudaMemcpyAsync( stats_h, stats_dev, 2 * sizeof( long long ), cudaMemcpyDeviceToHost,
+                              stream ) );
+    CB_CUDA( cudaStreamSynchronize( stream ) );
+    v->max_n = stats_h[0];
+    v->total = stats_h[1];
+    v->extent = v->total;
+    if ( layout == CB_LAYOUT_CSR )
+    {
+        if ( v->total > 2147483647ll )
+            return fail( CB_ERR_OVERFLOW, "cb_verlet_build_radii: total neighbours exceed INT_MAX" );
+        CB_TRY( v->neighbors.ensure( sizeof( int ) * (size_t)( v->total > 0 ? v->total : 1 ),
+                                     1.05 ) );
+        a.offsets = v->offsets.as<int>();
+    }
+    else
+    {
+        if ( max_neigh > 0 && v->max_n <= max_neigh )
+            v->width = max_neigh;
+        else
+        {
+            v->width = v->max_n;
+            if ( max_neigh > 0 )
+                v->refilled = 1;
+        }
+        if ( (double)na * (double)v->width > 9.0e18 )
+            return fail( CB_ERR_OVERFLOW, "cb_verlet_build_radii: 2D list too large" );
+        CB_TRY( v->neighbors.ensure( sizeof( int ) * na *
+                                     (size_t)( v->width > 0 ? v->width : 1 ) ) );
+        a.width = v->width;
+    }
+    a.neighbors = v->neighbors.as<int>();
+    if ( v->total > 0 )
+        CB_TRY( launch_radii_pass<kFill>( ra, algorithm, layout, stream ) );
     v->built = true;
     return CB_OK;
 }

@@ -36,6 +36,7 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "cabana_b200.h"
@@ -61,6 +62,26 @@ struct DeviceSpace
     using size_type = unsigned int; // Kokkos::CudaSpace::size_type
 };
 
+//! Execution space instance (stands in for Kokkos::Cuda): a CUDA stream.  Default-constructed it
+//! is the default stream, like Kokkos::Cuda().  Everything that takes an ExecutionSpace in the
+//! reference (VerletList constructors/build :1260-1281, :1351-1392; RangePolicy( space, b, e ))
+//! launches its kernels on this stream.
+class DeviceExecutionSpace
+{
+  public:
+    DeviceExecutionSpace() = default;
+    explicit DeviceExecutionSpace( cb_stream_t stream )
+        : _stream( stream )
+    {
+    }
+    cb_stream_t stream() const { return _stream; }
+    //! Kokkos::Cuda::fence()
+    void fence() const;
+
+  private:
+    cb_stream_t _stream = nullptr;
+};
+
 //! Kokkos::RangePolicy<ExecSpace[, WorkTag]> stand-in: [begin, end).
 template <class WorkTag = void>
 class RangePolicy
@@ -68,15 +89,24 @@ class RangePolicy
   public:
     using work_tag = WorkTag;
     using index_type = int;
+    using execution_space = DeviceExecutionSpace;
     RangePolicy( std::size_t b, std::size_t e )
         : _b( b )
         , _e( e )
     {
     }
+    RangePolicy( const DeviceExecutionSpace& space, std::size_t b, std::size_t e )
+        : _space( space )
+        , _b( b )
+        , _e( e )
+    {
+    }
     std::size_t begin() const { return _b; }
     std::size_t end() const { return _e; }
+    const DeviceExecutionSpace& space() const { return _space; }
 
   private:
+    DeviceExecutionSpace _space;
     std::size_t _b, _e;
 };
 
@@ -88,6 +118,13 @@ inline void check( int rc, const char* where )
         throw std::runtime_error( std::string( where ) + ": " + cb_last_error_string() );
 }
 
+} // namespace Impl
+inline void DeviceExecutionSpace::fence() const
+{
+    Impl::check( cb_stream_synchronize( _stream ), "Cabana::DeviceExecutionSpace::fence" );
+}
+namespace Impl
+{
 //! Ref-counted device allocation (Kokkos::View ownership semantics: copies are shallow).
 template <class T>
 std::shared_ptr<T> device_alloc( std::size_t n )
@@ -685,15 +722,46 @@ class VerletList
 
     VerletList() = default;
 
-    //! Constructor / build (:875-959)
+    //! Constructors (:875-1017, with a leading ExecutionSpace :1260-1281) and build (:1351-1392).
     template <class PositionType, class ArrayType>
     VerletList( PositionType x, const std::size_t begin, const std::size_t end,
                 const double neighborhood_radius, const double cell_size_ratio,
                 const ArrayType& grid_min, const ArrayType& grid_max,
                 const std::size_t max_neigh = 0 )
     {
-        build( x, begin, end, neighborhood_radius, cell_size_ratio, grid_min, grid_max,
-               max_neigh );
+        build( DeviceExecutionSpace(), x, begin, end, neighborhood_radius, cell_size_ratio,
+               grid_min, grid_max, max_neigh );
+    }
+    template <class PositionType, class ArrayType>
+    VerletList( const DeviceExecutionSpace& exec_space, PositionType x, const std::size_t begin,
+                const std::size_t end, const double neighborhood_radius,
+                const double cell_size_ratio, const ArrayType& grid_min,
+                const ArrayType& grid_max, const std::size_t max_neigh = 0 )
+    {
+        build( exec_space, x, begin, end, neighborhood_radius, cell_size_ratio, grid_min,
+               grid_max, max_neigh );
+    }
+    //! Per-particle cutoff: background radius for the linked cells + a radius slice/view (:989-1017)
+    template <class PositionType, class RadiusType, class ArrayType>
+    VerletList( PositionType x, const std::size_t begin, const std::size_t end,
+                const double background_radius, RadiusType neighborhood_radius,
+                const double cell_size_ratio, const ArrayType& grid_min,
+                const ArrayType& grid_max, const std::size_t max_neigh = 0,
+                decltype( std::declval<RadiusType>().field() )* = nullptr )
+    {
+        build( DeviceExecutionSpace(), x, begin, end, background_radius, neighborhood_radius,
+               cell_size_ratio, grid_min, grid_max, max_neigh );
+    }
+    template <class PositionType, class RadiusType, class ArrayType>
+    VerletList( const DeviceExecutionSpace& exec_space, PositionType x, const std::size_t begin,
+                const std::size_t end, const double background_radius,
+                RadiusType neighborhood_radius, const double cell_size_ratio,
+                const ArrayType& grid_min, const ArrayType& grid_max,
+                const std::size_t max_neigh = 0,
+                decltype( std::declval<RadiusType>().field() )* = nullptr )
+    {
+        build( exec_space, x, begin, end, background_radius, neighborhood_radius,
+               cell_size_ratio, grid_min, grid_max, max_neigh );
     }
 
     template <class PositionType, class ArrayType>
@@ -702,12 +770,16 @@ class VerletList
                 const ArrayType& grid_min, const ArrayType& grid_max,
                 const std::size_t max_neigh = 0 )
     {
-        if ( !_h )
-        {
-            cb_verlet* raw = nullptr;
-            Impl::check( cb_verlet_create( &raw ), "Cabana::VerletList" );
-            _h = std::shared_ptr<cb_verlet>( raw, []( cb_verlet* p ) { cb_verlet_destroy( p ); } );
-        }
+        build( DeviceExecutionSpace(), x, begin, end, neighborhood_radius, cell_size_ratio,
+               grid_min, grid_max, max_neigh );
+    }
+    template <class PositionType, class ArrayType>
+    void build( const DeviceExecutionSpace& exec_space, PositionType x, const std::size_t begin,
+                const std::size_t end, const double neighborhood_radius,
+                const double cell_size_ratio, const ArrayType& grid_min,
+                const ArrayType& grid_max, const std::size_t max_neigh = 0 )
+    {
+        ensure_handle();
         auto mn = Impl::to_array3( grid_min ), mx = Impl::to_array3( grid_max );
         cb_positions xd = x.positions();
         Impl::check( cb_verlet_build( _h.get(), &xd, (int64_t)begin, (int64_t)end,
@@ -715,7 +787,39 @@ class VerletList
                                       mx.data(), (int64_t)max_neigh,
                                       Impl::algorithm_enum<AlgorithmTag>::value,
                                       Impl::layout_enum<LayoutTag>::value,
-                                      Impl::op_enum<BuildTag>::value, nullptr ),
+                                      Impl::op_enum<BuildTag>::value, exec_space.stream() ),
+                     "Cabana::VerletList::build" );
+        Impl::check( cb_verlet_get( _h.get(), &_view ), "cb_verlet_get" );
+        fill_data( _data );
+    }
+    template <class PositionType, class RadiusType, class ArrayType>
+    auto build( PositionType x, const std::size_t begin, const std::size_t end,
+                const double background_radius, RadiusType neighborhood_radius,
+                const double cell_size_ratio, const ArrayType& grid_min,
+                const ArrayType& grid_max, const std::size_t max_neigh = 0 )
+        -> decltype( neighborhood_radius.field(), void() )
+    {
+        build( DeviceExecutionSpace(), x, begin, end, background_radius, neighborhood_radius,
+               cell_size_ratio, grid_min, grid_max, max_neigh );
+    }
+    template <class PositionType, class RadiusType, class ArrayType>
+    auto build( const DeviceExecutionSpace& exec_space, PositionType x, const std::size_t begin,
+                const std::size_t end, const double background_radius,
+                RadiusType neighborhood_radius, const double cell_size_ratio,
+                const ArrayType& grid_min, const ArrayType& grid_max,
+                const std::size_t max_neigh = 0 )
+        -> decltype( neighborhood_radius.field(), void() )
+    {
+        ensure_handle();
+        auto mn = Impl::to_array3( grid_min ), mx = Impl::to_array3( grid_max );
+        cb_positions xd = x.positions();
+        cb_field rd = neighborhood_radius.field();
+        Impl::check( cb_verlet_build_radii( _h.get(), &xd, &rd, (int64_t)begin, (int64_t)end,
+                                            background_radius, cell_size_ratio, mn.data(),
+                                            mx.data(), (int64_t)max_neigh,
+                                            Impl::algorithm_enum<AlgorithmTag>::value,
+                                            Impl::layout_enum<LayoutTag>::value,
+                                            Impl::op_enum<BuildTag>::value, exec_space.stream() ),
                      "Cabana::VerletList::build" );
         Impl::check( cb_verlet_get( _h.get(), &_view ), "cb_verlet_get" );
         fill_data( _data );
@@ -736,6 +840,15 @@ class VerletList
     device_view_type deviceView() const { return device_view_type{ _data }; }
 
   private:
+    void ensure_handle()
+    {
+        if ( !_h )
+        {
+            cb_verlet* raw = nullptr;
+            Impl::check( cb_verlet_create( &raw ), "Cabana::VerletList" );
+            _h = std::shared_ptr<cb_verlet>( raw, []( cb_verlet* p ) { cb_verlet_destroy( p ); } );
+        }
+    }
     void fill_data( VerletListData<memory_space, VerletLayoutCSR>& d )
     {
         d.counts = _view.counts;
@@ -759,7 +872,7 @@ class VerletList
     cb_verlet_view _view{};
 };
 
-//! createVerletList (:1528-1597)
+//! createVerletList (:1528-1597), fixed and per-particle radius, with/without ExecutionSpace
 template <class AlgorithmTag, class LayoutTag, class BuildTag, class PositionType,
           class ArrayType>
 auto createVerletList( PositionType positions, const std::size_t begin,
@@ -769,6 +882,30 @@ auto createVerletList( PositionType positions, const std::size_t begin,
 {
     return VerletList<typename PositionType::memory_space, AlgorithmTag, LayoutTag, BuildTag, 3>(
         positions, begin, end, radius, cell_size_ratio, grid_min, grid_max, max_neigh );
+}
+template <class AlgorithmTag, class LayoutTag, class BuildTag, class PositionType,
+          class ArrayType>
+auto createVerletList( const DeviceExecutionSpace& exec_space, PositionType positions,
+                       const std::size_t begin, const std::size_t end, const double radius,
+                       const double cell_size_ratio, const ArrayType& grid_min,
+                       const ArrayType& grid_max, const std::size_t max_neigh = 0 )
+{
+    return VerletList<typename PositionType::memory_space, AlgorithmTag, LayoutTag, BuildTag, 3>(
+        exec_space, positions, begin, end, radius, cell_size_ratio, grid_min, grid_max,
+        max_neigh );
+}
+template <class AlgorithmTag, class LayoutTag, class BuildTag, class PositionType,
+          class RadiusType, class ArrayType>
+auto createVerletList( PositionType positions, const std::size_t begin,
+                       const std::size_t end, const double background_radius,
+                       RadiusType radius, const double cell_size_ratio,
+                       const ArrayType& grid_min, const ArrayType& grid_max,
+                       const std::size_t max_neigh = 0,
+                       decltype( std::declval<RadiusType>().field() )* = nullptr )
+{
+    return VerletList<typename PositionType::memory_space, AlgorithmTag, LayoutTag, BuildTag, 3>(
+        positions, begin, end, background_radius, radius, cell_size_ratio, grid_min, grid_max,
+        max_neigh );
 }
 
 //---------------------------------------------------------------------------//
@@ -964,7 +1101,7 @@ void neighbor_parallel_for_lj( const RangePolicy<>& policy, const ListType& list
     cb_field fd = f.field();
     Impl::check( cb_neighbor_for_lj( &list.view(), &xd, &fd, eps, sigma, rc, newton ? 1 : 0,
                                      Impl::op_enum<OpTag>::value, (int64_t)policy.begin(),
-                                     (int64_t)policy.end(), nullptr ),
+                                     (int64_t)policy.end(), policy.space().stream() ),
                  "Cabana::neighbor_parallel_for(LJ)" );
 }
 //! neighbor_parallel_reduce with the LJ pair energy.
@@ -979,7 +1116,7 @@ double neighbor_parallel_reduce_lj( const RangePolicy<>& policy, const ListType&
     double e = 0.0;
     Impl::check( cb_neighbor_reduce_lj( &list.view(), &xd, eps, sigma, rc, scale,
                                         Impl::op_enum<OpTag>::value, (int64_t)policy.begin(),
-                                        (int64_t)policy.end(), &e, nullptr ),
+                                        (int64_t)policy.end(), &e, policy.space().stream() ),
                  "Cabana::neighbor_parallel_reduce(LJ)" );
     return e;
 }
@@ -1034,9 +1171,46 @@ __global__ void k_neighbor_for_team( FunctorType functor, ListType list, int beg
             functorTagDispatch<WorkTag>( functor, i, (int)traits::getNeighbor( list, i, n ) );
     }
 }
+// Sum of the threads' partial results: tree reduction of the CTA in shared memory, one value
+// per CTA written to partials[blockIdx.x] (any ReduceType with += ; no atomics, deterministic).
+template <class ReduceType>
+CABANA_B200_DEVICE void block_reduce_store( const ReduceType& local, ReduceType* partials )
+{
+    extern __shared__ __align__( 16 ) unsigned char cb_reduce_smem[];
+    ReduceType* sm = reinterpret_cast<ReduceType*>( cb_reduce_smem );
+    sm[threadIdx.x] = local;
+    __syncthreads();
+    for ( int s = blockDim.x >> 1; s > 0; s >>= 1 )
+    {
+        if ( (int)threadIdx.x < s )
+            sm[threadIdx.x] += sm[threadIdx.x + s];
+        __syncthreads();
+    }
+    if ( threadIdx.x == 0 )
+        partials[blockIdx.x] = sm[0];
+}
+template <class ReduceType>
+__global__ void k_sum_partials( const ReduceType* partials, int n, ReduceType* result )
+{
+    extern __shared__ __align__( 16 ) unsigned char cb_reduce_smem[];
+    ReduceType* sm = reinterpret_cast<ReduceType*>( cb_reduce_smem );
+    ReduceType local = ReduceType();
+    for ( int i = threadIdx.x; i < n; i += blockDim.x )
+        local += partials[i];
+    sm[threadIdx.x] = local;
+    __syncthreads();
+    for ( int s = blockDim.x >> 1; s > 0; s >>= 1 )
+    {
+        if ( (int)threadIdx.x < s )
+            sm[threadIdx.x] += sm[threadIdx.x + s];
+        __syncthreads();
+    }
+    if ( threadIdx.x == 0 )
+        *result = sm[0];
+}
 template <class WorkTag, class FunctorType, class ListType, class ReduceType, bool Team>
 __global__ void k_neighbor_reduce( FunctorType functor, ListType list, int begin, int end,
-                                   ReduceType* result )
+                                   ReduceType* partials )
 {
     using traits = NeighborList<ListType>;
     ReduceType local = ReduceType();
@@ -1064,7 +1238,7 @@ __global__ void k_neighbor_reduce( FunctorType functor, ListType list, int begin
                                              (int)traits::getNeighbor( list, i, n ), local );
         }
     }
-    atomicAdd( result, local );
+    block_reduce_store( local, partials );
 }
 // SecondNeighborsTag: every unordered pair (j,k) of neighbours of i, j before k in the row
 // (Cabana_Parallel.hpp:315-365 Serial, :458-522 Team, :527-594 TeamVector)
@@ -1132,7 +1306,7 @@ __global__ void k_second_neighbor_for_team( FunctorType functor, ListType list, 
 }
 template <class WorkTag, class FunctorType, class ListType, class ReduceType, bool Team>
 __global__ void k_second_neighbor_reduce( FunctorType functor, ListType list, int begin,
-                                          int end, ReduceType* result )
+                                          int end, ReduceType* result /* per-CTA partials */ )
 {
     using traits = NeighborList<ListType>;
     ReduceType local = ReduceType();
@@ -1151,7 +1325,7 @@ __global__ void k_second_neighbor_reduce( FunctorType functor, ListType list, in
                                              (int)traits::getNeighbor( list, i, a ), local );
         }
     }
-    atomicAdd( result, local );
+    block_reduce_store( local, result );
 }
 // neighbor_parallel_for directly on a LinkedCellList (LinkedCellParallelFor,
 // Cabana_Parallel.hpp:1122-1290): every particle j != i of the stencil cells of i's bin is
@@ -1194,12 +1368,83 @@ __global__ void k_linked_cell_for( FunctorType functor, cb_lcl_view l, int begin
                 }
     }
 }
+// neighbor_parallel_reduce directly on a LinkedCellList (LinkedCellParallelReduce,
+// Cabana_Parallel.hpp:1296-1468): functor( i, j, ival ) for every j != i of the stencil cells.
+template <class WorkTag, class FunctorType, class ReduceType, bool TEAM>
+__global__ void k_linked_cell_reduce( FunctorType functor, cb_lcl_view l, int begin, int end,
+                                      ReduceType* partials )
+{
+    ReduceType local = ReduceType();
+    const int lane = threadIdx.x & 31;
+    const int first = TEAM ? ( ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5 )
+                           : ( blockIdx.x * blockDim.x + threadIdx.x );
+    const int stride = TEAM ? ( ( gridDim.x * blockDim.x ) >> 5 ) : ( gridDim.x * blockDim.x );
+    const int sny = l.stencil_grid.nx[1], snz = l.stencil_grid.nx[2];
+    const int ny = l.grid.nx[1], nz = l.grid.nx[2];
+    for ( int i = begin + first; i < end; i += stride )
+    {
+        const int cell = l.particle_bins[i - l.begin];
+        const int ci = cell / ( sny * snz ), cj = ( cell / snz ) % sny, ck = cell % snz;
+        const int R = l.cell_range;
+        const int imin = ci - R > 0 ? ci - R : 0;
+        const int imax = ci + R + 1 < l.stencil_grid.nx[0] ? ci + R + 1 : l.stencil_grid.nx[0];
+        const int jmin = cj - R > 0 ? cj - R : 0;
+        const int jmax = cj + R + 1 < sny ? cj + R + 1 : sny;
+        const int kmin = ck - R > 0 ? ck - R : 0;
+        const int kmax = ck + R + 1 < snz ? ck + R + 1 : snz;
+        for ( int gi = imin; gi < imax; ++gi )
+            for ( int gj = jmin; gj < jmax; ++gj )
+                for ( int gk = kmin; gk < kmax; ++gk )
+                {
+                    const int c = ( gi * ny + gj ) * nz + gk;
+                    const unsigned n0 = l.offsets[c];
+                    const unsigned n1 = n0 + (unsigned)l.counts[c];
+                    for ( unsigned n = n0 + ( TEAM ? lane : 0 ); n < n1; n += TEAM ? 32 : 1 )
+                    {
+                        const int j = l.sorted ? (int)( n + l.begin ) : (int)l.permute[n];
+                        if ( j != i )
+                            functorTagDispatch<WorkTag>( functor, i, j, local );
+                    }
+                }
+    }
+    block_reduce_store( local, partials );
+}
 inline int grid_for( long long items, int block )
 {
     long long b = ( items + block - 1 ) / block;
     if ( b > 148 * 32 )
         b = 148 * 32;
     return (int)( b < 1 ? 1 : b );
+}
+inline cudaStream_t stream_of( const DeviceExecutionSpace& space )
+{
+    return static_cast<cudaStream_t>( space.stream() );
+}
+inline void check_launch( const char* where )
+{
+    if ( cudaGetLastError() != cudaSuccess )
+        throw std::runtime_error( std::string( where ) + ": launch failed" );
+}
+// Runs `launch( grid, block, smem_bytes, partials )` (a reduce kernel that leaves one partial
+// per CTA), sums the partials on the device and returns the value -- the synchronisation a
+// Kokkos::parallel_reduce into a host scalar implies.
+template <class ReduceType, class Launch>
+ReduceType run_reduce( const DeviceExecutionSpace& space, long long threads, Launch&& launch )
+{
+    constexpr int block = 256;
+    const int grid = grid_for( threads, block );
+    auto dev = device_alloc<ReduceType>( (std::size_t)grid + 1 );
+    cudaStream_t st = stream_of( space );
+    launch( grid, block, sizeof( ReduceType ) * block, dev.get() + 1 );
+    check_launch( "Cabana::neighbor_parallel_reduce" );
+    k_sum_partials<ReduceType>
+        <<<1, block, sizeof( ReduceType ) * block, st>>>( dev.get() + 1, grid, dev.get() );
+    check_launch( "Cabana::neighbor_parallel_reduce" );
+    ReduceType out;
+    check( cb_memcpy_d2h( &out, dev.get(), sizeof( ReduceType ), space.stream() ),
+           "Cabana::neighbor_parallel_reduce" );
+    check( cb_stream_synchronize( space.stream() ), "Cabana::neighbor_parallel_reduce" );
+    return out;
 }
 } // namespace Impl
 
@@ -1217,9 +1462,9 @@ inline void neighbor_parallel_for( const RangePolicy<WorkTag>& exec_policy,
     if ( e <= b )
         return;
     Impl::k_neighbor_for_serial<WorkTag>
-        <<<Impl::grid_for( e - b, 256 ), 256>>>( functor, list.deviceView(), b, e );
-    if ( cudaGetLastError() != cudaSuccess )
-        throw std::runtime_error( "Cabana::neighbor_parallel_for: launch failed" );
+        <<<Impl::grid_for( e - b, 256 ), 256, 0, Impl::stream_of( exec_policy.space() )>>>(
+            functor, list.deviceView(), b, e );
+    Impl::check_launch( "Cabana::neighbor_parallel_for" );
 }
 //! neighbor_parallel_for, FirstNeighborsTag x TeamOpTag (:386-435)
 template <class FunctorType, class NeighborListType, class WorkTag>
@@ -1235,10 +1480,9 @@ inline void neighbor_parallel_for( const RangePolicy<WorkTag>& exec_policy,
     if ( e <= b )
         return;
     Impl::k_neighbor_for_team<WorkTag>
-        <<<Impl::grid_for( (long long)( e - b ) * 32, 256 ), 256>>>( functor, list.deviceView(),
-                                                                     b, e );
-    if ( cudaGetLastError() != cudaSuccess )
-        throw std::runtime_error( "Cabana::neighbor_parallel_for: launch failed" );
+        <<<Impl::grid_for( (long long)( e - b ) * 32, 256 ), 256, 0,
+           Impl::stream_of( exec_policy.space() )>>>( functor, list.deviceView(), b, e );
+    Impl::check_launch( "Cabana::neighbor_parallel_for" );
 }
 //! neighbor_parallel_for on a LinkedCellList, no stored list (:1511-1595): Serial / Team.
 //! Positions must be in the order the list currently describes (permuted iff sorted()).
@@ -1259,9 +1503,38 @@ inline void neighbor_parallel_for( const RangePolicy<WorkTag>& exec_policy,
     constexpr bool team = std::is_same<OpTag, TeamOpTag>::value;
     const long long threads = team ? (long long)( e - b ) * 32 : ( e - b );
     Impl::k_linked_cell_for<WorkTag, FunctorType, team>
-        <<<Impl::grid_for( threads, 256 ), 256>>>( functor, list.deviceView().v, b, e );
-    if ( cudaGetLastError() != cudaSuccess )
-        throw std::runtime_error( "Cabana::neighbor_parallel_for: launch failed" );
+        <<<Impl::grid_for( threads, 256 ), 256, 0, Impl::stream_of( exec_policy.space() )>>>(
+            functor, list.deviceView().v, b, e );
+    Impl::check_launch( "Cabana::neighbor_parallel_for" );
+}
+//! neighbor_parallel_reduce on a LinkedCellList (:1596-1726): Serial / Team.  The range must be
+//! the binned range (the reference asserts equality, :1651-1652).
+template <class FunctorType, class M, class S, std::size_t D, class ReduceType, class WorkTag,
+          class OpTag>
+inline void neighbor_parallel_reduce( const RangePolicy<WorkTag>& exec_policy,
+                                      const FunctorType& functor,
+                                      const LinkedCellList<M, S, D>& list,
+                                      const FirstNeighborsTag, const OpTag,
+                                      ReduceType& reduce_val, const std::string& = "" )
+{
+    static_assert( std::is_same<OpTag, SerialOpTag>::value ||
+                       std::is_same<OpTag, TeamOpTag>::value,
+                   "LinkedCellList traversal is Serial or Team" );
+    const int b = (int)exec_policy.begin(), e = (int)exec_policy.end();
+    if ( b != (int)list.getParticleBegin() || e != (int)list.getParticleEnd() )
+        throw std::runtime_error(
+            "Cabana::neighbor_parallel_reduce: cannot iterate over a range that was not binned" );
+    constexpr bool team = std::is_same<OpTag, TeamOpTag>::value;
+    const long long threads = team ? (long long)( e - b ) * 32 : ( e - b );
+    const cb_lcl_view v = list.deviceView().v;
+    cudaStream_t st = Impl::stream_of( exec_policy.space() );
+    reduce_val = Impl::run_reduce<ReduceType>(
+        exec_policy.space(), threads > 0 ? threads : 1,
+        [&]( int grid, int block, std::size_t smem, ReduceType* partials )
+        {
+            Impl::k_linked_cell_reduce<WorkTag, FunctorType, ReduceType, team>
+                <<<grid, block, smem, st>>>( functor, v, b, e, partials );
+        } );
 }
 //! neighbor_parallel_for, SecondNeighborsTag x {Serial,Team,TeamVector} (:315-365, :458-594)
 template <class FunctorType, class NeighborListType, class WorkTag, class OpTag>
@@ -1274,19 +1547,19 @@ inline void neighbor_parallel_for( const RangePolicy<WorkTag>& exec_policy,
     if ( e <= b )
         return;
     using view_type = typename NeighborListType::device_view_type;
+    cudaStream_t st = Impl::stream_of( exec_policy.space() );
     if ( std::is_same<OpTag, SerialOpTag>::value )
         Impl::k_second_neighbor_for_serial<WorkTag, FunctorType, view_type>
-            <<<Impl::grid_for( e - b, 128 ), 128>>>( functor, list.deviceView(), b, e );
+            <<<Impl::grid_for( e - b, 128 ), 128, 0, st>>>( functor, list.deviceView(), b, e );
     else if ( std::is_same<OpTag, TeamOpTag>::value )
         Impl::k_second_neighbor_for_team<WorkTag, FunctorType, view_type, false>
-            <<<Impl::grid_for( (long long)( e - b ) * 32, 256 ), 256>>>(
+            <<<Impl::grid_for( (long long)( e - b ) * 32, 256 ), 256, 0, st>>>(
                 functor, list.deviceView(), b, e );
     else
         Impl::k_second_neighbor_for_team<WorkTag, FunctorType, view_type, true>
-            <<<Impl::grid_for( (long long)( e - b ) * 32, 256 ), 256>>>(
+            <<<Impl::grid_for( (long long)( e - b ) * 32, 256 ), 256, 0, st>>>(
                 functor, list.deviceView(), b, e );
-    if ( cudaGetLastError() != cudaSuccess )
-        throw std::runtime_error( "Cabana::neighbor_parallel_for: launch failed" );
+    Impl::check_launch( "Cabana::neighbor_parallel_for" );
 }
 //! neighbor_parallel_reduce, SecondNeighborsTag x {Serial,Team,TeamVector} (:704-759, :866-1001)
 template <class FunctorType, class NeighborListType, class ReduceType, class WorkTag,
@@ -1298,53 +1571,48 @@ inline void neighbor_parallel_reduce( const RangePolicy<WorkTag>& exec_policy,
                                       const std::string& = "" )
 {
     const int b = (int)exec_policy.begin(), e = (int)exec_policy.end();
-    auto dev = Impl::device_alloc<ReduceType>( 1 );
-    const ReduceType zero = ReduceType();
-    cudaMemcpy( dev.get(), &zero, sizeof( ReduceType ), cudaMemcpyHostToDevice );
-    if ( e > b )
-    {
-        constexpr bool team = !std::is_same<OpTag, SerialOpTag>::value;
-        const long long threads = team ? (long long)( e - b ) * 32 : ( e - b );
-        Impl::k_second_neighbor_reduce<WorkTag, FunctorType,
-                                       typename NeighborListType::device_view_type,
-                                       ReduceType, team>
-            <<<Impl::grid_for( threads, 256 ), 256>>>( functor, list.deviceView(), b, e,
-                                                       dev.get() );
-    }
-    ReduceType out;
-    cudaMemcpy( &out, dev.get(), sizeof( ReduceType ), cudaMemcpyDeviceToHost );
-    reduce_val = out;
+    constexpr bool team = !std::is_same<OpTag, SerialOpTag>::value;
+    const long long threads = team ? (long long)( e - b ) * 32 : ( e - b );
+    auto dv = list.deviceView();
+    cudaStream_t st = Impl::stream_of( exec_policy.space() );
+    reduce_val = Impl::run_reduce<ReduceType>(
+        exec_policy.space(), threads > 0 ? threads : 1,
+        [&]( int grid, int block, std::size_t smem, ReduceType* partials )
+        {
+            Impl::k_second_neighbor_reduce<WorkTag, FunctorType,
+                                           typename NeighborListType::device_view_type,
+                                           ReduceType, team>
+                <<<grid, block, smem, st>>>( functor, dv, b, e, partials );
+        } );
 }
 //! neighbor_parallel_reduce, FirstNeighborsTag x {SerialOpTag,TeamOpTag} (:638-685, :787-844)
 template <class FunctorType, class NeighborListType, class ReduceType, class WorkTag,
           class OpTag>
-inline void neighbor_parallel_reduce( const RangePolicy<WorkTag>& exec_policy,
-                                      const FunctorType& functor,
-                                      const NeighborListType& list, const FirstNeighborsTag,
-                                      const OpTag, ReduceType& reduce_val,
-                                      const std::string& = "" )
+inline typename std::enable_if<!is_linked_cell_list<NeighborListType>::value>::type
+neighbor_parallel_reduce( const RangePolicy<WorkTag>& exec_policy, const FunctorType& functor,
+                          const NeighborListType& list, const FirstNeighborsTag, const OpTag,
+                          ReduceType& reduce_val, const std::string& = "" )
 {
     static_assert( std::is_same<OpTag, SerialOpTag>::value ||
                        std::is_same<OpTag, TeamOpTag>::value,
                    "first-neighbour reduce is Serial or Team" );
     const int b = (int)exec_policy.begin(), e = (int)exec_policy.end();
-    auto dev = Impl::device_alloc<ReduceType>( 1 );
-    const ReduceType zero = ReduceType();
-    cudaMemcpy( dev.get(), &zero, sizeof( ReduceType ), cudaMemcpyHostToDevice );
-    if ( e > b )
-    {
-        constexpr bool team = std::is_same<OpTag, TeamOpTag>::value;
-        const long long threads = team ? (long long)( e - b ) * 32 : ( e - b );
-        Impl::k_neighbor_reduce<WorkTag, FunctorType,
-                                typename NeighborListType::device_view_type, ReduceType, team>
-            <<<Impl::grid_for( threads, 256 ), 256>>>( functor, list.deviceView(), b, e,
-                                                       dev.get() );
-    }
-    ReduceType out;
-    cudaMemcpy( &out, dev.get(), sizeof( ReduceType ), cudaMemcpyDeviceToHost );
-    reduce_val = out; // Kokkos::parallel_reduce overwrites the result argument
+    constexpr bool team = std::is_same<OpTag, TeamOpTag>::value;
+    const long long threads = team ? (long long)( e - b ) * 32 : ( e - b );
+    auto dv = list.deviceView();
+    cudaStream_t st = Impl::stream_of( exec_policy.space() );
+    // Kokkos::parallel_reduce overwrites the result argument
+    reduce_val = Impl::run_reduce<ReduceType>(
+        exec_policy.space(), threads > 0 ? threads : 1,
+        [&]( int grid, int block, std::size_t smem, ReduceType* partials )
+        {
+            Impl::k_neighbor_reduce<WorkTag, FunctorType,
+                                    typename NeighborListType::device_view_type, ReduceType,
+                                    team>
+                <<<grid, block, smem, st>>>( functor, dv, b, e, partials );
+        } );
 }
-//! for_each_neighbor inside a user kernel (:1058-1072)
+//! for_each_neighbor inside a user kernel, thread-serial (:1058-1072)
 template <class IndexType, class FunctorType, class NeighborListType>
 CABANA_B200_DEVICE void for_each_neighbor( const IndexType i, const FunctorType& functor,
                                            const NeighborListType& list,
@@ -1353,6 +1621,33 @@ CABANA_B200_DEVICE void for_each_neighbor( const IndexType i, const FunctorType&
     using traits = NeighborList<NeighborListType>;
     for ( IndexType n = 0; n < (IndexType)traits::numNeighbor( list, i ); ++n )
         functor( i, (IndexType)traits::getNeighbor( list, i, n ) );
+}
+//! Team handle for the team form of for_each_neighbor: the warp of the calling thread
+//! (stands in for Kokkos::TeamPolicy<>::member_type; league_rank() = global warp index).
+struct WarpTeamMember
+{
+    CABANA_B200_DEVICE int team_rank() const { return (int)( threadIdx.x & 31u ); }
+    CABANA_B200_DEVICE int team_size() const { return 32; }
+    CABANA_B200_DEVICE int league_rank() const
+    {
+        return (int)( ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5 );
+    }
+    CABANA_B200_DEVICE int league_size() const { return (int)( ( gridDim.x * blockDim.x ) >> 5 ); }
+    CABANA_B200_DEVICE void team_barrier() const { __syncwarp(); }
+};
+//! for_each_neighbor inside a user kernel, team-parallel over the neighbours (:1091-1110):
+//! every thread of the team calls it with the same i; the neighbours are strided over the team
+//! (Kokkos::TeamThreadRange).
+template <class IndexType, class FunctorType, class NeighborListType, class TeamMemberType>
+CABANA_B200_DEVICE void for_each_neighbor( const IndexType i, const TeamMemberType team,
+                                           const FunctorType& functor,
+                                           const NeighborListType& list,
+                                           const FirstNeighborsTag )
+{
+    using traits = NeighborList<NeighborListType>;
+    const IndexType nn = (IndexType)traits::numNeighbor( list, i );
+    for ( IndexType n = (IndexType)team.team_rank(); n < nn; n += (IndexType)team.team_size() )
+        Impl::functorTagDispatch<void>( functor, i, (IndexType)traits::getNeighbor( list, i, n ) );
 }
 #endif // __CUDACC__
 

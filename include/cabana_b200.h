@@ -264,6 +264,20 @@ int cb_verlet_destroy(cb_verlet* list);
 int cb_verlet_set_profiling(cb_verlet* list, int enable);
 int cb_verlet_get_phase_times(const cb_verlet* list, double* ms_h);
 
+/* Per-particle cutoff radius: VerletList( x, begin, end, background_radius, neighborhood_radius
+ * (slice or view, one double per particle), cell_size_ratio, grid_min, grid_max, max_neigh )
+ * (core/src/Cabana_VerletList.hpp:989-1017 -> VerletListBuilder :181-203; withinCutoff /
+ * neighborNotWithinCutoff / addNeighbor :244-305).  The linked cells use background_radius;
+ * row i holds every valid j with dist_sqr <= radius(i)^2, plus every j that found i with
+ * dist_sqr >= radius(i)^2 ("j adds itself because i will not find it").  counts/offsets describe
+ * exactly those rows: the reference's count pass books the extra entry on the other row
+ * (SURVEY.md Appendix B.6); its post-fill counts, which its test checks, are these. */
+int cb_verlet_build_radii(cb_verlet* list, const cb_positions* x, const cb_field* radii_h,
+                          int64_t begin, int64_t end, double background_radius,
+                          double cell_size_ratio, const double* grid_min_h,
+                          const double* grid_max_h, int64_t max_neigh, int algorithm,
+                          int layout, int build_op, cb_stream_t stream);
+
 /* Self-test of the tensor-core distance filter the build relies on (tests only): runs the
  * count pass over `x` with EVERY filter value compared with the exact FP64 arithmetic.
  * out_h[0] = largest |filter - exact| observed over pairs with s <= 4 r^2 (the range the bound

@@ -382,6 +382,37 @@ def verlet_build(
     )
 
 
+def verlet_build_radii(x: PositionsView, radii, begin, end, background_radius, ratio, gmin, gmax,
+                       max_neigh=0, algo=FULL, layout=CSR):
+    """Per-particle cutoff radius build (Cabana_VerletList.hpp:181-203, :244-305).  Returns
+    (VerletResult with the FILL semantics, literal count-pass counts) -- see the note on the
+    reference's count/fill asymmetry in cabana_oracle.cpp."""
+    n = x.n
+    radii = np.ascontiguousarray(radii, dtype=np.float64)
+    assert radii.shape == (n,)
+    counts = np.zeros(n, dtype=np.int32)
+    offsets = np.zeros(n, dtype=np.int32)
+    cp_counts = np.zeros(n, dtype=np.int32)
+    nb_ptr = C.POINTER(C.c_int)()
+    info = _VerletInfo()
+    d = x.desc()
+    rc = lib().orc_verlet_build_radii(
+        C.byref(d), radii.ctypes.data_as(C.c_void_p), C.c_int64(begin), C.c_int64(end),
+        C.c_double(background_radius), C.c_double(ratio), _d3(gmin), _d3(gmax), C.c_int64(max_neigh),
+        C.c_int(algo), C.c_int(layout), counts.ctypes.data_as(C.c_void_p),
+        offsets.ctypes.data_as(C.c_void_p), C.byref(nb_ptr), cp_counts.ctypes.data_as(C.c_void_p),
+        C.byref(info))
+    assert rc == 0
+    size = int(info.total) if layout == CSR else n * int(info.width)
+    nb = np.ctypeslib.as_array(nb_ptr, shape=(size,)).copy() if size > 0 else np.zeros(0, dtype=np.int32)
+    lib().orc_free(nb_ptr)
+    if layout == LAYOUT_2D:
+        nb = nb.reshape(n, int(info.width))
+    res = VerletResult(layout, counts, offsets if layout == CSR else None, nb, int(info.total),
+                       int(info.max_n), int(info.width), bool(info.refilled))
+    return res, cp_counts
+
+
 def brute_force(x: PositionsView, radius, with_neighbors=True) -> VerletResult:
     """N^2 list (core/unit_test/neighbor_unit_test.hpp:86-158), 2D row-major."""
     n = x.n

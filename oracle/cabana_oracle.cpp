@@ -572,6 +572,137 @@ int orc_verlet_build( const orc_positions* x, int64_t begin, int64_t end,
     return 0;
 }
 
+// -----------------------------------------------------------------------------
+// VerletList build with a PER-PARTICLE cutoff radius
+// (core/src/Cabana_VerletList.hpp:181-203 builder ctor; :244-305 withinCutoff /
+//  neighborNotWithinCutoff / countNeighbor / addNeighbor; :989-1017 list ctor).
+//
+// The LinkedCellList and the stencil use `background_radius`; the cell prune and
+// the pair test use radius(i) of the particle whose row is being built (:401-403,
+// :254).  A pair found by i with dist_sqr >= radius(j)^2 "will not be found by j",
+// so i also appears in j's row (:299-304).
+//
+// Reference quirk: the COUNT pass adds that extra entry
+// to i's count (:277-290) while the FILL pass appends it to j's row (:293-305).
+// The CSR offsets are scanned from the count-pass values, so rows can overrun
+// their slots; only the totals agree.  The counts after the fill pass -- which is
+// what the reference's own test checks (tstNeighborList.hpp:244-252) -- are the
+// row sizes of the fill semantics.  This restatement returns
+//   counts / offsets / neighbors : the FILL semantics (rows as addNeighbor builds
+//                                  them, offsets = exclusive scan of those sizes),
+//   count_pass_counts (optional) : the literal count-pass values (:277-290),
+// so a test can show both the 6/4 answer and the asymmetry.
+// 2D: width = max(max_neigh, max row size) (no entry is ever dropped).
+// -----------------------------------------------------------------------------
+int orc_verlet_build_radii( const orc_positions* x, const double* radii, int64_t begin,
+                            int64_t end, double background_radius, double cell_size_ratio,
+                            const double* grid_min, const double* grid_max,
+                            int64_t max_neigh, int algo, int layout, int* counts,
+                            int* offsets, int** neighbors_out, int* count_pass_counts,
+                            orc_verlet_info* info )
+{
+    const int64_t n = x->n;
+    orc_grid grid;
+    orc_stencil stencil;
+    double grid_size = cell_size_ratio * background_radius; // :224
+    double delta[3] = { grid_size, grid_size, grid_size };
+    orc_grid_init( &grid, grid_min, grid_max, delta );
+    orc_stencil_init( &stencil, background_radius, cell_size_ratio, grid_min, grid_max );
+    const int64_t ncell = (int64_t)grid.nx[0] * grid.nx[1] * grid.nx[2];
+    std::vector<int> lcl_counts( ncell );
+    std::vector<int64_t> lcl_offsets( ncell ), lcl_permute( n );
+    orc_lcl_build( &grid, x, 0, n, lcl_counts.data(), lcl_offsets.data(), lcl_permute.data(),
+                   nullptr, 0 );
+    std::vector<std::vector<int>> rows( (size_t)n );
+    if ( count_pass_counts )
+        std::fill( count_pass_counts, count_pass_counts + n, 0 );
+    for ( int64_t cell = 0; cell < ncell; ++cell )
+    {
+        int mn[3], mx[3];
+        orc_stencil_cells( &stencil, (int)cell, mn, mx );
+        for ( int bi = 0; bi < lcl_counts[cell]; ++bi )
+        {
+            const int64_t pid = lcl_permute[bi + lcl_offsets[cell]];
+            if ( pid < begin || pid >= end )
+                continue;
+            double xp[3];
+            for ( int d = 0; d < 3; ++d )
+                xp[d] = pos_at( x, pid, d );
+            const double ri2 = radii[pid] * radii[pid]; // withinCutoff :252
+            int ijk[3];
+            for ( ijk[0] = mn[0]; ijk[0] < mx[0]; ++ijk[0] )
+                for ( ijk[1] = mn[1]; ijk[1] < mx[1]; ++ijk[1] )
+                    for ( ijk[2] = mn[2]; ijk[2] < mx[2]; ++ijk[2] )
+                    {
+                        if ( !( orc_grid_min_distance( &stencil.grid, xp, ijk ) <= ri2 ) )
+                            continue; // :401-403 with the particle's own radius
+                        const int c = cardinal( &grid, ijk[0], ijk[1], ijk[2] );
+                        for ( int k = 0; k < lcl_counts[c]; ++k )
+                        {
+                            const int64_t nid = lcl_permute[lcl_offsets[c] + k];
+                            double xn[3];
+                            for ( int d = 0; d < 3; ++d )
+                                xn[d] = pos_at( x, nid, d );
+                            if ( !is_valid( algo, pid, xp, nid, xn ) )
+                                continue;
+                            double dist_sqr = 0.0;
+                            for ( int d = 0; d < 3; ++d )
+                            {
+                                double dx = xp[d] - xn[d];
+                                dist_sqr += dx * dx;
+                            }
+                            if ( dist_sqr <= ri2 ) // :299
+                            {
+                                rows[(size_t)pid].push_back( (int)nid ); // :301
+                                if ( count_pass_counts )
+                                    count_pass_counts[pid] += 1; // :284
+                                if ( dist_sqr >= radii[nid] * radii[nid] ) // :268
+                                {
+                                    rows[(size_t)nid].push_back( (int)pid ); // :304
+                                    if ( count_pass_counts )
+                                        count_pass_counts[pid] += 1; // :288 (sic: i, not j)
+                                }
+                            }
+                        }
+                    }
+        }
+    }
+    int64_t total = 0, mxn = 0;
+    for ( int64_t i = 0; i < n; ++i )
+    {
+        counts[i] = (int)rows[(size_t)i].size();
+        if ( layout == ORC_CSR )
+            offsets[i] = (int)total;
+        total += counts[i];
+        mxn = std::max<int64_t>( mxn, counts[i] );
+    }
+    info->total = total;
+    info->max_n = mxn;
+    info->refilled = 0;
+    info->width = 0;
+    int* nb = nullptr;
+    if ( layout == ORC_CSR )
+    {
+        nb = (int*)std::malloc( sizeof( int ) * (size_t)std::max<int64_t>( total, 1 ) );
+        for ( int64_t i = 0; i < n; ++i )
+            std::copy( rows[(size_t)i].begin(), rows[(size_t)i].end(), nb + offsets[i] );
+    }
+    else
+    {
+        int64_t width = mxn;
+        if ( max_neigh > 0 && mxn <= max_neigh )
+            width = max_neigh;
+        else if ( max_neigh > 0 )
+            info->refilled = 1;
+        info->width = width;
+        nb = (int*)std::calloc( (size_t)std::max<int64_t>( n * width, 1 ), sizeof( int ) );
+        for ( int64_t i = 0; i < n; ++i )
+            std::copy( rows[(size_t)i].begin(), rows[(size_t)i].end(), nb + i * width );
+    }
+    *neighbors_out = nb;
+    return 0;
+}
+
 void orc_free( void* p ) { std::free( p ); }
 
 // Order-independent 64-bit hash of every row (multiset of neighbour ids): equal hashes for

@@ -199,6 +199,10 @@ struct TripletSumPositionsFunctor
         sum += x( i, 0 ) + x( j, 0 ) + x( k, 0 );
     }
 };
+struct IdReduceFunctor
+{
+    __device__ void operator()( const int, const int j, long long& sum ) const { sum += j; }
+};
 struct SumPositionsFunctor
 {
     Cabana::Slice<double, 3> x;
@@ -749,6 +753,243 @@ static void testLinkedCellParallelFor()
     cudaFree( d_res );
 }
 
+// ---- testNonUniformRadius (tstNeighborList.hpp:210-253): per-particle cutoff radius ---------
+template <class LayoutTag>
+static void testNonUniformRadius()
+{
+    const int px = 2, n = px * px * px;
+    const double dx = 5.0 / px, large_radius = 4.05, small_radius = 3.32;
+    std::vector<double> xyz( 3 * n ), rad( n, small_radius );
+    for ( int p = 0; p < n; ++p )
+    {
+        xyz[3 * p + 0] = dx / 2 + dx * ( p / ( px * px ) );
+        xyz[3 * p + 1] = dx / 2 + dx * ( ( p / px ) % px );
+        xyz[3 * p + 2] = dx / 2 + dx * ( p % px );
+    }
+    rad[0] = rad[n - 1] = large_radius;
+    double *d_x = nullptr, *d_r = nullptr;
+    cudaMalloc( &d_x, xyz.size() * sizeof( double ) );
+    cudaMalloc( &d_r, rad.size() * sizeof( double ) );
+    cudaMemcpy( d_x, xyz.data(), xyz.size() * sizeof( double ), cudaMemcpyHostToDevice );
+    cudaMemcpy( d_r, rad.data(), rad.size() * sizeof( double ), cudaMemcpyHostToDevice );
+    Cabana::View2D<double, 3> position( d_x, n );
+    Cabana::View2D<double, 1> radii( d_r, n );
+    std::array<double, 3> grid_min = { 0.0, 0.0, 0.0 }, grid_max = { 5.0, 5.0, 5.0 };
+    using ListType = Cabana::VerletList<Cabana::DeviceSpace, Cabana::FullNeighborTag, LayoutTag,
+                                        Cabana::TeamOpTag>;
+    ListType nlist( position, 0, position.size(), small_radius, radii, 0.5, grid_min, grid_max );
+    auto rows = copyListToHost( nlist, n );
+    for ( int p = 0; p < n; ++p )
+        EXPECT_EQ( (int)rows[p].size(), ( p == 0 || p == n - 1 ) ? 6 : 4 );
+    // the same through createVerletList and an explicit execution space (a non-default stream)
+    cudaStream_t st;
+    cudaStreamCreate( &st );
+    Cabana::DeviceExecutionSpace space( st );
+    ListType on_stream( space, position, 0, position.size(), small_radius, radii, 0.5, grid_min,
+                        grid_max );
+    space.fence();
+    auto rows2 = copyListToHost( on_stream, n );
+    EXPECT_TRUE( rows2 == rows );
+    auto made = Cabana::createVerletList<Cabana::FullNeighborTag, LayoutTag, Cabana::TeamOpTag>(
+        position, 0, position.size(), small_radius, radii, 0.5, grid_min, grid_max );
+    EXPECT_TRUE( copyListToHost( made, n ) == rows );
+    cudaStreamDestroy( st );
+    cudaFree( d_x );
+    cudaFree( d_r );
+}
+
+// ---- ExecutionSpace overloads (Cabana_VerletList.hpp:1260-1281, :1351-1392) ----------------
+static void testExecutionSpaceOverloads()
+{
+    TestData t;
+    auto n2 = bruteForce( t );
+    cudaStream_t st;
+    cudaStreamCreateWithFlags( &st, cudaStreamNonBlocking );
+    Cabana::DeviceExecutionSpace space( st );
+    using ListType = Cabana::VerletList<Cabana::DeviceSpace, Cabana::FullNeighborTag,
+                                        Cabana::VerletLayoutCSR, Cabana::TeamVectorOpTag>;
+    ListType list;
+    list.build( space, t.positions(), 0, t.num_particle, t.test_radius, t.cell_size_ratio,
+                t.grid_min, t.grid_max );
+    auto made = Cabana::createVerletList<Cabana::FullNeighborTag, Cabana::VerletLayoutCSR,
+                                         Cabana::TeamVectorOpTag>(
+        space, t.positions(), 0, t.num_particle, t.test_radius, t.cell_size_ratio, t.grid_min,
+        t.grid_max );
+    space.fence();
+    checkFullNeighborList( list, t, n2, 0, t.num_particle );
+    checkFullNeighborList( made, t, n2, 0, t.num_particle );
+    // traversal on the same stream: RangePolicy( space, begin, end )
+    long long* d_sum = nullptr;
+    cudaMalloc( &d_sum, t.num_particle * sizeof( long long ) );
+    cudaMemsetAsync( d_sum, 0, t.num_particle * sizeof( long long ), st );
+    Cabana::RangePolicy<> policy( space, 0, t.num_particle );
+    Cabana::neighbor_parallel_for( policy, IdSumFunctor{ d_sum }, list,
+                                   Cabana::FirstNeighborsTag(), Cabana::TeamOpTag(), "on_stream" );
+    long long total = 0;
+    Cabana::neighbor_parallel_reduce( policy, IdReduceFunctor{}, list,
+                                      Cabana::FirstNeighborsTag(), Cabana::SerialOpTag(), total );
+    space.fence();
+    std::vector<long long> sums( t.num_particle );
+    cudaMemcpy( sums.data(), d_sum, sums.size() * sizeof( long long ), cudaMemcpyDeviceToHost );
+    long long expect_total = 0;
+    bool ok = true;
+    for ( std::size_t i = 0; i < t.num_particle; ++i )
+    {
+        long long e = 0;
+        for ( int j : n2[i] )
+            e += j;
+        ok = ok && sums[i] == e;
+        expect_total += e;
+    }
+    EXPECT_TRUE( ok );
+    EXPECT_EQ( total, expect_total );
+    cudaFree( d_sum );
+    cudaStreamDestroy( st );
+}
+
+// ---- for_each_neighbor, serial and team forms (Cabana_Parallel.hpp:1058-1110;
+//      neighbor_unit_test.hpp:511-590) inside a user kernel ---------------------------------
+struct AtomicIdSum
+{
+    long long* out;
+    __device__ void operator()( const int i, const int j ) const
+    {
+        atomicAdd( reinterpret_cast<unsigned long long*>( out + i ), (unsigned long long)j );
+    }
+};
+template <class ViewType>
+__global__ void k_for_each_serial( ViewType list, AtomicIdSum f, int n )
+{
+    for ( int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
+        Cabana::for_each_neighbor( i, f, list, Cabana::FirstNeighborsTag() );
+}
+template <class ViewType>
+__global__ void k_for_each_team( ViewType list, AtomicIdSum f, int n )
+{
+    const Cabana::WarpTeamMember team;
+    for ( int i = team.league_rank(); i < n; i += team.league_size() )
+        Cabana::for_each_neighbor( i, team, f, list, Cabana::FirstNeighborsTag() );
+}
+template <class LayoutTag>
+static void testForEachNeighbor()
+{
+    TestData t;
+    auto n2 = bruteForce( t );
+    using ListType = Cabana::VerletList<Cabana::DeviceSpace, Cabana::FullNeighborTag, LayoutTag,
+                                        Cabana::TeamOpTag>;
+    ListType list( t.positions(), 0, t.num_particle, t.test_radius, t.cell_size_ratio,
+                   t.grid_min, t.grid_max );
+    const int n = (int)t.num_particle;
+    long long* d_sum = nullptr;
+    cudaMalloc( &d_sum, n * sizeof( long long ) );
+    std::vector<long long> sums( n );
+    for ( int team = 0; team < 2; ++team )
+    {
+        cudaMemset( d_sum, 0, n * sizeof( long long ) );
+        if ( team )
+            k_for_each_team<<<16, 128>>>( list.deviceView(), AtomicIdSum{ d_sum }, n );
+        else
+            k_for_each_serial<<<4, 128>>>( list.deviceView(), AtomicIdSum{ d_sum }, n );
+        EXPECT_TRUE( cudaDeviceSynchronize() == cudaSuccess );
+        cudaMemcpy( sums.data(), d_sum, n * sizeof( long long ), cudaMemcpyDeviceToHost );
+        bool ok = true;
+        for ( int i = 0; i < n; ++i )
+        {
+            long long e = 0;
+            for ( int j : n2[i] )
+                e += j;
+            ok = ok && sums[i] == e;
+        }
+        EXPECT_TRUE( ok );
+    }
+    cudaFree( d_sum );
+}
+
+// ---- neighbor_parallel_reduce on a LinkedCellList (Cabana_Parallel.hpp:1596-1726;
+//      tstLinkedCellList.hpp:704-1003) -------------------------------------------------------
+struct LclPairCountReduce
+{
+    Cabana::View2D<double, 3> x;
+    double rsqr;
+    __device__ void operator()( const int i, const int j, long long& sum ) const
+    {
+        const double dx = x( i, 0 ) - x( j, 0 ), dy = x( i, 1 ) - x( j, 1 ),
+                     dz = x( i, 2 ) - x( j, 2 );
+        const double d2 = __dadd_rn( __dadd_rn( __dmul_rn( dx, dx ), __dmul_rn( dy, dy ) ),
+                                     __dmul_rn( dz, dz ) );
+        if ( d2 <= rsqr )
+            sum += 1 + j; // depends on the neighbour, so a wrong pairing cannot cancel
+    }
+};
+struct LclDistanceSumReduce
+{
+    Cabana::View2D<double, 3> x;
+    double rsqr;
+    __device__ void operator()( const int i, const int j, double& sum ) const
+    {
+        const double dx = x( i, 0 ) - x( j, 0 ), dy = x( i, 1 ) - x( j, 1 ),
+                     dz = x( i, 2 ) - x( j, 2 );
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if ( d2 <= rsqr )
+            sum += d2;
+    }
+};
+static void testLinkedCellParallelReduce()
+{
+    TestData t;
+    auto n2 = bruteForce( t );
+    const std::size_t n = t.num_particle;
+    double* d_x = nullptr;
+    cudaMalloc( &d_x, 3 * n * sizeof( double ) );
+    cudaMemcpy( d_x, t.xyz.data(), 3 * n * sizeof( double ), cudaMemcpyHostToDevice );
+    Cabana::View2D<double, 3> pos( d_x, n );
+    const double dcell = t.test_radius * t.cell_size_ratio;
+    std::array<double, 3> delta = { dcell, dcell, dcell };
+    auto lcl = Cabana::createLinkedCellList( pos, delta, t.grid_min, t.grid_max, t.test_radius,
+                                             t.cell_size_ratio );
+    long long expect = 0;
+    double expect_d2 = 0.0;
+    for ( std::size_t i = 0; i < n; ++i )
+        for ( int j : n2[i] )
+        {
+            expect += 1 + j;
+            double d2 = 0.0;
+            for ( int d = 0; d < 3; ++d )
+                d2 += ( t.xyz[3 * i + d] - t.xyz[3 * j + d] ) * ( t.xyz[3 * i + d] - t.xyz[3 * j + d] );
+            expect_d2 += d2;
+        }
+    Cabana::RangePolicy<> policy( 0, n );
+    const double rsqr = t.test_radius * t.test_radius;
+    long long got = -1;
+    Cabana::neighbor_parallel_reduce( policy, LclPairCountReduce{ pos, rsqr }, lcl,
+                                      Cabana::FirstNeighborsTag(), Cabana::SerialOpTag(), got,
+                                      "lcl_reduce_serial" );
+    EXPECT_EQ( got, expect );
+    got = -1;
+    Cabana::neighbor_parallel_reduce( policy, LclPairCountReduce{ pos, rsqr }, lcl,
+                                      Cabana::FirstNeighborsTag(), Cabana::TeamOpTag(), got,
+                                      "lcl_reduce_team" );
+    EXPECT_EQ( got, expect );
+    double got_d2 = 0.0;
+    Cabana::neighbor_parallel_reduce( policy, LclDistanceSumReduce{ pos, rsqr }, lcl,
+                                      Cabana::FirstNeighborsTag(), Cabana::TeamOpTag(), got_d2 );
+    EXPECT_TRUE( std::fabs( got_d2 - expect_d2 ) <= 1e-10 * expect_d2 );
+    // a range that was not binned is refused (the reference asserts, :1651-1652)
+    bool threw = false;
+    try
+    {
+        Cabana::RangePolicy<> part( 10, n - 10 );
+        Cabana::neighbor_parallel_reduce( part, LclPairCountReduce{ pos, rsqr }, lcl,
+                                          Cabana::FirstNeighborsTag(), Cabana::SerialOpTag(), got );
+    }
+    catch ( const std::runtime_error& )
+    {
+        threw = true;
+    }
+    EXPECT_TRUE( threw );
+    cudaFree( d_x );
+}
+
 int main()
 {
     if ( cb_device_count() < 1 )
@@ -764,6 +1005,12 @@ int main()
     testNeighborParallelFor<Cabana::VerletLayoutCSR>();
     testNeighborParallelFor<Cabana::VerletLayout2D>();
     testLinkedCellParallelFor();
+    testLinkedCellParallelReduce();
+    testNonUniformRadius<Cabana::VerletLayoutCSR>();
+    testNonUniformRadius<Cabana::VerletLayout2D>();
+    testExecutionSpaceOverloads();
+    testForEachNeighbor<Cabana::VerletLayoutCSR>();
+    testForEachNeighbor<Cabana::VerletLayout2D>();
     testBinningData();
     testNeighborHistogram();
     cudaDeviceSynchronize();

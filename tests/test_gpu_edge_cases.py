@@ -115,25 +115,30 @@ def test_handle_reuse_across_regimes(orc, cb):
 # ---------------------------------------------------------------- kernel generations
 @pytest.fixture
 def verlet_impl():
-    """Select the kernel generation for one test (the library reads CB_VERLET_IMPL per build)."""
+    """Select the kernel generation for one test (the library reads CB_VERLET_IMPL and
+    CB_TILE_STAGING per build): v0, v1, v2 (default: TMA bulk-copy staging) or v2-async (v2 with
+    the per-lane cp.async gather)."""
     import os
 
-    old = os.environ.get("CB_VERLET_IMPL")
+    old = {k: os.environ.get(k) for k in ("CB_VERLET_IMPL", "CB_TILE_STAGING")}
 
     def select(name):
-        if name in (None, "v2"):
-            os.environ.pop("CB_VERLET_IMPL", None)
-        else:
+        os.environ.pop("CB_VERLET_IMPL", None)
+        os.environ.pop("CB_TILE_STAGING", None)
+        if name == "v2-async":
+            os.environ["CB_TILE_STAGING"] = "async"
+        elif name not in (None, "v2"):
             os.environ["CB_VERLET_IMPL"] = name
 
     yield select
-    if old is None:
-        os.environ.pop("CB_VERLET_IMPL", None)
-    else:
-        os.environ["CB_VERLET_IMPL"] = old
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
-@pytest.mark.parametrize("impl", ["v0", "v1", "v2"])
+@pytest.mark.parametrize("impl", ["v0", "v1", "v2", "v2-async"])
 def test_kernel_generations_match_oracle(orc, cb, verlet_impl, impl):
     """v2 (tile kernels) is the default; v1 (refined grid + FP32 SIMT filter) and v0
     (reference-shaped exact FP64) stay selectable with CB_VERLET_IMPL and must give the same

@@ -300,3 +300,30 @@ def test_near_cutoff_adversarial_matches_structure(orc):
         assert set(vl.row(i)) <= set(n2.row(i))
     # the set is actually adversarial: a good share of pairs sit within 4 ulp of r
     assert n2.total > 100
+
+
+def test_non_uniform_radius_literal_answer(orc):
+    """testNonUniformRadius (core/unit_test/tstNeighborList.hpp:210-253): 2^3 ordered particles,
+    the first and last with radius 4.05 (reach everything but the body diagonal), the others
+    3.32 (nearest neighbours only): 6 / 4 neighbours after the fill pass.  The count pass of the
+    reference books the symmetric extra on the finder's row: 9 / 3,
+    same total."""
+    px, dx = 2, 2.5
+    xyz = np.array([[dx / 2 + dx * i, dx / 2 + dx * j, dx / 2 + dx * k]
+                    for i in range(px) for j in range(px) for k in range(px)])
+    radii = np.full(8, 3.32)
+    radii[0] = radii[7] = 4.05
+    for layout in (orc.CSR, orc.LAYOUT_2D):
+        res, cp = orc.verlet_build_radii(orc.view_from_xyz(xyz), radii, 0, 8, 3.32, 0.5,
+                                         (0.0,) * 3, (5.0,) * 3, layout=layout)
+        assert list(res.counts) == [6, 4, 4, 4, 4, 4, 4, 6]
+        assert list(cp) == [9, 3, 3, 3, 3, 3, 3, 9]
+        assert res.total == 36 and res.max_n == 6
+        # particle 1 = (0,0,1): its three edge neighbours plus particle 7 (face diagonal, found
+        # from 7's side only)
+        assert sorted(int(v) for v in res.row(1)) == [0, 3, 5, 7]
+    # equal radii reduce to the fixed-radius list
+    res, _ = orc.verlet_build_radii(orc.view_from_xyz(xyz), np.full(8, 3.32), 0, 8, 3.32, 0.5,
+                                    (0.0,) * 3, (5.0,) * 3)
+    ref = orc.verlet_build(orc.view_from_xyz(xyz), 0, 8, 3.32, 0.5, (0.0,) * 3, (5.0,) * 3)
+    assert np.array_equal(res.counts, ref.counts)
