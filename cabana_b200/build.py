@@ -107,6 +107,31 @@ def build_cpp_test(force: bool = False) -> str:
     return CPP_TEST_BIN
 
 
+CPP_COMM_SRC = os.path.join(ROOT, "tests", "cpp", "test_cabana_comm.cu")
+CPP_COMM_BIN = os.path.join(ROOT, "tests", "cpp", "test_cabana_comm.bin")
+
+
+def build_cpp_comm_test(force: bool = False) -> str:
+    """Compile the C++ test of include/Cabana_B200_Comm.hpp (Halo / Distributor over NCCL) against
+    the in-tree library and the system NCCL."""
+    build()
+    deps = [CPP_COMM_SRC, os.path.join(ROOT, "include", "Cabana_B200_Comm.hpp"),
+            os.path.join(ROOT, "include", "Cabana_B200.hpp"),
+            os.path.join(ROOT, "include", "cabana_b200.h"), LIB_PATH]
+    if (not force and os.path.exists(CPP_COMM_BIN)
+            and all(os.path.getmtime(CPP_COMM_BIN) >= os.path.getmtime(d) for d in deps)):
+        return CPP_COMM_BIN
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
+           "-ccbin", HOST_CXX, "--extended-lambda", "-I", os.path.join(ROOT, "include"),
+           CPP_COMM_SRC, "-o", CPP_COMM_BIN, "-L", LIB_DIR, "-lcabana_b200", "-lnccl",
+           "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../cabana_b200/lib", "-cudart", "shared"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("C++ comm test failed to compile")
+    return CPP_COMM_BIN
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(path)

@@ -120,14 +120,17 @@ def _world(group=None):
 class CommunicationPlan:
     """Export-built plan with the reference's neighbour ordering.
 
-    neighbors: self first, then the other ranks that we export to or import from in
-    ascending order (getUniqueTopology, Cabana_CommunicationPlanBase.hpp:374-394).
-    Export blocks and import blocks are laid out in that neighbour order
-    (:626-637; impl/Cabana_Halo_Mpi.hpp:73-101).
+    Without a topology (impl/Cabana_CommunicationPlan_Mpi.hpp:270-410): the ranks we export to in
+    ascending order, this rank swapped to the front when it sends to itself (:318-328), then the
+    ranks we only import from (the reference appends them in message-arrival order; here
+    ascending).  With a topology (`neighbor_ranks`, :105-192): getUniqueTopology
+    (Cabana_CommunicationPlanBase.hpp:374-394) -- sorted, unique, this rank swapped with the
+    first entry -- whether or not there is traffic.  Export blocks and import blocks are laid
+    out in that neighbour order (:626-637; impl/Cabana_Halo_Mpi.hpp:73-101).
     """
 
     def __init__(self, export_ranks: torch.Tensor | None, export_ids: torch.Tensor | None = None,
-                 group=None, kernels=None, plan=None):
+                 group=None, kernels=None, plan=None, neighbor_ranks=None):
         self.kernels = kernels if kernels is not None else CudaCommKernels()
         self.group = group
         self.rank, self.world = _world(group)
@@ -147,9 +150,22 @@ class CommunicationPlan:
             allc = mine.view(1, 1).cpu()
         self.export_matrix = allc  # [src, dst]
         imports = [int(allc[s, self.rank]) for s in range(self.world)]
-        others = sorted(r for r in range(self.world)
-                        if r != self.rank and (counts[r] > 0 or imports[r] > 0))
-        self.neighbors = [self.rank] + others
+        if neighbor_ranks is not None:
+            topo = sorted(set(int(r) for r in neighbor_ranks if int(r) >= 0))
+            if self.rank in topo:
+                i = topo.index(self.rank)
+                topo[0], topo[i] = topo[i], topo[0]
+            extra = [r for r in range(self.world) if r not in topo and (counts[r] > 0 or imports[r] > 0)]
+            if extra:
+                raise ValueError(f"CommunicationPlan: traffic with ranks {extra} outside the given topology")
+            self.neighbors = topo
+        else:
+            nb = [r for r in range(self.world) if counts[r] > 0]
+            if self.rank in nb:
+                i = nb.index(self.rank)
+                nb[0], nb[i] = nb[i], nb[0]
+            nb += [r for r in range(self.world) if imports[r] > 0 and r not in nb]
+            self.neighbors = nb
         self.num_export = [counts[r] for r in self.neighbors]
         self.num_import = [imports[r] for r in self.neighbors]
         # steering comes back grouped by ascending rank; re-express as neighbour-ordered blocks
@@ -261,8 +277,9 @@ class Halo(CommunicationPlan):
     """Cabana::Halo<MemorySpace, Export|Import, Nccl> (core/src/Cabana_Halo.hpp:59-268)."""
 
     def __init__(self, num_local: int, export_ids: torch.Tensor | None,
-                 export_ranks: torch.Tensor | None, group=None, kernels=None, plan=None):
-        super().__init__(export_ranks, export_ids, group, kernels, plan)
+                 export_ranks: torch.Tensor | None, group=None, kernels=None, plan=None,
+                 neighbor_ranks=None):
+        super().__init__(export_ranks, export_ids, group, kernels, plan, neighbor_ranks)
         self._num_local = int(num_local)
 
     @classmethod
@@ -308,16 +325,15 @@ def scatter(halo: Halo, field: Slice):
     back to their owners and atomically summed into them."""
     k = halo.kernels
     k.scatter_dtype(field)             # reject unsupported value types before posting anything
-    es = field.data.element_size()
-    nc = field.num_comp
+    tb = k.tuple_bytes([field])        # packed single-field tuples (4-byte types pad to 8 bytes)
     sends, recvs = {}, {}
     for r, ne, ni in zip(halo.neighbors, halo.num_export, halo.num_import):
         if ni > 0:
-            buf = torch.empty(ni * nc * es, dtype=torch.uint8, device=k.device)
+            buf = torch.empty(ni * tb, dtype=torch.uint8, device=k.device)
             k.pack_range([field], halo.numLocal() + halo.import_offset[r], ni, buf)
             sends[r] = buf
         if ne > 0:
-            recvs[r] = torch.empty(ne * nc * es, dtype=torch.uint8, device=k.device)
+            recvs[r] = torch.empty(ne * tb, dtype=torch.uint8, device=k.device)
     halo.exchange(sends, recvs)
     for r, ne in zip(halo.neighbors, halo.num_export):
         if ne > 0:
@@ -491,6 +507,12 @@ class SlabDecomposition:
         self.halo_width = float(halo_width) * (1.0 + 2.0**-40)
         self.lo = self.bounds[self.rank]
         self.hi = self.bounds[self.rank + 1]
+        # a slab thinner than the halo would need ghosts from ranks two or more away, which the
+        # nearest-neighbour topology below would silently lose
+        for g in range(self.world):
+            if self.world > 1 and self.bounds[g + 1] - self.bounds[g] < self.halo_width:
+                raise ValueError(f"SlabDecomposition: slab {g} is thinner ({self.bounds[g + 1] - self.bounds[g]:g}) "
+                                 f"than the halo width ({self.halo_width:g})")
         self.lo_rank = self.rank - 1 if self.rank > 0 else -1
         self.hi_rank = self.rank + 1 if self.rank < self.world - 1 else -1
 
@@ -514,9 +536,15 @@ class SlabDecomposition:
             if self.hi_rank >= 0:
                 counts[self.hi_rank] = n_hi
                 offsets[self.hi_rank] = max(num_local, 1)
-            return Halo(num_local, None, None, self.group, self.kernels, plan=(counts, offsets, steer))
+            return Halo(num_local, None, None, self.group, self.kernels, plan=(counts, offsets, steer),
+                        neighbor_ranks=self.topology())
         ids, ranks = self.kernels.slab_halo_select(x, num_local, lo_t, hi_t, self.lo_rank, self.hi_rank)
-        return Halo(num_local, ids, ranks, self.group, self.kernels)
+        return Halo(num_local, ids, ranks, self.group, self.kernels, neighbor_ranks=self.topology())
+
+    def topology(self):
+        """The known point-to-point topology of the slab halo (neighbour ranks incl. this one), as
+        Cabana::Grid passes it to Halo's topology constructor."""
+        return [r for r in (self.lo_rank, self.rank, self.hi_rank) if r >= 0]
 
     def create_distributor(self, x: Slice, num_local: int) -> Distributor:
         dest = self.kernels.slab_destinations(x, num_local, self.bounds)

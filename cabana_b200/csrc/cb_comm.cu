@@ -170,10 +170,12 @@ __global__ void __launch_bounds__( kBlock )
 
 // Cabana::scatter sums ghost contributions into their owners for any arithmetic slice value type
 // (impl/Cabana_Halo_Mpi.hpp:334-347, Kokkos::atomic_add on the slice's value_type).
+// recv holds one packed tuple of this single field per export slot (the layout cb_comm_pack /
+// cb_comm_pack_range write: `tuple_elems` values of T per tuple, the first num_comp used).
 template <class T>
 __global__ void __launch_bounds__( kBlock )
     k_scatter_add( FieldAccess f, const unsigned* __restrict__ steering, long long count,
-                   const T* __restrict__ recv )
+                   const T* __restrict__ recv, int tuple_elems )
 {
     T* fb = reinterpret_cast<T*>( f.base );
     for ( long long j = (long long)blockIdx.x * kBlock + threadIdx.x; j < count;
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__( kBlock )
     {
         const long long off = f.offset( (long long)steering[j] );
         for ( int c = 0; c < f.num_comp; ++c )
-            atomicAdd( fb + off + f.comp_stride * c, recv[j * f.num_comp + c] );
+            atomicAdd( fb + off + f.comp_stride * c, recv[j * tuple_elems + c] );
     }
 }
 
@@ -539,23 +541,24 @@ extern "C" int cb_comm_scatter_add_typed( const cb_field* field, const uint32_t*
     const int grid = launch_grid_for( count, kBlock );
     cudaStream_t stream = (cudaStream_t)stream_;
     const FieldAccess f = make_access( *field );
+    const int te = (int)( cb_comm_tuple_bytes( field, 1 ) / field->elem_bytes );
     switch ( dtype )
     {
     case CB_DTYPE_F64:
         k_scatter_add<double><<<grid, kBlock, 0, stream>>>( f, steering, count,
-                                                            (const double*)recv_buffer );
+                                                            (const double*)recv_buffer, te );
         break;
     case CB_DTYPE_F32:
         k_scatter_add<float><<<grid, kBlock, 0, stream>>>( f, steering, count,
-                                                           (const float*)recv_buffer );
+                                                           (const float*)recv_buffer, te );
         break;
     case CB_DTYPE_I32:
         k_scatter_add<int><<<grid, kBlock, 0, stream>>>( f, steering, count,
-                                                         (const int*)recv_buffer );
+                                                         (const int*)recv_buffer, te );
         break;
     default: // two's complement: the unsigned 64-bit atomic adds signed values correctly
         k_scatter_add<unsigned long long><<<grid, kBlock, 0, stream>>>(
-            f, steering, count, (const unsigned long long*)recv_buffer );
+            f, steering, count, (const unsigned long long*)recv_buffer, te );
         break;
     }
     CB_CHECK_LAUNCH();

@@ -395,11 +395,14 @@ int cb_comm_pack(const cb_field* fields_h, int num_fields, const uint32_t* steer
 /* field(dst_begin + j) = recv_buffer[j]  (gather unpack / migrate unpack) */
 int cb_comm_unpack(const cb_field* fields_h, int num_fields, int64_t dst_begin,
                    int64_t count, const void* recv_buffer, cb_stream_t stream);
-/* scatter: field(steering[j]) += recv_buffer[j]  (atomic add; doubles only) */
+/* scatter: field(steering[j]) += recv_buffer[j]  (atomic add; doubles only: tuples of
+ * num_comp doubles, no padding) */
 int cb_comm_scatter_add(const cb_field* field_h, const uint32_t* steering,
                         int64_t count, const void* recv_buffer, cb_stream_t stream);
 /* The same for every arithmetic slice value type Cabana::scatter accepts
- * (impl/Cabana_Halo_Mpi.hpp:334-347): recv_buffer holds count*num_comp values of `dtype`. */
+ * (impl/Cabana_Halo_Mpi.hpp:334-347): recv_buffer holds `count` packed tuples of this ONE field
+ * in the layout cb_comm_pack / cb_comm_pack_range write (cb_comm_tuple_bytes(field, 1) bytes per
+ * tuple: num_comp values of `dtype`, padded to 8 bytes). */
 enum { CB_DTYPE_F64 = 0, CB_DTYPE_F32 = 1, CB_DTYPE_I32 = 2, CB_DTYPE_I64 = 3 };
 int cb_comm_scatter_add_typed(const cb_field* field_h, const uint32_t* steering,
                               int64_t count, const void* recv_buffer, int dtype,

@@ -85,14 +85,21 @@ def test_pack_unpack_scatter(mods, layout):
     np.add.at(exp, st, contrib)
     assert np.allclose(f.to_array().cpu().numpy(), exp, rtol=1e-13, atol=1e-13)
     # the other value types Cabana::scatter sums (typed atomic adds) and pack_range
-    for dt, tol in ((np.float32, 1e-5), (np.int32, 0), (np.int64, 0)):
-        ft = mk(np.zeros((n, 2), dtype=dt))
+    for dt, tol, nc in ((np.float32, 1e-5, 3), (np.int32, 0, 1), (np.int64, 0, 2), (np.float32, 1e-5, 2)):
+        ft = mk(np.zeros((n, nc), dtype=dt))
         if dt == np.float32:
-            ct = rng.random((777, 2)).astype(dt)
+            ct = rng.random((777, nc)).astype(dt)
         else:
-            ct = rng.integers(-1000, 1000, (777, 2)).astype(dt)
-        k.scatter_add(ft, steering, 777, torch.from_numpy(ct).cuda().view(torch.uint8).reshape(-1))
-        et = np.zeros((n, 2), dtype=np.float64)
+            ct = rng.integers(-1000, 1000, (777, nc)).astype(dt)
+        # the receive buffer of a scatter holds packed single-field tuples (4-byte types with an
+        # odd component count are padded to 8 bytes): produce it the way the sender does
+        src = mk(ct)
+        tbs = k.tuple_bytes([src])
+        assert tbs == ((nc * ct.itemsize + 7) // 8) * 8
+        cbuf = torch.zeros(777 * tbs, dtype=torch.uint8, device="cuda")
+        k.pack_range([src], 0, 777, cbuf)
+        k.scatter_add(ft, steering, 777, cbuf)
+        et = np.zeros((n, nc), dtype=np.float64)
         np.add.at(et, st, ct.astype(np.float64))
         assert np.allclose(ft.to_array().cpu().numpy().astype(np.float64), et, rtol=tol, atol=tol)
     buf2 = torch.zeros(300 * tb, dtype=torch.uint8, device="cuda")
