@@ -72,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         sys.stderr.write("\n".join(log))
         raise RuntimeError("nvcc failed; see cabana_b200/lib/build.log")
-    link = [NVCC, "-shared", "-ccbin", HOST_CXX, "-o", LIB_PATH, *objs, "-cudart", "shared"]
+    link = [NVCC, "-shared", "-ccbin", HOST_CXX, "-o", LIB_PATH, *objs, "-cudart", "shared", "-ldl"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
@@ -98,7 +98,7 @@ def build_cpp_test(force: bool = False) -> str:
         return CPP_TEST_BIN
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
            "-ccbin", HOST_CXX, "--extended-lambda", "-I", os.path.join(ROOT, "include"),
-           CPP_TEST_SRC, "-o", CPP_TEST_BIN, "-L", LIB_DIR, "-lcabana_b200",
+           CPP_TEST_SRC, "-o", CPP_TEST_BIN, "-L", LIB_DIR, "-lcabana_b200", "-ldl",
            "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../cabana_b200/lib", "-cudart", "shared"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -123,7 +123,7 @@ def build_cpp_comm_test(force: bool = False) -> str:
         return CPP_COMM_BIN
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
            "-ccbin", HOST_CXX, "--extended-lambda", "-I", os.path.join(ROOT, "include"),
-           CPP_COMM_SRC, "-o", CPP_COMM_BIN, "-L", LIB_DIR, "-lcabana_b200", "-lnccl",
+           CPP_COMM_SRC, "-o", CPP_COMM_BIN, "-L", LIB_DIR, "-lcabana_b200", "-lnccl", "-ldl",
            "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../cabana_b200/lib", "-cudart", "shared"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -356,8 +356,8 @@ struct CommScratch
 };
 CommScratch& scratch()
 {
-    static thread_local CommScratch s;
-    return s;
+    static thread_local CommScratch s[kMaxDevices];
+    return s[current_device_slot()];
 }
 
 } // namespace
@@ -793,6 +793,7 @@ extern "C" int cb_slab_halo_push( const cb_positions* x, const cb_field* fields,
                                   int64_t capacity_tuples, uint64_t sequence,
                                   uint32_t* steer_scratch, cb_stream_t stream_ )
 {
+    ScopedRegion region( "Cabana::gather" );
     FieldSet fs;
     CB_TRY( make_field_set( fields, num_fields, fs ) );
     if ( !x || !steer_scratch || num_local < 0 || num_local > x->n || x->vlen < 1 ||
@@ -842,6 +843,7 @@ extern "C" int cb_slab_halo_wait( cb_p2p_window* from_lo, cb_p2p_window* from_hi
                                   uint64_t sequence, int64_t* counts_h, const void** data_lo,
                                   const void** data_hi, cb_stream_t stream_ )
 {
+    ScopedRegion region( "Cabana::gather" );
     if ( !counts_h || !data_lo || !data_hi )
         return fail( CB_ERR_INVALID, "cb_slab_halo_wait: null argument" );
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -7,6 +7,8 @@
 
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/cabana_b200.h"
 
 namespace cb
@@ -32,6 +34,29 @@ int cuda_fail( cudaError_t err, const char* what, const char* file, int line );
         if ( cb_rc__ != CB_OK )                                                \
             return cb_rc__;                                                    \
     } while ( 0 )
+
+// Tracing range with the reference's region names (Kokkos::Profiling::ScopedRegion in
+// Cabana_VerletList.hpp:1377, Cabana_LinkedCellList.hpp:655, Cabana_Parallel.hpp:259,
+// Cabana_Sort.hpp:557, impl/Cabana_Halo_Mpi.hpp:48): NVTX, visible to nsys / ncu --nvtx.
+struct ScopedRegion
+{
+    explicit ScopedRegion( const char* name ) { nvtxRangePushA( name ); }
+    ~ScopedRegion() { nvtxRangePop(); }
+    ScopedRegion( const ScopedRegion& ) = delete;
+    ScopedRegion& operator=( const ScopedRegion& ) = delete;
+};
+
+// Scratch that outlives a call is kept PER DEVICE (function attributes and allocations belong
+// to the device that was current when they were made; a process may cb_set_device() between
+// calls).
+constexpr int kMaxDevices = 64;
+inline int current_device_slot()
+{
+    int d = 0;
+    if ( cudaGetDevice( &d ) != cudaSuccess || d < 0 )
+        d = 0;
+    return d < kMaxDevices ? d : kMaxDevices - 1;
+}
 
 void note_launch();
 #define CB_CHECK_LAUNCH()                                                      \

@@ -210,6 +210,7 @@ extern "C" int cb_lcl_create( cb_lcl** out, const double* delta_h, const double*
 extern "C" int cb_lcl_build( cb_lcl* l, const cb_positions* x, int64_t begin,
                              int64_t end, cb_stream_t stream_ )
 {
+    ScopedRegion region( "Cabana::LinkedCellList::build" );
     if ( !l || !x )
         return fail( CB_ERR_INVALID, "cb_lcl_build: null argument" );
     // asserts of the reference (:659-660)
@@ -296,10 +297,12 @@ extern "C" int cb_binning_permute( int64_t begin, int64_t end, const uint32_t* p
                                    const cb_field* fields, int num_fields,
                                    cb_stream_t stream_ )
 {
+    ScopedRegion region( "Cabana::permute" );
     if ( begin < 0 || end < begin || ( end > begin && !permute ) ||
          ( num_fields > 0 && !fields ) )
         return fail( CB_ERR_INVALID, "cb_binning_permute: bad argument" );
-    static cb::DeviceBuffer scratch; // single caller per GPU (see cabana_b200.h)
+    static cb::DeviceBuffer scratch_of[cb::kMaxDevices]; // single caller per GPU (cabana_b200.h)
+    cb::DeviceBuffer& scratch = scratch_of[cb::current_device_slot()];
     return permute_fields( begin, end, permute, fields, num_fields, scratch,
                            (cudaStream_t)stream_, "cb_binning_permute: bad field descriptor" );
 }
@@ -307,6 +310,7 @@ extern "C" int cb_binning_permute( int64_t begin, int64_t end, const uint32_t* p
 extern "C" int cb_lcl_permute( cb_lcl* l, const cb_field* fields, int num_fields,
                                cb_stream_t stream_ )
 {
+    ScopedRegion region( "Cabana::permute" );
     if ( !l || ( num_fields > 0 && !fields ) )
         return fail( CB_ERR_INVALID, "cb_lcl_permute: null argument" );
     if ( !l->built )

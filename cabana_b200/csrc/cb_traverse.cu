@@ -493,11 +493,11 @@ using namespace cb;
 
 namespace
 {
-// packed positions scratch (grow-only, one per process: the library is single-caller per GPU)
+// packed positions scratch (grow-only, one per device: the library is single-caller per GPU)
 cb::DeviceBuffer& packed_scratch()
 {
-    static cb::DeviceBuffer b;
-    return b;
+    static cb::DeviceBuffer b[cb::kMaxDevices];
+    return b[cb::current_device_slot()];
 }
 
 int pack_positions( const cb_positions* x, cudaStream_t stream, Packed& out )
@@ -521,6 +521,7 @@ extern "C" int cb_neighbor_for_lj( const cb_verlet_view* list, const cb_position
                                    double rc, int newton, int op, int64_t begin,
                                    int64_t end, cb_stream_t stream_ )
 {
+    ScopedRegion region( "Cabana::neighbor_parallel_for" );
     CB_TRY( check_list( list, begin, end, "cb_neighbor_for_lj: bad list or range" ) );
     if ( !x || !f || x->vlen < 1 || f->vlen < 1 )
         return fail( CB_ERR_INVALID, "cb_neighbor_for_lj: null argument" );
@@ -566,6 +567,7 @@ extern "C" int cb_neighbor_reduce_lj( const cb_verlet_view* list, const cb_posit
                                       int op, int64_t begin, int64_t end,
                                       double* energy_h, cb_stream_t stream_ )
 {
+    ScopedRegion region( "Cabana::neighbor_parallel_reduce" );
     CB_TRY( check_list( list, begin, end, "cb_neighbor_reduce_lj: bad list or range" ) );
     if ( !x || !energy_h || x->vlen < 1 || x->n < list->n )
         return fail( CB_ERR_INVALID, "cb_neighbor_reduce_lj: null argument" );
@@ -604,6 +606,7 @@ extern "C" int cb_neighbor_for_id_sum( const cb_verlet_view* list, int64_t* resu
                                        int op, int64_t begin, int64_t end,
                                        cb_stream_t stream_ )
 {
+    ScopedRegion region( "Cabana::neighbor_parallel_for" );
     CB_TRY( check_list( list, begin, end, "cb_neighbor_for_id_sum: bad list or range" ) );
     if ( !result )
         return fail( CB_ERR_INVALID, "cb_neighbor_for_id_sum: null argument" );
@@ -627,6 +630,7 @@ extern "C" int cb_lcl_neighbor_for_lj( const cb_lcl* lcl, const cb_positions* x,
                                        const cb_field* f, double eps, double sigma, double rc,
                                        int op, int64_t begin, int64_t end, cb_stream_t stream_ )
 {
+    ScopedRegion region( "Cabana::neighbor_parallel_for" );
     LclAccess l;
     CB_TRY( lcl_access( lcl, l ) );
     if ( !x || !f || x->vlen < 1 || f->vlen < 1 || f->elem_bytes != 8 || f->num_comp != 3 )
@@ -658,6 +662,7 @@ extern "C" int cb_lcl_neighbor_for_count( const cb_lcl* lcl, const cb_positions*
                                           double cutoff, int32_t* result, int op,
                                           int64_t begin, int64_t end, cb_stream_t stream_ )
 {
+    ScopedRegion region( "Cabana::neighbor_parallel_for" );
     LclAccess l;
     CB_TRY( lcl_access( lcl, l ) );
     if ( !x || !result || x->vlen < 1 )

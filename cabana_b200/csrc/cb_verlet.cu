@@ -19,7 +19,6 @@
 // reference's, so every in/out decision matches bit for bit by construction.
 #include <new>
 #include <utility>
-#include <vector>
 
 #include <math.h>
 #include <stdlib.h>
@@ -437,7 +436,7 @@ struct cb_verlet
     DeviceBuffer worklist, tmp, tmp_off, ctrl;
     // v2 (tile) workspace
     DeviceBuffer block_tiles, tile_base, recs, spans, tile_chunks, chunk_off, masks, cellslot,
-        pads, tau_tab, cnt_sorted, dst_sorted;
+        pads, cnt_sorted, dst_sorted;
     DeviceBuffer row_cursor; // per-row fill positions (per-particle radius build)
     DeviceBuffer host_stage; // device copy of host positions (build_host)
     PinnedScalars pinned;
@@ -590,20 +589,8 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
         memcpy( &lo, &hb, 4 );
         a.r2hi = hi;
         a.r2lo = lo;
-        // tau = twice the proven bound; one entry per number of z cells one origin serves
-        // (a tile: <= zb cells; the CTA kernel stages up to 8 tiles under one origin)
-        const int ntab = 8 * tg.zb + 2;
-        std::vector<float> tab( (size_t)ntab );
-        for ( int k = 0; k < ntab; ++k )
-            tab[(size_t)k] =
-                nextafterf( (float)( 2.0 * tile_filter_bound( tg, radius, k ) ), INFINITY );
-        CB_TRY( v->tau_tab.ensure( sizeof( float ) * (size_t)ntab ) );
-        CB_CUDA( cudaMemcpyAsync( v->tau_tab.ptr, tab.data(), sizeof( float ) * (size_t)ntab,
-                                  cudaMemcpyHostToDevice, stream ) );
-        CB_CUDA( cudaStreamSynchronize( stream ) ); // `tab` is a stack object
-        a.tau_tab = v->tau_tab.as<float>();
-        a.tau_tab_n = ntab;
-        a.tau = tab[(size_t)tg.zb];
+        // tau = twice the proven bound for a tile whose home particles span up to zb z cells
+        a.tau = nextafterf( (float)( 2.0 * tile_filter_bound( tg, radius, tg.zb ) ), INFINITY );
         if ( diag )
             diag[1] = tile_filter_bound( tg, radius, tg.zb );
     }
@@ -721,6 +708,7 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
                                 int64_t max_neigh, int algorithm, int layout,
                                 int build_op, cb_stream_t stream_ )
 {
+    ScopedRegion region( "Cabana::VerletList::build" );
     if ( !v || !x || !grid_min || !grid_max )
         return fail( CB_ERR_INVALID, "cb_verlet_build: null argument" );
     // asserts of the reference (:1381-1382)
@@ -983,10 +971,20 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
             double vol = 1.0;
             for ( int d = 0; d < 3; ++d )
                 vol *= grid.max[d] - grid.min[d];
-            const double k_est = 4.18879 * radius * radius * radius * (double)n / vol *
-                                 ( algorithm == CB_NEIGHBOR_HALF ? 0.5 : 1.0 );
-            const double est = 1.15 * k_est * (double)n + 16.0 * (double)n + 6.0e7;
-            CB_TRY( v->tmp.ensure( sizeof( int ) * (size_t)est ) );
+            double k_est = 4.18879 * radius * radius * radius * (double)n / vol *
+                           ( algorithm == CB_NEIGHBOR_HALF ? 0.5 : 1.0 );
+            if ( k_est > (double)( n > 1 ? n - 1 : 1 ) )
+                k_est = (double)( n > 1 ? n - 1 : 1 ); // a row never holds more than n - 1 ids
+            // + the slack of the per-warp reservations of a persistent grid (a few thousand
+            // warps x a few hundred ids); the pass reports the exact need if this is short
+            double est = 1.15 * k_est * (double)n + 16.0 * (double)n + 4.0e6;
+            if ( v->tmp.ensure( sizeof( int ) * (size_t)est ) != CB_OK )
+            {
+                // too optimistic for this device: start small and let the overflow retry size it
+                (void)cudaGetLastError();
+                est = 16.0 * (double)n + 4.0e6;
+                CB_TRY( v->tmp.ensure( sizeof( int ) * (size_t)est ) );
+            }
         }
         fa.tmp_off = v->tmp_off.as<unsigned>();
         const bool binned_rows = v->row_placement == CB_ROWS_BINNED && layout == CB_LAYOUT_CSR;
@@ -1011,6 +1009,10 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
             v->mark( 4, stream );
             CB_CUDA( cudaStreamSynchronize( stream ) ); // sizes the allocation (:518-528)
             const int overflowed = (int)( stats_h[3] & 0xffffffffll );
+            // row starts inside the temporary are 32-bit
+            if ( stats_h[2] > 4294967295ll )
+                return fail( CB_ERR_OVERFLOW,
+                             "cb_verlet_build: more than 2^32 stored ids (v1 temporary)" );
             if ( !overflowed )
                 break;
             if ( attempt >= 2 )
@@ -1148,6 +1150,7 @@ extern "C" int cb_verlet_build_radii( cb_verlet* v, const cb_positions* x,
                                       int64_t max_neigh, int algorithm, int layout,
                                       int build_op, cb_stream_t stream_ )
 {
+    ScopedRegion region( "Cabana::VerletList::build" );
     if ( !v || !x || !radii || !grid_min || !grid_max )
         return fail( CB_ERR_INVALID, "cb_verlet_build_radii: null argument" );
     if ( begin < 0 || end < begin || end > x->n )

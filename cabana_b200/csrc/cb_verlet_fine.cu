@@ -916,7 +916,9 @@ int launch_fine_single( const FineArgs& a, int algorithm, cudaStream_t stream )
         long long blocks = ( items + kColWarps - 1 ) / kColWarps;
         // persistent grid: every resident CTA slot once (keeps the reservation slack of
         // the temporary buffer at warps * kReserve ids)
-        static int per_sm[2] = { 0, 0 };
+        // (per device: the attribute and the occupancy belong to the current device)
+        static int per_sm_of[kMaxDevices][2] = {};
+        int* per_sm = per_sm_of[current_device_slot()];
         if ( per_sm[half] == 0 )
         {
             int nb = 0;

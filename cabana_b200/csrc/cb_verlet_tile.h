@@ -52,9 +52,7 @@ struct TileArgs
     int R;                     // reference stencil range in user cells
     double rsqr, band;
     float r2hi, r2lo;          // tf32 split of r*r
-    float tau;                 // |c| <= tau: decided by the exact tier (one tile per origin)
-    const float* tau_tab;      // tau when the home particles of one origin span k z cells
-    int tau_tab_n;
+    float tau;                 // |c| <= tau: decided by the exact tier
     // rows
     long long n, begin, end;
     int* counts;

@@ -41,6 +41,13 @@
 
 #include "cabana_b200.h"
 
+#if defined( __has_include )
+#if __has_include( <nvtx3/nvToolsExt.h> )
+#include <nvtx3/nvToolsExt.h>
+#define CABANA_B200_HAVE_NVTX 1
+#endif
+#endif
+
 #if defined( __CUDACC__ )
 #include <cuda_runtime.h>
 #define CABANA_B200_FUNCTION __host__ __device__
@@ -112,6 +119,18 @@ class RangePolicy
 
 namespace Impl
 {
+//! Kokkos::Profiling::ScopedRegion stand-in: an NVTX range with the reference's region name.
+struct ScopedRegion
+{
+#ifdef CABANA_B200_HAVE_NVTX
+    explicit ScopedRegion( const char* name ) { nvtxRangePushA( name ); }
+    ~ScopedRegion() { nvtxRangePop(); }
+#else
+    explicit ScopedRegion( const char* ) {}
+#endif
+    ScopedRegion( const ScopedRegion& ) = delete;
+    ScopedRegion& operator=( const ScopedRegion& ) = delete;
+};
 inline void check( int rc, const char* where )
 {
     if ( rc != CB_OK )
@@ -1431,6 +1450,7 @@ inline void check_launch( const char* where )
 template <class ReduceType, class Launch>
 ReduceType run_reduce( const DeviceExecutionSpace& space, long long threads, Launch&& launch )
 {
+    ScopedRegion region( "Cabana::neighbor_parallel_reduce" ); // Cabana_Parallel.hpp:648
     constexpr int block = 256;
     const int grid = grid_for( threads, block );
     auto dev = device_alloc<ReduceType>( (std::size_t)grid + 1 );
@@ -1458,6 +1478,7 @@ inline void neighbor_parallel_for( const RangePolicy<WorkTag>& exec_policy,
                                        !is_linked_cell_list<NeighborListType>::value,
                                        int>::type* = 0 )
 {
+    Impl::ScopedRegion region( "Cabana::neighbor_parallel_for" ); // Cabana_Parallel.hpp:259
     const int b = (int)exec_policy.begin(), e = (int)exec_policy.end();
     if ( e <= b )
         return;
@@ -1476,6 +1497,7 @@ inline void neighbor_parallel_for( const RangePolicy<WorkTag>& exec_policy,
                                        !is_linked_cell_list<NeighborListType>::value,
                                        int>::type* = 0 )
 {
+    Impl::ScopedRegion region( "Cabana::neighbor_parallel_for" ); // :394
     const int b = (int)exec_policy.begin(), e = (int)exec_policy.end();
     if ( e <= b )
         return;

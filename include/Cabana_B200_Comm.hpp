@@ -424,6 +424,7 @@ struct scatter_dtype<long long>
 template <class HaloType, class... Slices>
 void gather( const HaloType& halo, const Slices&... slices )
 {
+    Impl::ScopedRegion region( "Cabana::gather" ); // impl/Cabana_Halo_Mpi.hpp:48
     auto fields = Impl::fields_of( slices... );
     for ( const auto& f : fields )
         if ( (std::size_t)f.n != halo.numLocal() + halo.numGhost() )
@@ -460,6 +461,7 @@ void gather( const HaloType& halo, const Slices&... slices )
 template <class HaloType, class SliceType>
 void scatter( const HaloType& halo, const SliceType& slice )
 {
+    Impl::ScopedRegion region( "Cabana::scatter" ); // impl/Cabana_Halo_Mpi.hpp:251
     cb_field f = slice.field();
     if ( (std::size_t)f.n != halo.numLocal() + halo.numGhost() )
         throw std::runtime_error( "Cabana::scatter: Slice is the wrong size" );
@@ -500,6 +502,7 @@ template <class DistributorType>
 void migrate_fields( const DistributorType& d, std::vector<cb_field> src,
                      std::vector<cb_field> dst )
 {
+    ScopedRegion region( "Cabana::migrate" ); // impl/Cabana_Migrate_Mpi.hpp:48
     const int nf = (int)src.size();
     const std::size_t tb = (std::size_t)cb_comm_tuple_bytes( src.data(), nf );
     cudaStream_t st = d.comm().stream();
