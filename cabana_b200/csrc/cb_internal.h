@@ -157,6 +157,8 @@ int exclusive_scan_i32( const int* in, int* out, long long n, bool write_total_a
                         long long* total_dev, DeviceBuffer& scratch,
                         cudaStream_t stream );
 // stats_dev[0] = max(in), stats_dev[1] = sum(in) (long long, device).
+int exclusive_scan_stats_i32( const int* in, int* out, long long n, long long* stats_dev,
+                              DeviceBuffer& scratch, cudaStream_t stream );
 int max_and_sum_i32( const int* in, long long n, long long* stats_dev,
                      cudaStream_t stream );
 

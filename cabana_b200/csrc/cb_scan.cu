@@ -19,8 +19,9 @@ namespace
 {
 
 constexpr int kScanThreads = 512;
-constexpr int kScanItems = 4;
-constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr int kScanVec = 4;                 // int4 vectors per thread
+constexpr int kScanItems = 4 * kScanVec;    // 16 consecutive items per thread
+constexpr int kScanTile = kScanThreads * kScanItems; // 8192 items per tile
 constexpr int kScanWarps = kScanThreads / 32;
 
 using ull = unsigned long long;
@@ -42,7 +43,8 @@ CB_D void store_status( ull* p, ull v )
 __global__ void __launch_bounds__( kScanThreads )
     k_exclusive_scan( const int* __restrict__ in, int* out, long long n,
                       int write_total_at_n, long long* total_dev, ull* status,
-                      unsigned* tile_counter, unsigned num_tiles, int aligned16 )
+                      unsigned* tile_counter, unsigned num_tiles, int aligned16,
+                      long long* stats /* optional: [0] = max (zeroed by the host), [1] = sum */ )
 {
     __shared__ unsigned s_tile;
     __shared__ long long s_warp_excl[kScanWarps];
@@ -61,17 +63,31 @@ __global__ void __launch_bounds__( kScanThreads )
     int v[kScanItems];
     if ( aligned16 && base + kScanItems <= n )
     {
-        const int4 q = *reinterpret_cast<const int4*>( in + base );
-        v[0] = q.x;
-        v[1] = q.y;
-        v[2] = q.z;
-        v[3] = q.w;
+#pragma unroll
+        for ( int k = 0; k < kScanVec; ++k )
+        {
+            const int4 q = *reinterpret_cast<const int4*>( in + base + 4 * k );
+            v[4 * k + 0] = q.x;
+            v[4 * k + 1] = q.y;
+            v[4 * k + 2] = q.z;
+            v[4 * k + 3] = q.w;
+        }
     }
     else
     {
 #pragma unroll
         for ( int e = 0; e < kScanItems; ++e )
             v[e] = ( base + e < n ) ? in[base + e] : 0;
+    }
+    if ( stats )
+    {
+        int mx = v[0];
+#pragma unroll
+        for ( int e = 1; e < kScanItems; ++e )
+            mx = max( mx, v[e] );
+        mx = warp_reduce_max( mx );
+        if ( lane == 0 && mx > 0 )
+            atomicMax( reinterpret_cast<long long*>( &stats[0] ), (long long)mx );
     }
     long long tsum = 0;
 #pragma unroll
@@ -152,6 +168,8 @@ __global__ void __launch_bounds__( kScanThreads )
             {
                 if ( total_dev )
                     *total_dev = prefix + agg;
+                if ( stats )
+                    stats[1] = prefix + agg;
                 if ( write_total_at_n )
                     out[n] = (int)( prefix + agg );
             }
@@ -162,15 +180,20 @@ __global__ void __launch_bounds__( kScanThreads )
     long long run = s_tile_prefix + s_warp_excl[warp] + ( incl - tsum );
     if ( aligned16 && base + kScanItems <= n )
     {
-        int4 q;
-        q.x = (int)run;
-        run += v[0];
-        q.y = (int)run;
-        run += v[1];
-        q.z = (int)run;
-        run += v[2];
-        q.w = (int)run;
-        *reinterpret_cast<int4*>( out + base ) = q;
+#pragma unroll
+        for ( int k = 0; k < kScanVec; ++k )
+        {
+            int4 q;
+            q.x = (int)run;
+            run += v[4 * k + 0];
+            q.y = (int)run;
+            run += v[4 * k + 1];
+            q.z = (int)run;
+            run += v[4 * k + 2];
+            q.w = (int)run;
+            run += v[4 * k + 3];
+            *reinterpret_cast<int4*>( out + base + 4 * k ) = q;
+        }
     }
     else
     {
@@ -244,12 +267,14 @@ int launch_grid_for( long long work_items, int block )
     return (int)blocks;
 }
 
-int exclusive_scan_i32( const int* in, int* out, long long n, bool write_total_at_n,
-                        long long* total_dev, DeviceBuffer& scratch,
-                        cudaStream_t stream )
+static int scan_impl( const int* in, int* out, long long n, bool write_total_at_n,
+                      long long* total_dev, long long* stats_dev, DeviceBuffer& scratch,
+                      cudaStream_t stream )
 {
     if ( n < 0 )
         return fail( CB_ERR_INVALID, "exclusive_scan_i32: n < 0" );
+    if ( stats_dev )
+        CB_CUDA( cudaMemsetAsync( stats_dev, 0, 2 * sizeof( long long ), stream ) );
     if ( n == 0 )
     {
         k_scan_empty<<<1, 1, 0, stream>>>( out, write_total_at_n ? 1 : 0, total_dev );
@@ -265,9 +290,24 @@ int exclusive_scan_i32( const int* in, int* out, long long n, bool write_total_a
     const int aligned16 = ( ( (uintptr_t)in | (uintptr_t)out ) & 15u ) == 0 ? 1 : 0;
     k_exclusive_scan<<<(unsigned)num_tiles, kScanThreads, 0, stream>>>(
         in, out, n, write_total_at_n ? 1 : 0, total_dev, status, counter,
-        (unsigned)num_tiles, aligned16 );
+        (unsigned)num_tiles, aligned16, stats_dev );
     CB_CHECK_LAUNCH();
     return CB_OK;
+}
+
+int exclusive_scan_i32( const int* in, int* out, long long n, bool write_total_at_n,
+                        long long* total_dev, DeviceBuffer& scratch,
+                        cudaStream_t stream )
+{
+    return scan_impl( in, out, n, write_total_at_n, total_dev, nullptr, scratch, stream );
+}
+
+// The same scan that also leaves max(in) in stats_dev[0] and sum(in) in stats_dev[1]
+// (processCounts needs both: Cabana_VerletList.hpp:507-523 and :536-551) in the one pass.
+int exclusive_scan_stats_i32( const int* in, int* out, long long n, long long* stats_dev,
+                              DeviceBuffer& scratch, cudaStream_t stream )
+{
+    return scan_impl( in, out, n, false, nullptr, stats_dev, scratch, stream );
 }
 
 int max_and_sum_i32( const int* in, long long n, long long* stats_dev,

@@ -636,11 +636,13 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
         if ( n > 0 )
             CB_TRY( tile_count_pass( a, half, stream ) );
         v->mark( 3, stream );
-        CB_TRY( max_and_sum_i32( v->counts.as<int>(), n, stats_dev, stream ) );
+        if ( !csr )
+            CB_TRY( max_and_sum_i32( v->counts.as<int>(), n, stats_dev, stream ) );
         if ( csr )
         {
-            CB_TRY( exclusive_scan_i32( v->counts.as<int>(), v->offsets.as<int>(), n, false,
-                                        nullptr, v->scan, stream ) );
+            // offsets + max + sum of the counts in ONE pass over them
+            CB_TRY( exclusive_scan_stats_i32( v->counts.as<int>(), v->offsets.as<int>(), n,
+                                              stats_dev, v->scan, stream ) );
             a.offsets = v->offsets.as<int>();
             if ( n > 0 )
                 CB_TRY( tile_sorted_dst( a, tg.ncells, ns_cap, v->dst_sorted.as<int>(), stream ) );

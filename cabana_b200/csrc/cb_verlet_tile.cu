@@ -355,6 +355,8 @@ __global__ void __launch_bounds__( 256 )
     }
 }
 
+// Eight threads per block share its tiles (thread `sub` takes tiles sub, sub + 8, ...).
+constexpr int kPlanSplit = 8;
 __global__ void __launch_bounds__( 128 )
     k_plan_tiles( const unsigned* __restrict__ cell_off, GridInts gi, int zb, int nzb,
                   long long nblocks, int half, const int* __restrict__ block_tiles,
@@ -362,11 +364,13 @@ __global__ void __launch_bounds__( 128 )
                   uint2* __restrict__ spans, int* __restrict__ tile_chunks,
                   long long rec_capacity )
 {
-    for ( long long b = (long long)blockIdx.x * 128 + threadIdx.x; b < nblocks;
-          b += (long long)gridDim.x * 128 )
+    for ( long long item = (long long)blockIdx.x * 128 + threadIdx.x; item < nblocks * kPlanSplit;
+          item += (long long)gridDim.x * 128 )
     {
+        const long long b = item / kPlanSplit;
+        const int sub = (int)( item - b * kPlanSplit );
         const int nt = block_tiles[b];
-        if ( nt == 0 )
+        if ( sub >= nt )
             continue;
         const long long tb = tile_base[b];
         const long long col = b / nzb;
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__( 128 )
         const unsigned p0 = cell_off[base + z0];
         const unsigned pend = cell_off[base + z1];
         int zc = z0;
-        for ( int ti = 0; ti < nt; ++ti )
+        for ( int ti = sub; ti < nt; ti += kPlanSplit )
         {
             const unsigned first = p0 + (unsigned)( ti * kTileHomes );
             const unsigned last = min( first + (unsigned)kTileHomes, pend ) - 1u;
@@ -1373,7 +1377,7 @@ int tile_plan( const TileGrid& tg, const unsigned* cell_off, bool half, int* blo
     CB_TRY( exclusive_scan_i32( block_tiles, tile_base, tg.nblocks, true, nullptr,
                                 scan_scratch, stream ) );
     CB_CUDA( cudaMemsetAsync( tile_chunks, 0, sizeof( int ) * (size_t)rec_capacity, stream ) );
-    k_plan_tiles<<<launch_grid_for( tg.nblocks, 128 ), 128, 0, stream>>>(
+    k_plan_tiles<<<launch_grid_for( tg.nblocks * kPlanSplit, 128 ), 128, 0, stream>>>(
         cell_off, gi, tg.zb, tg.nzb, tg.nblocks, half ? 1 : 0, block_tiles, tile_base, recs,
         spans, tile_chunks, rec_capacity );
     CB_CHECK_LAUNCH();
