@@ -229,37 +229,58 @@ __device__ __noinline__ double exact_c( const TileArgs& a, int pi, int pj )
 // Every column is padded with sentinel slots to a multiple of 8 plus 8, so 8-aligned windows
 // of the sorted array never leave their column.
 // ---------------------------------------------------------------------------------------
+constexpr int kBinBatch = 4; // particles per thread and round: their loads are issued together
+
 __global__ void __launch_bounds__( 256 )
     k_tbin_count( PosAccess x, Grid g, long long n, int* __restrict__ counts,
                   uint2* __restrict__ cellslot )
 {
     const unsigned lane = lane_id();
     const unsigned lt = lanemask_lt();
-    for ( long long p0 = (long long)blockIdx.x * 256; p0 < n; p0 += (long long)gridDim.x * 256 )
+    for ( long long p0 = (long long)blockIdx.x * ( 256 * kBinBatch ); p0 < n;
+          p0 += (long long)gridDim.x * ( 256 * kBinBatch ) )
     {
-        const long long p = p0 + threadIdx.x;
-        const bool valid = p < n;
-        int c = -1 - (int)lane; // unique dummy key for idle lanes
-        if ( valid )
+        double px[kBinBatch], py[kBinBatch], pz[kBinBatch];
+#pragma unroll
+        for ( int k = 0; k < kBinBatch; ++k )
         {
-            const long long off = x.offset( p );
-            int ci = locate_1d( g, 0, x.base[off] );
-            int cj = locate_1d( g, 1, x.base[off + x.comp_stride] );
-            int ck = locate_1d( g, 2, x.base[off + 2 * x.comp_stride] );
-            // points outside [min,max] are undefined behaviour in the reference; clamp
-            ci = min( max( ci, 0 ), g.nx[0] - 1 );
-            cj = min( max( cj, 0 ), g.nx[1] - 1 );
-            ck = min( max( ck, 0 ), g.nx[2] - 1 );
-            c = cardinal_index( g, ci, cj, ck );
+            const long long p = p0 + k * 256 + threadIdx.x;
+            px[k] = py[k] = pz[k] = 0.0;
+            if ( p < n )
+            {
+                const long long off = x.offset( p );
+                px[k] = x.base[off];
+                py[k] = x.base[off + x.comp_stride];
+                pz[k] = x.base[off + 2 * x.comp_stride];
+            }
         }
-        const unsigned peers = __match_any_sync( kFullMask, c );
-        const int leader = __ffs( peers ) - 1;
-        int base = 0;
-        if ( valid && (int)lane == leader )
-            base = atomicAdd( &counts[c], __popc( peers ) );
-        base = __shfl_sync( peers, base, leader );
-        if ( valid )
-            cellslot[p] = make_uint2( (unsigned)c, (unsigned)( base + __popc( peers & lt ) ) );
+#pragma unroll
+        for ( int k = 0; k < kBinBatch; ++k )
+        {
+            const long long p = p0 + k * 256 + threadIdx.x;
+            const bool valid = p < n;
+            int c = -1 - (int)lane; // unique dummy key for idle lanes
+            if ( valid )
+            {
+                int ci = locate_1d( g, 0, px[k] );
+                int cj = locate_1d( g, 1, py[k] );
+                int ck = locate_1d( g, 2, pz[k] );
+                // points outside [min,max] are undefined behaviour in the reference; clamp
+                ci = min( max( ci, 0 ), g.nx[0] - 1 );
+                cj = min( max( cj, 0 ), g.nx[1] - 1 );
+                ck = min( max( ck, 0 ), g.nx[2] - 1 );
+                c = cardinal_index( g, ci, cj, ck );
+            }
+            const unsigned peers = __match_any_sync( kFullMask, c );
+            const int leader = __ffs( peers ) - 1;
+            int base = 0;
+            if ( valid && (int)lane == leader )
+                base = atomicAdd( &counts[c], __popc( peers ) );
+            base = __shfl_sync( peers, base, leader );
+            if ( valid )
+                cellslot[p] =
+                    make_uint2( (unsigned)c, (unsigned)( base + __popc( peers & lt ) ) );
+        }
     }
 }
 
@@ -292,18 +313,42 @@ __global__ void __launch_bounds__( 256 )
                     const unsigned* __restrict__ cell_off, float4* __restrict__ q,
                     unsigned* __restrict__ permute, double ox, double oy, double oz )
 {
-    for ( long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < n;
-          p += (long long)gridDim.x * 256 )
+    for ( long long p0 = (long long)blockIdx.x * ( 256 * kBinBatch ); p0 < n;
+          p0 += (long long)gridDim.x * ( 256 * kBinBatch ) )
     {
-        const long long off = x.offset( p );
-        const double px = x.base[off];
-        const double py = x.base[off + x.comp_stride];
-        const double pz = x.base[off + 2 * x.comp_stride];
-        const uint2 cs = cellslot[p];
-        const unsigned s = cell_off[cs.x] + cs.y;
-        q[s] = make_float4( __double2float_rn( px - ox ), __double2float_rn( py - oy ),
-                            __double2float_rn( pz - oz ), __int_as_float( (int)p ) );
-        permute[s] = (unsigned)p;
+        double px[kBinBatch], py[kBinBatch], pz[kBinBatch];
+        uint2 cs[kBinBatch];
+#pragma unroll
+        for ( int k = 0; k < kBinBatch; ++k )
+        {
+            const long long p = p0 + k * 256 + threadIdx.x;
+            px[k] = py[k] = pz[k] = 0.0;
+            cs[k] = make_uint2( 0u, 0u );
+            if ( p < n )
+            {
+                const long long off = x.offset( p );
+                px[k] = x.base[off];
+                py[k] = x.base[off + x.comp_stride];
+                pz[k] = x.base[off + 2 * x.comp_stride];
+                cs[k] = cellslot[p];
+            }
+        }
+        unsigned base[kBinBatch];
+#pragma unroll
+        for ( int k = 0; k < kBinBatch; ++k )
+            base[k] = ( p0 + k * 256 + threadIdx.x < n ) ? cell_off[cs[k].x] : 0u;
+#pragma unroll
+        for ( int k = 0; k < kBinBatch; ++k )
+        {
+            const long long p = p0 + k * 256 + threadIdx.x;
+            if ( p < n )
+            {
+                const unsigned s = base[k] + cs[k].y;
+                q[s] = make_float4( __double2float_rn( px[k] - ox ), __double2float_rn( py[k] - oy ),
+                                    __double2float_rn( pz[k] - oz ), __int_as_float( (int)p ) );
+                permute[s] = (unsigned)p;
+            }
+        }
     }
 }
 
@@ -1344,7 +1389,7 @@ int tile_bin( const TileGrid& tg, const cb_positions& x, int* cell_counts, unsig
     CB_CUDA( cudaMemsetAsync( cell_counts, 0, sizeof( int ) * (size_t)tg.ncells, stream ) );
     if ( n > 0 )
     {
-        k_tbin_count<<<launch_grid_for( n, 256 ), 256, 0, stream>>>(
+        k_tbin_count<<<launch_grid_for( n, 256 * kBinBatch ), 256, 0, stream>>>(
             make_access( x ), to_grid( tg.g ), n, cell_counts, cellslot );
         CB_CHECK_LAUNCH();
     }
@@ -1355,7 +1400,7 @@ int tile_bin( const TileGrid& tg, const cb_positions& x, int* cell_counts, unsig
                                 true, nullptr, scan_scratch, stream ) );
     if ( n > 0 )
     {
-        k_tbin_scatter<<<launch_grid_for( n, 256 ), 256, 0, stream>>>(
+        k_tbin_scatter<<<launch_grid_for( n, 256 * kBinBatch ), 256, 0, stream>>>(
             make_access( x ), n, cellslot, cell_off, q, permute, tg.g.min[0], tg.g.min[1],
             tg.g.min[2] );
         CB_CHECK_LAUNCH();
