@@ -321,6 +321,21 @@ class VerletList:
             C.c_int(self.algorithm), C.c_int(self.layout), C.c_int(self.build_tag), _stream()))
         self._refresh()
 
+    def build_2d(self, x2: Slice, begin, end, neighborhood_radius, cell_size_ratio, grid_min2, grid_max2,
+                 max_neigh=0):
+        """VerletList<MemorySpace, AlgorithmTag, LayoutTag, BuildTag, 2>: positions with two
+        components, two-component grid bounds (Cabana_VerletList.hpp:377-392, :626-639)."""
+        b = 0 if begin is None else int(begin)
+        e = x2.size() if end is None else int(end)
+        d = x2.positions_desc()
+        g2 = C.c_double * 2
+        capi.check(capi.lib().cb_verlet_build_2d(
+            self._h, C.byref(d), C.c_int64(b), C.c_int64(e), C.c_double(neighborhood_radius),
+            C.c_double(cell_size_ratio), g2(*[float(v) for v in grid_min2]), g2(*[float(v) for v in grid_max2]),
+            C.c_int64(max_neigh), C.c_int(self.algorithm), C.c_int(self.layout), C.c_int(self.build_tag),
+            _stream()))
+        self._refresh()
+
     def build_host(self, x_host, begin, end, neighborhood_radius, cell_size_ratio, grid_min, grid_max,
                    max_neigh=0):
         """End-to-end entry: positions in HOST memory (numpy / pinned torch CPU tensor, (n,3))."""

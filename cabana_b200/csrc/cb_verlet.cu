@@ -377,6 +377,21 @@ int launch_radii_pass( const RadiiArgs& a, int algorithm, int layout, cudaStream
     return CB_OK;
 }
 
+// NumSpaceDim = 2 (Cabana_VerletList.hpp:377-392, :626-639): the two coordinates are copied
+// into a dense (n,3) view with z = 0.
+__global__ void __launch_bounds__( kBlock )
+    k_embed_2d( PosAccess x, long long n, double* __restrict__ out )
+{
+    for ( long long p = (long long)blockIdx.x * kBlock + threadIdx.x; p < n;
+          p += (long long)gridDim.x * kBlock )
+    {
+        const long long off = x.offset( p );
+        out[3 * p] = x.base[off];
+        out[3 * p + 1] = x.base[off + x.comp_stride];
+        out[3 * p + 2] = 0.0;
+    }
+}
+
 __global__ void k_set_neighbor( int* neighbors, const int* offsets, long long i,
                                 long long k, long long width, int value )
 {
@@ -1409,6 +1424,42 @@ extern "C" int cb_verlet_build_host( cb_verlet* v, const cb_positions* x_h,
     xd.base = v->host_stage.as<double>();
     return cb_verlet_build( v, &xd, begin, end, radius, cell_size_ratio, grid_min,
                             grid_max, max_neigh, algorithm, layout, build_op, stream_ );
+}
+
+extern "C" int cb_verlet_build_2d( cb_verlet* v, const cb_positions* x2, int64_t begin,
+                                   int64_t end, double radius, double cell_size_ratio,
+                                   const double* grid_min2, const double* grid_max2,
+                                   int64_t max_neigh, int algorithm, int layout, int build_op,
+                                   cb_stream_t stream_ )
+{
+    if ( !v || !x2 || !grid_min2 || !grid_max2 )
+        return fail( CB_ERR_INVALID, "cb_verlet_build_2d: null argument" );
+    if ( x2->vlen < 1 || x2->n < 0 || !( radius > 0.0 ) || !( cell_size_ratio > 0.0 ) )
+        return fail( CB_ERR_INVALID, "cb_verlet_build_2d: bad argument" );
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long n = x2->n;
+    CB_TRY( v->host_stage.ensure( sizeof( double ) * 3 * (size_t)( n > 0 ? n : 1 ), 1.1 ) );
+    if ( n > 0 )
+    {
+        k_embed_2d<<<launch_grid_for( n, kBlock ), kBlock, 0, stream>>>(
+            make_access( *x2 ), n, v->host_stage.as<double>() );
+        CB_CHECK_LAUNCH();
+    }
+    // Third dimension: every particle at z = 0 in the MIDDLE of the middle cell of a z range
+    // 3.5 cells wide (floor( 3.5 ) = 3 cells whatever the rounding of delta).  All particles share
+    // that z cell; its minDistanceToPoint term and every (dz * dz) are exactly +0.0, so the cell
+    // prune, the distances and the x-then-y half criterion are bit for bit the 2-D ones.
+    const double delta = cell_size_ratio * radius;
+    const double gmin[3] = { grid_min2[0], grid_min2[1], -1.75 * delta };
+    const double gmax[3] = { grid_max2[0], grid_max2[1], 1.75 * delta };
+    cb_positions x3;
+    x3.base = v->host_stage.as<double>();
+    x3.n = n;
+    x3.outer_stride = 3;
+    x3.vlen = 1;
+    x3.comp_stride = 1;
+    return cb_verlet_build( v, &x3, begin, end, radius, cell_size_ratio, gmin, gmax, max_neigh,
+                            algorithm, layout, build_op, stream_ );
 }
 
 extern "C" int cb_verlet_copy_to_host( const cb_verlet* v, int32_t* counts_h,

@@ -187,7 +187,7 @@ class Slice
     cb_positions positions() const
     {
         static_assert( std::is_same<typename std::remove_const<T>::type, double>::value,
-                       "positions are double (float positions: SURVEY.md 8f next)" );
+                       "positions are double (float positions are not instantiated)" );
         return cb_positions{ _data, (int64_t)_n, (int64_t)_stride, (int32_t)_vlen,
                              (int64_t)_vlen };
     }
@@ -439,7 +439,7 @@ struct LinkedCellListView
 template <class MemorySpace, class Scalar = double, std::size_t NumSpaceDim = 3>
 class LinkedCellList
 {
-    static_assert( NumSpaceDim == 3, "2-D space: SURVEY.md 8f (next)" );
+    static_assert( NumSpaceDim == 3 || NumSpaceDim == 2, "VerletList: 2-D or 3-D space" );
     static_assert( std::is_same<Scalar, double>::value, "float positions: SURVEY.md 8f (next)" );
 
   public:
@@ -728,7 +728,7 @@ template <class MemorySpace, class AlgorithmTag, class LayoutTag,
           class BuildTag = TeamVectorOpTag, std::size_t NumSpaceDim = 3>
 class VerletList
 {
-    static_assert( NumSpaceDim == 3, "2-D space: SURVEY.md 8f (next)" );
+    static_assert( NumSpaceDim == 3 || NumSpaceDim == 2, "VerletList: 2-D or 3-D space" );
 
   public:
     static constexpr std::size_t num_space_dim = NumSpaceDim;
@@ -799,15 +799,33 @@ class VerletList
                 const ArrayType& grid_max, const std::size_t max_neigh = 0 )
     {
         ensure_handle();
-        auto mn = Impl::to_array3( grid_min ), mx = Impl::to_array3( grid_max );
         cb_positions xd = x.positions();
-        Impl::check( cb_verlet_build( _h.get(), &xd, (int64_t)begin, (int64_t)end,
-                                      neighborhood_radius, cell_size_ratio, mn.data(),
-                                      mx.data(), (int64_t)max_neigh,
-                                      Impl::algorithm_enum<AlgorithmTag>::value,
-                                      Impl::layout_enum<LayoutTag>::value,
-                                      Impl::op_enum<BuildTag>::value, exec_space.stream() ),
-                     "Cabana::VerletList::build" );
+        if constexpr ( NumSpaceDim == 2 )
+        {
+            // NumSpaceDim = 2 (:377-392, :626-639): two-component positions and grid bounds
+            const double mn[2] = { (double)grid_min[0], (double)grid_min[1] };
+            const double mx[2] = { (double)grid_max[0], (double)grid_max[1] };
+            Impl::check( cb_verlet_build_2d( _h.get(), &xd, (int64_t)begin, (int64_t)end,
+                                             neighborhood_radius, cell_size_ratio, mn, mx,
+                                             (int64_t)max_neigh,
+                                             Impl::algorithm_enum<AlgorithmTag>::value,
+                                             Impl::layout_enum<LayoutTag>::value,
+                                             Impl::op_enum<BuildTag>::value,
+                                             exec_space.stream() ),
+                         "Cabana::VerletList::build" );
+        }
+        else
+        {
+            auto mn = Impl::to_array3( grid_min ), mx = Impl::to_array3( grid_max );
+            Impl::check( cb_verlet_build( _h.get(), &xd, (int64_t)begin, (int64_t)end,
+                                          neighborhood_radius, cell_size_ratio, mn.data(),
+                                          mx.data(), (int64_t)max_neigh,
+                                          Impl::algorithm_enum<AlgorithmTag>::value,
+                                          Impl::layout_enum<LayoutTag>::value,
+                                          Impl::op_enum<BuildTag>::value,
+                                          exec_space.stream() ),
+                         "Cabana::VerletList::build" );
+        }
         Impl::check( cb_verlet_get( _h.get(), &_view ), "cb_verlet_get" );
         fill_data( _data );
     }

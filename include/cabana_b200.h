@@ -278,6 +278,15 @@ int cb_verlet_build_radii(cb_verlet* list, const cb_positions* x, const cb_field
                           const double* grid_max_h, int64_t max_neigh, int algorithm,
                           int layout, int build_op, cb_stream_t stream);
 
+/* NumSpaceDim = 2 (VerletList<..., 2>; Cabana_VerletList.hpp:377-392, :626-639): x2 describes
+ * (n,2) positions (element (i,d), d < 2); grid_min2 / grid_max2 hold two values.  The list is
+ * built by the 3-D kernels on [x, y, 0] with one shared z cell, which reproduces the 2-D cell
+ * prune, distances and half criterion bit for bit. */
+int cb_verlet_build_2d(cb_verlet* list, const cb_positions* x2, int64_t begin, int64_t end,
+                       double neighborhood_radius, double cell_size_ratio,
+                       const double* grid_min2_h, const double* grid_max2_h, int64_t max_neigh,
+                       int algorithm, int layout, int build_op, cb_stream_t stream);
+
 /* Self-test of the tensor-core distance filter the build relies on (tests only): runs the
  * count pass over `x` with EVERY filter value compared with the exact FP64 arithmetic.
  * out_h[0] = largest |filter - exact| observed over pairs with s <= 4 r^2 (the range the bound

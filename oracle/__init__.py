@@ -413,6 +413,29 @@ def verlet_build_radii(x: PositionsView, radii, begin, end, background_radius, r
     return res, cp_counts
 
 
+def verlet_build_2d(xy: np.ndarray, begin, end, radius, ratio, gmin, gmax, algo=FULL) -> VerletResult:
+    """NumSpaceDim = 2 build (CSR): xy is an (n,2) array."""
+    xy = np.ascontiguousarray(xy, dtype=np.float64)
+    n = xy.shape[0]
+    x = PositionsView(xy.reshape(-1), n, 2, 1, 1)
+    counts = np.zeros(n, dtype=np.int32)
+    offsets = np.zeros(n, dtype=np.int32)
+    nb_ptr = C.POINTER(C.c_int)()
+    info = _VerletInfo()
+    d = x.desc()
+    g2 = (C.c_double * 2)
+    rc = lib().orc_verlet_build_2d(
+        C.byref(d), C.c_int64(begin), C.c_int64(end), C.c_double(radius), C.c_double(ratio),
+        g2(*[float(v) for v in gmin]), g2(*[float(v) for v in gmax]), C.c_int(algo),
+        counts.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p), C.byref(nb_ptr),
+        C.byref(info))
+    assert rc == 0
+    size = int(info.total)
+    nb = np.ctypeslib.as_array(nb_ptr, shape=(size,)).copy() if size > 0 else np.zeros(0, dtype=np.int32)
+    lib().orc_free(nb_ptr)
+    return VerletResult(CSR, counts, offsets, nb, int(info.total), int(info.max_n), 0, False)
+
+
 def brute_force(x: PositionsView, radius, with_neighbors=True) -> VerletResult:
     """N^2 list (core/unit_test/neighbor_unit_test.hpp:86-158), 2D row-major."""
     n = x.n

@@ -703,6 +703,128 @@ int orc_verlet_build_radii( const orc_positions* x, const double* radii, int64_t
     return 0;
 }
 
+// -----------------------------------------------------------------------------
+// 2-D VerletList build (NumSpaceDim = 2: Cabana_VerletList.hpp:377-392 / :626-639 stencil
+// loops, impl/Cabana_CartesianGrid.hpp for two dimensions, the 2-D cardinal index
+// i * ny + j (:268-275), the 2-D half criterion Cabana_NeighborList.hpp:185-190).
+// Positions: (n,2) elements described like every slice; CSR layout only (the 2D-layout
+// bookkeeping is dimension independent and covered by orc_verlet_build).
+// -----------------------------------------------------------------------------
+int orc_verlet_build_2d( const orc_positions* x, int64_t begin, int64_t end, double radius,
+                         double cell_size_ratio, const double* grid_min, const double* grid_max,
+                         int algo, int* counts, int* offsets, int** neighbors_out,
+                         orc_verlet_info* info )
+{
+    const int64_t n = x->n;
+    // CartesianGrid<double,2>::init (:61-73) for the binning grid (delta = ratio * r, :224) and
+    // the stencil grid (r * ratio, Cabana_LinkedCellList.hpp:60): the same doubles.
+    const double delta = cell_size_ratio * radius;
+    int nx[2];
+    double dx[2], rdx[2];
+    for ( int d = 0; d < 2; ++d )
+    {
+        nx[d] = cells_between( grid_max[d], grid_min[d], 1.0 / delta );
+        dx[d] = ( grid_max[d] - grid_min[d] ) / nx[d];
+        rdx[d] = 1.0 / dx[d];
+    }
+    const int cell_range = (int)std::ceil( 1 / cell_size_ratio );
+    auto locate = [&]( double p, int d )
+    {
+        int c = cells_between( p, grid_min[d], rdx[d] ); // :171-182
+        return c == nx[d] ? c - 1 : c;
+    };
+    auto min_dist = [&]( const double* xp, int i, int j )
+    {
+        // minDistanceToPoint (:207-223), two dimensions
+        const int ij[2] = { i, j };
+        double rsqr = 0.0;
+        for ( int d = 0; d < 2; ++d )
+        {
+            const double xc = grid_min[d] + ( ij[d] + 0.5 ) * dx[d];
+            const double rx = std::fabs( xp[d] - xc ) - 0.5 * dx[d];
+            const double r = rx > 0.0 ? rx : 0.0;
+            rsqr += r * r;
+        }
+        return rsqr;
+    };
+    const int64_t ncell = (int64_t)nx[0] * nx[1];
+    std::vector<int> cc( ncell, 0 );
+    std::vector<int64_t> coff( ncell + 1, 0 ), perm( n ), cell_of( n );
+    for ( int64_t p = 0; p < n; ++p )
+    {
+        const int i = locate( pos_at( x, p, 0 ), 0 ), j = locate( pos_at( x, p, 1 ), 1 );
+        cell_of[p] = (int64_t)i * nx[1] + j;
+        ++cc[cell_of[p]];
+    }
+    for ( int64_t c = 0; c < ncell; ++c )
+        coff[c + 1] = coff[c] + cc[c];
+    {
+        std::vector<int64_t> fill( coff.begin(), coff.end() - 1 );
+        for ( int64_t p = 0; p < n; ++p )
+            perm[fill[cell_of[p]]++] = p;
+    }
+    const double rsqr = radius * radius;
+    std::vector<std::vector<int>> rows( (size_t)n );
+    for ( int64_t cell = 0; cell < ncell; ++cell )
+    {
+        const int ci = (int)( cell / nx[1] ), cj = (int)( cell % nx[1] );
+        const int imin = ci - cell_range > 0 ? ci - cell_range : 0;
+        const int imax = ci + cell_range + 1 < nx[0] ? ci + cell_range + 1 : nx[0];
+        const int jmin = cj - cell_range > 0 ? cj - cell_range : 0;
+        const int jmax = cj + cell_range + 1 < nx[1] ? cj + cell_range + 1 : nx[1];
+        for ( int64_t b = coff[cell]; b < coff[cell + 1]; ++b )
+        {
+            const int64_t pid = perm[b];
+            if ( pid < begin || pid >= end )
+                continue;
+            const double xp[2] = { pos_at( x, pid, 0 ), pos_at( x, pid, 1 ) };
+            for ( int i = imin; i < imax; ++i )
+                for ( int j = jmin; j < jmax; ++j )
+                {
+                    if ( !( min_dist( xp, i, j ) <= rsqr ) )
+                        continue;
+                    const int64_t c = (int64_t)i * nx[1] + j;
+                    for ( int64_t k = coff[c]; k < coff[c + 1]; ++k )
+                    {
+                        const int64_t nid = perm[k];
+                        const double xn[2] = { pos_at( x, nid, 0 ), pos_at( x, nid, 1 ) };
+                        bool valid = pid != nid;
+                        if ( algo == ORC_HALF ) // :185-190
+                            valid = valid && ( ( xn[0] > xp[0] ) ||
+                                               ( ( xn[0] == xp[0] ) && ( xn[1] > xp[1] ) ) );
+                        if ( !valid )
+                            continue;
+                        double dist_sqr = 0.0;
+                        for ( int d = 0; d < 2; ++d )
+                        {
+                            const double dd = xp[d] - xn[d];
+                            dist_sqr += dd * dd;
+                        }
+                        if ( dist_sqr <= rsqr )
+                            rows[(size_t)pid].push_back( (int)nid );
+                    }
+                }
+        }
+    }
+    int64_t total = 0, mxn = 0;
+    for ( int64_t i = 0; i < n; ++i )
+    {
+        counts[i] = (int)rows[(size_t)i].size();
+        offsets[i] = (int)total;
+        total += counts[i];
+        mxn = std::max<int64_t>( mxn, counts[i] );
+    }
+    int* nb = (int*)std::malloc( sizeof( int ) * (size_t)std::max<int64_t>( total, 1 ) );
+    for ( int64_t i = 0; i < n; ++i )
+        std::copy( rows[(size_t)i].begin(), rows[(size_t)i].end(), nb + offsets[i] );
+    info->total = total;
+    info->max_n = mxn;
+    info->width = 0;
+    info->refilled = 0;
+    *neighbors_out = nb;
+    return 0;
+}
+
 void orc_free( void* p ) { std::free( p ); }
 
 // Order-independent 64-bit hash of every row (multiset of neighbour ids): equal hashes for

@@ -990,6 +990,62 @@ static void testLinkedCellParallelReduce()
     cudaFree( d_x );
 }
 
+// ---- NumSpaceDim = 2 (tstNeighborList.hpp testVerletListFull<2,...>) -------------------------
+template <class LayoutTag>
+static void testVerletList2d()
+{
+    const std::size_t n = 400;
+    const double r = 2.32, lo = -5.3 * 2.32, hi = 4.7 * 2.32;
+    std::vector<double> xy( 2 * n );
+    std::uint64_t s = 1234567890123ull;
+    for ( auto& v : xy )
+    {
+        s ^= s << 13;
+        s ^= s >> 7;
+        s ^= s << 17;
+        v = lo + ( hi - lo ) * ( ( s >> 11 ) * ( 1.0 / 9007199254740992.0 ) );
+    }
+    double* d_xy = nullptr;
+    cudaMalloc( &d_xy, xy.size() * sizeof( double ) );
+    cudaMemcpy( d_xy, xy.data(), xy.size() * sizeof( double ), cudaMemcpyHostToDevice );
+    Cabana::View2D<double, 2> pos( d_xy, n );
+    std::array<double, 2> gmin = { lo, lo }, gmax = { hi, hi };
+    using Full = Cabana::VerletList<Cabana::DeviceSpace, Cabana::FullNeighborTag, LayoutTag,
+                                    Cabana::TeamOpTag, 2>;
+    using Half = Cabana::VerletList<Cabana::DeviceSpace, Cabana::HalfNeighborTag, LayoutTag,
+                                    Cabana::TeamOpTag, 2>;
+    Full full( pos, 0, n, r, 0.5, gmin, gmax );
+    Half half( pos, 0, n, r, 0.5, gmin, gmax );
+    auto rf = copyListToHost( full, n );
+    auto rh = copyListToHost( half, n );
+    std::size_t tf = 0, th = 0;
+    bool ok = true;
+    for ( std::size_t i = 0; i < n; ++i )
+    {
+        std::vector<int> ef, eh;
+        for ( std::size_t j = 0; j < n; ++j )
+        {
+            if ( i == j )
+                continue;
+            const double dx = xy[2 * i] - xy[2 * j], dy = xy[2 * i + 1] - xy[2 * j + 1];
+            if ( dx * dx + dy * dy <= r * r )
+            {
+                ef.push_back( (int)j );
+                if ( xy[2 * j] > xy[2 * i] ||
+                     ( xy[2 * j] == xy[2 * i] && xy[2 * j + 1] > xy[2 * i + 1] ) )
+                    eh.push_back( (int)j );
+            }
+        }
+        ok = ok && rf[i] == ef && rh[i] == eh;
+        tf += ef.size();
+        th += eh.size();
+    }
+    EXPECT_TRUE( ok );
+    EXPECT_EQ( tf, 2 * th );
+    EXPECT_EQ( Cabana::NeighborList<Full>::totalNeighbor( full ), tf );
+    cudaFree( d_xy );
+}
+
 int main()
 {
     if ( cb_device_count() < 1 )
@@ -1011,6 +1067,8 @@ int main()
     testExecutionSpaceOverloads();
     testForEachNeighbor<Cabana::VerletLayoutCSR>();
     testForEachNeighbor<Cabana::VerletLayout2D>();
+    testVerletList2d<Cabana::VerletLayoutCSR>();
+    testVerletList2d<Cabana::VerletLayout2D>();
     testBinningData();
     testNeighborHistogram();
     cudaDeviceSynchronize();
