@@ -271,15 +271,24 @@ __global__ void __launch_bounds__( 256 )
                 ck = min( max( ck, 0 ), g.nx[2] - 1 );
                 c = cardinal_index( g, ci, cj, ck );
             }
-            const unsigned peers = __match_any_sync( kFullMask, c );
-            const int leader = __ffs( peers ) - 1;
+            // Warp aggregation only over RUNS of equal cells (neighbouring lanes): one shuffle and
+            // one ballot instead of __match_any_sync, whose all-pairs comparison stalled this
+            // kernel on the MIO queue (ncu: short-scoreboard 25 cycles per issue).  Particle arrays
+            // that are sorted or lattice-ordered put equal cells next to each other; unordered
+            // input degenerates to one atomic per particle, which is what it needs anyway.
+            const int cprev = __shfl_up_sync( kFullMask, c, 1 );
+            const bool head = lane == 0u || cprev != c;
+            const unsigned heads = __ballot_sync( kFullMask, head );
+            const unsigned below = heads & ( lt | ( 1u << lane ) );     // heads at or below me
+            const int leader = 31 - __clz( below );                    // start of my run
+            const unsigned above = heads & ~( lt | ( 1u << lane ) );    // heads above me
+            const int run_end = above ? __ffs( above ) - 1 : 32;        // one past my run
             int base = 0;
-            if ( valid && (int)lane == leader )
-                base = atomicAdd( &counts[c], __popc( peers ) );
-            base = __shfl_sync( peers, base, leader );
+            if ( valid && head )
+                base = atomicAdd( &counts[c], run_end - (int)lane );
+            base = __shfl_sync( kFullMask, base, leader );
             if ( valid )
-                cellslot[p] =
-                    make_uint2( (unsigned)c, (unsigned)( base + __popc( peers & lt ) ) );
+                cellslot[p] = make_uint2( (unsigned)c, (unsigned)( base + (int)lane - leader ) );
         }
     }
 }
