@@ -778,7 +778,13 @@ def run_ours(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": _workload_config(world) if args.workload == "cfg3" else
         {"workload": args.workload + " (BASELINE.json parity configuration, informational)",
-         "particles": int(num_local)},
+         "particles": int(num_local),
+         # per-row work spread the scheduler has to absorb (BASELINE.md section 4 asks for it on the
+         # clustered set): rows are handed out as tiles of 16 by a global ticket, so the spread
+         # shows up as tail time, not as idle SMs
+         "load_imbalance": {"max_neighbors_per_row": int(lst._data.max_n),
+                            "mean_neighbors_per_row": float(global_total) / max(int(num_local), 1),
+                            "factor_max_over_mean": float(lst._data.max_n) * int(num_local) / max(float(global_total), 1.0)}},
         "neighbors_per_step": global_total,
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -466,8 +466,9 @@ class Distributor(CommunicationPlan):
     export_ranks[i] = destination rank of element i, -1 to drop it.
     """
 
-    def __init__(self, export_ranks: torch.Tensor, group=None, kernels=None):
-        super().__init__(export_ranks, None, group, kernels)
+    def __init__(self, export_ranks: torch.Tensor, group=None, kernels=None, neighbor_ranks=None):
+        # neighbor_ranks: the topology constructor (Cabana_Distributor.hpp:103-122)
+        super().__init__(export_ranks, None, group, kernels, neighbor_ranks=neighbor_ranks)
 
 
 def migrate(distributor: Distributor, src_fields, dst_fields):
