@@ -999,20 +999,35 @@ struct __align__( 16 ) FillSmem
 
 // Expand one mask word: tile i of the chunk is bit 31 - i, and its ids sit at
 // ids2[8 * (31 - i)], so the bit position indexes the table directly.
+// bfind = position of the most significant set bit (one FLO; 31 - __clz costs two more adds).
+CB_D unsigned top_bit( unsigned m )
+{
+    unsigned p;
+    asm( "bfind.u32 %0, %1;" : "=r"( p ) : "r"( m ) );
+    return p;
+}
+// The expansion loop is the hot spot of the fill pass (one iteration per stored neighbour and
+// lane): 32-bit shared-window addresses keep it at FLO, LEA, LDS, SHF, LOP3, STS, IADD, BRA.
 CB_D void expand_word( unsigned mm, const unsigned* ids2, int* rows, int& w )
 {
+    unsigned out = smem_u32( rows + w );
+    const unsigned tab = smem_u32( ids2 );
+    w += __popc( mm );
     while ( mm )
     {
-        const int p = 31 - __clz( mm );
-        mm ^= 1u << p;
-        rows[w++] = (int)ids2[kTileCands * p];
+        const unsigned p = top_bit( mm );
+        asm( "xor.b32 %0, %0, %1;" : "+r"( mm ) : "r"( 1u << p ) ); // (in place: no copy per trip)
+        unsigned v;
+        asm volatile( "ld.shared.u32 %0, [%1];" : "=r"( v ) : "r"( tab + ( p << 5 ) ) );
+        asm volatile( "st.shared.u32 [%0], %1;" ::"r"( out ), "r"( v ) : "memory" );
+        out += 4u;
     }
 }
 CB_D void expand_word_global( unsigned mm, const unsigned* ids2, int*& out )
 {
     while ( mm )
     {
-        const int p = 31 - __clz( mm );
+        const unsigned p = top_bit( mm );
         mm ^= 1u << p;
         *out++ = (int)ids2[kTileCands * p];
     }
@@ -1104,7 +1119,8 @@ __global__ void __launch_bounds__( kBlockT, 4 )
         const int nchunks = ( T + kChunkTiles - 1 ) / kChunkTiles;
         // ids of the candidates of chunk ci, one register per 32 entries (pad slots carry -1;
         // their mask bits are zero)
-        unsigned idr[kChunkEntries / 32];
+        // (lane i takes mma tile i of the chunk: its 8 ids are 32 contiguous, aligned bytes)
+        uint4 idr[2];
         auto load_ids = [&]( int ci )
         {
             const int seg = ( ci * kChunkTiles ) / kTableTiles;
@@ -1115,13 +1131,11 @@ __global__ void __launch_bounds__( kBlockT, 4 )
                 table_seg = seg;
                 __syncwarp();
             }
-#pragma unroll
-            for ( int k = 0; k < kChunkEntries / 32; ++k )
-            {
-                const int e = (int)lane + 32 * k;
-                const int tl = min( ci * kChunkTiles + ( e >> 3 ), T - 1 );
-                idr[k] = a.permute[S.tsrc[tl & ( kTableTiles - 1 )] + (unsigned)( e & 7 )];
-            }
+            const int tl = min( ci * kChunkTiles + (int)lane, T - 1 );
+            const uint4* src =
+                reinterpret_cast<const uint4*>( a.permute + S.tsrc[tl & ( kTableTiles - 1 )] );
+            idr[0] = src[0];
+            idr[1] = src[1];
         };
 
         // Row windows [ha, hb): as many rows as fit the staging buffer (normally all 16);
@@ -1157,11 +1171,10 @@ __global__ void __launch_bounds__( kBlockT, 4 )
                 {
                     uint4 m = m_next;
                     __syncwarp(); // the previous chunk's walk is done with S.ids
-#pragma unroll
-                    for ( int k = 0; k < kChunkEntries / 32; ++k )
                     {
-                        const int e = (int)lane + 32 * k;
-                        S.ids[( 31 - ( e >> 3 ) ) * kTileCands + ( e & 7 )] = idr[k];
+                        uint4* d = reinterpret_cast<uint4*>( S.ids + ( 31 - (int)lane ) * kTileCands );
+                        d[0] = idr[0];
+                        d[1] = idr[1];
                     }
                     if ( ci + 1 < nchunks )
                     {
