@@ -482,6 +482,10 @@ def run_ours(args):
         def step():
             t0 = time.perf_counter()
             x_own = cb.Slice(x_all.data, num_local, x_all.outer_stride, x_all.vlen, x_all.comp_stride, 3)
+            if peer is not None and not trace:
+                # the whole step from one C entry: push -> wait -> unpack -> owner-local build
+                peer.step(lst, x_all, [x_all], num_local, RADIUS, CELL_RATIO, lmin, lmax)
+                return lst.total
             if peer is not None:
                 n_lo, n_hi = peer.gather(x_own, [x_all], num_local)
                 n_tot = num_local + n_lo + n_hi

@@ -649,6 +649,31 @@ class PeerHalo:
                                         C.c_int64(n_hi), data[1], st))
         return n_lo, n_hi
 
+    def step(self, lst, x_all: Slice, fields, num_local: int, neighborhood_radius, cell_size_ratio,
+             grid_min, grid_max, max_neigh=0):
+        """gather() followed by lst.build( x[0:num_local+ghosts], 0, num_local, ... ) in ONE host
+        call (cb_slab_step): push, wait, unpack and the owner-local build are issued from C.
+        `x_all` / `fields` are sized for owned + ghost tuples.  Returns (n_lo, n_hi)."""
+        L = capi.lib()
+        s = self.slab
+        self._seq += 1
+        if self._steer is None or self._steer.numel() < 2 * max(num_local, 1):
+            self._steer = torch.empty(2 * max(num_local, 1), dtype=torch.int32, device="cuda")
+        arr = (capi.Field * len(fields))(*[f.field_desc() for f in fields])
+        d = x_all.positions_desc()
+        counts = (C.c_int64 * 2)()
+        capi.check(L.cb_slab_step(
+            lst._h, C.byref(d), arr, len(fields), C.c_int64(num_local),
+            C.c_double(s.lo + s.halo_width), C.c_double(s.hi - s.halo_width),
+            self._peer[0], self._peer[1],
+            self._win[0] if s.lo_rank >= 0 else None, self._win[1] if s.hi_rank >= 0 else None,
+            C.c_int64(self.capacity), C.c_uint64(self._seq), C.c_void_p(self._steer.data_ptr()),
+            C.c_double(neighborhood_radius), C.c_double(cell_size_ratio), capi.d3(grid_min),
+            capi.d3(grid_max), C.c_int64(max_neigh), C.c_int(lst.algorithm), C.c_int(lst.layout),
+            C.c_int(lst.build_tag), counts, _stream()))
+        lst._refresh()
+        return int(counts[0]), int(counts[1])
+
     def close(self):
         torch.cuda.synchronize()
         if dist.is_initialized():

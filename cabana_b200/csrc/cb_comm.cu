@@ -644,15 +644,29 @@ struct WinLayout
 };
 
 // pack the export list of one side into a (possibly remote) window buffer
-__global__ void __launch_bounds__( kBlock )
-    k_halo_push( FieldSet fs, const unsigned* __restrict__ steering,
-                 const long long* __restrict__ total, long long capacity, char* data )
+// Both faces in ONE launch (blockIdx.y = face), and the publication folded in: every CTA fences
+// its tuples system-wide and takes a ticket; the face's last CTA writes the count, then the
+// sequence number, into the neighbour's window header (what k_halo_signal does on its own).
+struct PushFace
 {
-    const long long count = min( *total, capacity );
+    const unsigned* steering;
+    char* buf; // peer window buffer of this sequence parity (header + data), nullptr: no neighbour
+};
+__global__ void __launch_bounds__( kBlock )
+    k_halo_push_signal( FieldSet fs, PushFace lo, PushFace hi, const long long* __restrict__ totals,
+                        long long capacity, unsigned* done /* [2], zeroed */,
+                        unsigned long long seq )
+{
+    const int side = (int)blockIdx.y;
+    const PushFace face = side ? hi : lo;
+    if ( !face.buf )
+        return;
+    const long long count = min( totals[side], capacity );
+    char* data = face.buf + kWinHeader;
     for ( long long j = (long long)blockIdx.x * kBlock + threadIdx.x; j < count;
           j += (long long)gridDim.x * kBlock )
     {
-        const long long elem = (long long)steering[j];
+        const long long elem = (long long)face.steering[j];
         char* tuple = data + j * fs.tuple_bytes;
         for ( int k = 0; k < fs.num; ++k )
         {
@@ -674,16 +688,20 @@ __global__ void __launch_bounds__( kBlock )
             }
         }
     }
-}
-
-// after the pack kernel: publish (count, sequence) in the remote header
-__global__ void k_halo_signal( const long long* total, char* header, unsigned long long seq )
-{
     __threadfence_system();
-    *reinterpret_cast<volatile long long*>( header + 8 ) = *total;
-    __threadfence_system();
-    *reinterpret_cast<volatile unsigned long long*>( header ) = seq;
-    __threadfence_system();
+    __syncthreads();
+    if ( threadIdx.x == 0 )
+    {
+        const unsigned ticket = atomicAdd( done + side, 1u );
+        if ( ticket == gridDim.x - 1 )
+        {
+            __threadfence_system();
+            *reinterpret_cast<volatile long long*>( face.buf + 8 ) = totals[side];
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long*>( face.buf ) = seq;
+            __threadfence_system();
+        }
+    }
 }
 
 // receiver: bounded wait on the local header(s)
@@ -821,19 +839,16 @@ extern "C" int cb_slab_halo_push( const cb_positions* x, const cb_field* fields,
     WinLayout lay{ capacity_tuples, fs.tuple_bytes };
     const size_t parity_off = ( sequence & 1ull ) ? lay.buffer_bytes() : 0;
     // my LOWER neighbour receives my low-face particles in ITS "from_hi" window and vice
-    // versa; the caller passes the matching peer bases, so side only selects the list.
-    for ( int side = 0; side < 2; ++side )
+    // versa; the caller passes the matching peer bases, so the face only selects the list.
+    // Ghost layers are thin: a grid sized for the capacity, threads past the count exit.
+    if ( peer_lo || peer_hi )
     {
-        char* peer = (char*)( side ? peer_hi : peer_lo );
-        if ( !peer )
-            continue;
-        char* buf = peer + parity_off;
-        // ghost layers are thin: a grid sized for the capacity, threads past the count exit
-        const int grid = launch_grid_for( capacity_tuples, kBlock );
-        k_halo_push<<<grid, kBlock, 0, stream>>>( fs, side ? steer_hi : steer_lo, totals + side,
-                                                  capacity_tuples, buf + kWinHeader );
-        CB_CHECK_LAUNCH();
-        k_halo_signal<<<1, 1, 0, stream>>>( totals + side, buf, (unsigned long long)sequence );
+        const PushFace flo{ steer_lo, peer_lo ? (char*)peer_lo + parity_off : nullptr };
+        const PushFace fhi{ steer_hi, peer_hi ? (char*)peer_hi + parity_off : nullptr };
+        const dim3 grid( (unsigned)launch_grid_for( capacity_tuples, kBlock ), 2u );
+        k_halo_push_signal<<<grid, kBlock, 0, stream>>>(
+            fs, flo, fhi, totals, capacity_tuples, s.scan.as<unsigned>() + 2,
+            (unsigned long long)sequence );
         CB_CHECK_LAUNCH();
     }
     return CB_OK;
@@ -881,4 +896,43 @@ extern "C" int cb_slab_halo_wait( cb_p2p_window* from_lo, cb_p2p_window* from_hi
          ( from_hi && counts_h[1] > from_hi->lay.capacity ) )
         return fail( CB_ERR_NOMEM, "cb_slab_halo_wait: ghost layer larger than the window" );
     return CB_OK;
+}
+
+// One host entry for the sharded step: ghost selection + plan + push to the neighbours' windows
+// -> wait for theirs -> unpack behind the owned particles -> owner-local Verlet build with
+// begin = 0, end = num_local (impl/Cabana_Halo_Mpi.hpp:41-125 + Cabana_VerletList.hpp:1351-1392).
+// Two host synchronisations in all (the ghost counts; the list size).
+extern "C" int cb_slab_step( cb_verlet* list, const cb_positions* x_all, const cb_field* fields,
+                             int num_fields, int64_t num_local, double lo_thresh,
+                             double hi_thresh, void* peer_lo, void* peer_hi,
+                             cb_p2p_window* from_lo, cb_p2p_window* from_hi,
+                             int64_t capacity_tuples, uint64_t sequence,
+                             uint32_t* steer_scratch, double radius, double cell_size_ratio,
+                             const double* grid_min, const double* grid_max, int64_t max_neigh,
+                             int algorithm, int layout, int build_op, int64_t* counts_h,
+                             cb_stream_t stream )
+{
+    if ( !list || !x_all || !fields || !counts_h || num_local < 0 || num_local > x_all->n )
+        return fail( CB_ERR_INVALID, "cb_slab_step: bad argument" );
+    cb_positions x_own = *x_all;
+    x_own.n = num_local;
+    CB_TRY( cb_slab_halo_push( &x_own, fields, num_fields, num_local, lo_thresh, hi_thresh,
+                               peer_lo, peer_hi, capacity_tuples, sequence, steer_scratch,
+                               stream ) );
+    const void* data_lo = nullptr;
+    const void* data_hi = nullptr;
+    CB_TRY( cb_slab_halo_wait( from_lo, from_hi, sequence, counts_h, &data_lo, &data_hi,
+                               stream ) );
+    const int64_t n_tot = num_local + counts_h[0] + counts_h[1];
+    if ( n_tot > x_all->n )
+        return fail( CB_ERR_NOMEM, "cb_slab_step: position slice too small for the ghosts" );
+    if ( counts_h[0] > 0 )
+        CB_TRY( cb_comm_unpack( fields, num_fields, num_local, counts_h[0], data_lo, stream ) );
+    if ( counts_h[1] > 0 )
+        CB_TRY( cb_comm_unpack( fields, num_fields, num_local + counts_h[0], counts_h[1],
+                                data_hi, stream ) );
+    cb_positions x_tot = *x_all;
+    x_tot.n = n_tot;
+    return cb_verlet_build( list, &x_tot, 0, num_local, radius, cell_size_ratio, grid_min,
+                            grid_max, max_neigh, algorithm, layout, build_op, stream );
 }

@@ -458,6 +458,20 @@ int cb_slab_halo_wait(cb_p2p_window* from_lo, cb_p2p_window* from_hi, uint64_t s
                       int64_t* counts_h /* [2] */, const void** data_lo, const void** data_hi,
                       cb_stream_t stream);
 
+/* The whole sharded step in one host call (bench.py, N > 1): cb_slab_halo_push +
+ * cb_slab_halo_wait + cb_comm_unpack (lower neighbour's ghosts first) + cb_verlet_build with
+ * begin = 0, end = num_local on x_all (whose n is its CAPACITY: owned + room for ghosts; the
+ * fields must have the same capacity).  counts_h[0..1] = ghosts received from the lower / upper
+ * neighbour.  Replaces Halo construction + gather (impl/Cabana_Halo_Mpi.hpp:41-125) followed
+ * by VerletList::build (Cabana_VerletList.hpp:1351-1392). */
+int cb_slab_step(cb_verlet* list, const cb_positions* x_all, const cb_field* fields_h,
+                 int num_fields, int64_t num_local, double lo_thresh, double hi_thresh,
+                 void* peer_lo, void* peer_hi, cb_p2p_window* from_lo, cb_p2p_window* from_hi,
+                 int64_t capacity_tuples, uint64_t sequence, uint32_t* steer_scratch,
+                 double neighborhood_radius, double cell_size_ratio, const double* grid_min_h,
+                 const double* grid_max_h, int64_t max_neigh, int algorithm, int layout,
+                 int build_op, int64_t* counts_h, cb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

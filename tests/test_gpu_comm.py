@@ -244,6 +244,23 @@ def _rank_main(rank, world, port, ret):
             if it == 0:
                 peer_ok &= bool(np.array_equal(x2.to_array().cpu().numpy()[:nt], ref_x))
                 peer_ok &= bool(np.array_equal(g2.to_array().cpu().numpy()[:nt], ref_g))
+        # the whole step from one C entry (cb_slab_step): same ghosts, same list as gather + build
+        store4 = np.zeros((cap, 3))
+        store4[:nl] = ps.xyz[mine]
+        x4 = cb.slice_from_array(store4, vlen=32)
+        g4 = cb.view_from_array(gid)
+        lst4 = cb.VerletList(algorithm=cb.FULL, layout=cb.CSR)
+        n_lo, n_hi = ph.step(lst4, x4, [x4, g4], nl, r, 1.0, (lgx[0], 0.0, 0.0),
+                             (lgx[1], ps.grid_max[1], ps.grid_max[2]))
+        step_ok = (nl + n_lo + n_hi == nt)
+        step_ok &= bool(np.array_equal(x4.to_array().cpu().numpy()[:nt], ref_x))
+        c4 = lst4._data.counts.cpu().numpy()[:nl]
+        o4 = lst4._data.offsets.cpu().numpy()[:nl]
+        n4 = lst4._data.neighbors.cpu().numpy()
+        g4h = g4.to_array().cpu().numpy()[:, 0]
+        rows4 = {int(mine[i]): sorted(int(v) for v in g4h[n4[o4[i]:o4[i] + c4[i]]]) for i in range(nl)}
+        step_ok &= rows4 == out[cb.FULL]
+        out["slab_step_ok"] = bool(step_ok)
         ph.close()
         out["peer_halo_ok"] = peer_ok
         # persistent Gather / Scatter objects (Cabana_Halo.hpp:392-870) over NCCL
@@ -291,6 +308,7 @@ def test_two_gpu_slab_build_equals_single_gpu(orc):
     for r in range(world):
         assert isinstance(ret[r], dict), ret[r]
         assert ret[r]["peer_halo_ok"], "peer-memory halo differs from the send/recv halo"
+        assert ret[r]["slab_step_ok"], "cb_slab_step differs from gather + build"
         assert ret[r]["gather_obj_ok"] and ret[r]["scatter_obj_ok"]
     ps = datasets.fcc_lattice(24, jitter=0.03)
     # import-built halo: rank r received the global ids of the OTHER rank's local 5,17,3,17,250
