@@ -140,3 +140,62 @@ def test_virtual_slabs_uniform_and_forces(orc, cb, P):
         for i in range(ps.n):
             assert rows[i] == sorted(int(v) for v in ref.row(i)), (P, algo, i)
         assert np.all(np.abs(forces - f_ref) <= 1e-12 * np.maximum(fabs, 1e-300))
+
+
+def _single_rank_step(rank, port, ret):
+    import os
+
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        import oracle
+        from cabana_b200 import comm
+        from cabana_b200 import core as cb
+
+        ps = datasets.fcc_lattice(12, jitter=0.03)
+        slab = comm.SlabDecomposition([0.0, ps.grid_max[0]], ps.radius)
+        cap = ps.n + 1000
+        store = np.zeros((cap, 3))
+        store[: ps.n] = ps.xyz
+        x_all = cb.slice_from_array(store, vlen=32)
+        peer = slab.create_peer_halo([x_all], 1000)
+        lst = cb.VerletList(algorithm=cb.HALF, layout=cb.CSR)
+        ok = True
+        for _ in range(3):       # the entry is re-entrant: sequence numbers, buffers re-used
+            n_lo, n_hi = peer.step(lst, x_all, [x_all], ps.n, ps.radius, 1.0, ps.grid_min, ps.grid_max)
+            ok &= (n_lo, n_hi) == (0, 0)
+        ref = oracle.verlet_build(oracle.view_from_xyz(ps.xyz), 0, ps.n, ps.radius, 1.0, ps.grid_min,
+                                  ps.grid_max, algo=oracle.HALF)
+        counts = lst._data.counts.cpu().numpy()[: ps.n]
+        got, _ = oracle.sorted_rows_flat(oracle.CSR, counts, lst._data.offsets.cpu().numpy()[: ps.n],
+                                         lst._data.neighbors.cpu().numpy(), 0)
+        ok &= bool(np.array_equal(counts, ref.counts)) and bool(np.array_equal(got, ref.sorted_rows_flat()[0]))
+        peer.close()
+        ret[0] = bool(ok)
+    except Exception:
+        import traceback
+
+        ret[0] = traceback.format_exc()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_step_entry_single_rank(orc):
+    """cb_slab_step (push -> wait -> unpack -> build from one C entry) on a one-rank "slab
+    decomposition": no neighbours, so the step must equal a plain build; the two-rank case is
+    tests/test_gpu_comm.py::test_two_gpu_slab_build_equals_single_gpu."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_single_rank_step, args=(port, ret), nprocs=1, join=True)
+    assert ret[0] is True, ret[0]

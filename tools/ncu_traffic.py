@@ -7,6 +7,7 @@ kernel change; bench.py quotes it as roofline.traffic with the source named).
 import csv
 import io
 import json
+import re
 import subprocess
 import sys
 
@@ -29,7 +30,8 @@ def main():
     per_kernel, per_phase, other = {}, {}, {}
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]
-        short = name.split("::")[-1].split("(")[0].split("<")[0]
+        m = re.search(r"\b(k_\w+)", name)
+        short = m.group(1) if m else name.split("(")[0]
         b = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
         per_kernel.setdefault(short, []).append(b)
         for key, ph in PHASE_OF.items():
