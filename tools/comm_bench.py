@@ -27,6 +27,10 @@ import torch.distributed as dist  # noqa: E402
 
 
 def main():
+    # libraries (NCCL banner) must not pollute stdout: only the JSON line goes there
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--particles", type=int, default=1_000_000)
     ap.add_argument("--runs", type=int, default=10)
@@ -101,7 +105,7 @@ def main():
         results["fractions"][str(frac)] = out
         del dst, big
     if rank == 0:
-        print(json.dumps(results))
+        os.write(real_stdout, (json.dumps(results) + "\n").encode())
     dist.destroy_process_group()
 
 
