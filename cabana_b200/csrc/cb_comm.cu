@@ -733,6 +733,104 @@ __global__ void k_halo_wait( const char* hdr_lo, const char* hdr_hi, unsigned lo
     }
     out[2] = ok ? 0 : 1;
 }
+
+// Receiver, no host in the loop: every CTA waits (bounded) for the neighbours' publications on
+// its OWN window headers, then the grid unpacks both ghost layers behind the owned particles
+// (the lower neighbour's first: impl/Cabana_Halo_Mpi.hpp:108-121) and leaves the counts, the
+// flags and the new particle count in device memory for the build that follows on the stream.
+// blockIdx.y = face.  out[0..1] = counts as published, out[2] = flags (1 timed out, 2 a layer
+// larger than the window, 4 the slices cannot hold the ghosts), out[3] = num_local + ghosts.
+__global__ void __launch_bounds__( kBlock )
+    k_halo_wait_unpack( FieldSet fs, const char* hdr_lo, const char* hdr_hi,
+                        unsigned long long seq, long long num_local, long long capacity,
+                        long long field_n, long long* out )
+{
+    __shared__ long long s_cnt[2];
+    __shared__ int s_flags;
+    if ( threadIdx.x == 0 )
+    {
+        const long long start = clock64();
+        const long long limit = 20000000000ll; // ~10 s at 2 GHz: never hang the GPU
+        int flags = 0;
+        for ( int side = 0; side < 2; ++side )
+        {
+            const char* h = side ? hdr_hi : hdr_lo;
+            long long count = 0;
+            if ( h )
+            {
+                while ( *reinterpret_cast<const volatile unsigned long long*>( h ) != seq )
+                {
+                    if ( clock64() - start > limit )
+                    {
+                        flags |= 1;
+                        break;
+                    }
+                    __nanosleep( 100 );
+                }
+                __threadfence_system();
+                if ( !( flags & 1 ) )
+                    count = *reinterpret_cast<const volatile long long*>( h + 8 );
+            }
+            s_cnt[side] = count;
+        }
+        s_flags = flags;
+    }
+    __syncthreads();
+    int flags = s_flags;
+    long long c_lo = s_cnt[0], c_hi = s_cnt[1];
+    if ( c_lo > capacity || c_hi > capacity )
+        flags |= 2;
+    c_lo = min( max( c_lo, 0ll ), capacity );
+    c_hi = min( max( c_hi, 0ll ), capacity );
+    const long long room = max( field_n - num_local, 0ll );
+    if ( c_lo + c_hi > room )
+    {
+        flags |= 4;
+        c_lo = min( c_lo, room );
+        c_hi = min( c_hi, room - c_lo );
+    }
+    if ( blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 )
+    {
+        out[0] = s_cnt[0];
+        out[1] = s_cnt[1];
+        out[2] = flags;
+        out[3] = num_local + c_lo + c_hi;
+    }
+    const int side = (int)blockIdx.y;
+    const char* h = side ? hdr_hi : hdr_lo;
+    if ( !h )
+        return;
+    const char* data = h + kWinHeader;
+    const long long dst_begin = num_local + ( side ? c_lo : 0 );
+    const long long count = side ? c_hi : c_lo;
+    for ( long long j = (long long)blockIdx.x * kBlock + threadIdx.x; j < count;
+          j += (long long)gridDim.x * kBlock )
+    {
+        const long long elem = dst_begin + j;
+        const char* tuple = data + j * fs.tuple_bytes;
+        for ( int k = 0; k < fs.num; ++k )
+        {
+            const FieldAccess& f = fs.f[k];
+            const long long off = f.offset( elem );
+            // (L2 loads: the tuples were written by the neighbour over NVLink)
+            if ( f.elem_bytes == 8 )
+            {
+                unsigned long long* fb = reinterpret_cast<unsigned long long*>( f.base );
+                const unsigned long long* tb =
+                    reinterpret_cast<const unsigned long long*>( tuple + fs.byte_off[k] );
+                for ( int c = 0; c < f.num_comp; ++c )
+                    fb[off + f.comp_stride * c] = __ldcg( tb + c );
+            }
+            else
+            {
+                unsigned* fb = reinterpret_cast<unsigned*>( f.base );
+                const unsigned* tb = reinterpret_cast<const unsigned*>( tuple + fs.byte_off[k] );
+                for ( int c = 0; c < f.num_comp; ++c )
+                    fb[off + f.comp_stride * c] = __ldcg( tb + c );
+            }
+        }
+    }
+}
 } // namespace
 } // namespace cb
 
@@ -785,6 +883,14 @@ extern "C" int cb_p2p_window_get_handle( const cb_p2p_window* w, void* handle_h 
     cudaIpcMemHandle_t h;
     CB_CUDA( cudaIpcGetMemHandle( &h, w->base ) );
     memcpy( handle_h, &h, sizeof( h ) );
+    return CB_OK;
+}
+
+extern "C" int cb_p2p_window_local_base( const cb_p2p_window* w, void** base )
+{
+    if ( !w || !base )
+        return fail( CB_ERR_INVALID, "cb_p2p_window_local_base: null argument" );
+    *base = w->base;
     return CB_OK;
 }
 
@@ -845,7 +951,12 @@ extern "C" int cb_slab_halo_push( const cb_positions* x, const cb_field* fields,
     {
         const PushFace flo{ steer_lo, peer_lo ? (char*)peer_lo + parity_off : nullptr };
         const PushFace fhi{ steer_hi, peer_hi ? (char*)peer_hi + parity_off : nullptr };
-        const dim3 grid( (unsigned)launch_grid_for( capacity_tuples, kBlock ), 2u );
+        // (one CTA per SM and face, grid-stride: every CTA pays one system-wide fence and one
+        // ticket however many tuples it moved -- the layer's size is only known on the device)
+        long long push_ctas = launch_grid_for( capacity_tuples, kBlock );
+        if ( push_ctas > kNumSMs )
+            push_ctas = kNumSMs;
+        const dim3 grid( (unsigned)push_ctas, 2u );
         k_halo_push_signal<<<grid, kBlock, 0, stream>>>(
             fs, flo, fhi, totals, capacity_tuples, s.scan.as<unsigned>() + 2,
             (unsigned long long)sequence );
@@ -919,6 +1030,64 @@ extern "C" int cb_slab_step( cb_verlet* list, const cb_positions* x_all, const c
     CB_TRY( cb_slab_halo_push( &x_own, fields, num_fields, num_local, lo_thresh, hi_thresh,
                                peer_lo, peer_hi, capacity_tuples, sequence, steer_scratch,
                                stream ) );
+    counts_h[0] = counts_h[1] = 0;
+    const char* sync_env = getenv( "CB_SLAB_SYNC" );
+    const bool device_counts = ( from_lo || from_hi ) && cb::verlet_devcount_supported() &&
+                               !( sync_env && sync_env[0] == '1' );
+    if ( device_counts )
+    {
+        // Ghost counts never visit the host before the build: wait + unpack is one kernel that
+        // leaves the particle count on the device, the build reads it there, and the counts come
+        // back with the build's own (single, overlapped) read-back.
+        ScopedRegion region( "Cabana::gather" );
+        FieldSet fs;
+        CB_TRY( make_field_set( fields, num_fields, fs ) );
+        long long field_n = x_all->n;
+        for ( int k = 0; k < num_fields; ++k )
+            field_n = fields[k].n < field_n ? fields[k].n : field_n;
+        cudaStream_t st = (cudaStream_t)stream;
+        CommScratch& s = scratch();
+        CB_TRY( s.pinned.ensure() );
+        cb_p2p_window* any = from_lo ? from_lo : from_hi;
+        CB_TRY( any->scratch.ensure( 64 ) );
+        const size_t poff_lo =
+            from_lo ? ( ( sequence & 1ull ) ? from_lo->lay.buffer_bytes() : 0 ) : 0;
+        const size_t poff_hi =
+            from_hi ? ( ( sequence & 1ull ) ? from_hi->lay.buffer_bytes() : 0 ) : 0;
+        const char* hl = from_lo ? from_lo->base + poff_lo : nullptr;
+        const char* hh = from_hi ? from_hi->base + poff_hi : nullptr;
+        const long long cap = from_lo ? from_lo->lay.capacity : from_hi->lay.capacity;
+        if ( ( from_lo && from_lo->lay.tuple_bytes != fs.tuple_bytes ) ||
+             ( from_hi && ( from_hi->lay.tuple_bytes != fs.tuple_bytes ||
+                            from_hi->lay.capacity != cap ) ) )
+            return fail( CB_ERR_INVALID, "cb_slab_step: windows do not match the fields" );
+        long long* out = any->scratch.as<long long>();
+        const dim3 grid( (unsigned)launch_grid_for( cap, kBlock ), 2u );
+        k_halo_wait_unpack<<<grid, kBlock, 0, st>>>( fs, hl, hh, (unsigned long long)sequence,
+                                                     num_local, cap, field_n, out );
+        CB_CHECK_LAUNCH();
+        CB_CUDA( cudaMemcpyAsync( s.pinned.ptr + 8, out, 4 * sizeof( long long ),
+                                  cudaMemcpyDeviceToHost, st ) );
+        cb_positions x_tot = *x_all;
+        const long long bound = num_local + ( from_lo ? cap : 0 ) + ( from_hi ? cap : 0 );
+        x_tot.n = bound < field_n ? bound : field_n;
+        const int rc = cb::verlet_build_devcount( list, &x_tot, 0, num_local, radius,
+                                                  cell_size_ratio, grid_min, grid_max, max_neigh,
+                                                  algorithm, layout, build_op, stream, out + 3 );
+        if ( rc != CB_OK )
+            return rc;
+        // (the build waited for an event recorded after the copy above)
+        const long long flags = s.pinned.ptr[10];
+        if ( flags & 1 )
+            return fail( CB_ERR_CUDA, "cb_slab_step: timed out waiting for a neighbour's push" );
+        if ( flags & 2 )
+            return fail( CB_ERR_NOMEM, "cb_slab_step: ghost layer larger than the window" );
+        if ( flags & 4 )
+            return fail( CB_ERR_NOMEM, "cb_slab_step: position slice too small for the ghosts" );
+        counts_h[0] = s.pinned.ptr[8];
+        counts_h[1] = s.pinned.ptr[9];
+        return CB_OK;
+    }
     const void* data_lo = nullptr;
     const void* data_hi = nullptr;
     CB_TRY( cb_slab_halo_wait( from_lo, from_hi, sequence, counts_h, &data_lo, &data_hi,

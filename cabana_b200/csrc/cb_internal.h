@@ -178,6 +178,15 @@ int bin_particles( const cb_grid& grid, const cb_positions& x, long long begin,
 
 int launch_grid_for( long long work_items, int block );
 
+// cb_verlet_build with the particle count left on the device (cb_verlet.cu): x->n is then the
+// host-side BOUND every array is sized for, *n_dev (<= x->n, written earlier on the same
+// stream) the real count; [begin, end) must lie below it.  v2 kernels only.
+bool verlet_devcount_supported();
+int verlet_build_devcount( cb_verlet* v, const cb_positions* x, long long begin, long long end,
+                           double radius, double cell_size_ratio, const double* grid_min,
+                           const double* grid_max, long long max_neigh, int algorithm,
+                           int layout, int build_op, void* stream, const long long* n_dev );
+
 } // namespace cb
 
 // The LinkedCellList handle (shared by cb_lcl.cu and the LCL-direct traversal).

@@ -455,6 +455,7 @@ struct cb_verlet
     DeviceBuffer row_cursor; // per-row fill positions (per-particle radius build)
     DeviceBuffer host_stage; // device copy of host positions (build_host)
     PinnedScalars pinned;
+    cudaEvent_t ev_stats = nullptr; // "sizes are on the host" (the build's one host wait)
     // optional phase timing
     bool profiling = false;
     cudaEvent_t ev[CB_VERLET_NUM_PHASES + 1] = {};
@@ -465,6 +466,8 @@ struct cb_verlet
         if ( have_events )
             for ( auto& e : ev )
                 cudaEventDestroy( e );
+        if ( ev_stats )
+            cudaEventDestroy( ev_stats );
     }
     // mark(i): boundary i on the stream -- 0 start, 1 after binning, 2 after gather,
     // 3 after count, 4 after scan, 5 after fill.
@@ -505,8 +508,12 @@ extern "C" int cb_verlet_destroy( cb_verlet* v )
 static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, long long end,
                        double radius, const cb_grid& ugrid, int cell_range,
                        const double* grid_min, const double* grid_max, long long max_neigh,
-                       int algorithm, int layout, cudaStream_t stream, double* diag )
+                       int algorithm, int layout, cudaStream_t stream, double* diag,
+                       const long long* n_dev = nullptr )
 {
+    // n_dev (device, optional): the particle count when the host only knows the bound x->n
+    // (cb_slab_step: ghost counts stay on the GPU).  Every array is sized for x->n; rows and
+    // slots past the real count stay empty; v->n is set from the read-back below.
     const long long n = x->n;
     const size_t na = (size_t)( n > 0 ? n : 1 );
     const bool half = algorithm == CB_NEIGHBOR_HALF;
@@ -548,7 +555,7 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
     // LCL over ALL particles, not just [begin,end) (:229-235), on the internal grid
     CB_TRY( tile_bin( tg, *x, v->cell_counts.as<int>(), v->cell_off.as<unsigned>(),
                       v->cellslot.as<uint2>(), v->pads.as<unsigned char>(), v->q.as<float4>(),
-                      v->permute.as<unsigned>(), v->scan, stream ) );
+                      v->permute.as<unsigned>(), v->scan, stream, n_dev ) );
     v->mark( 1, stream );
     CB_TRY( tile_plan( tg, v->cell_off.as<unsigned>(), half, v->block_tiles.as<int>(),
                        v->tile_base.as<int>(), v->recs.as<uint4>(), v->spans.as<uint2>(),
@@ -641,6 +648,16 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
     // pass reports the exact need if it does not fit
     if ( v->masks.capacity == 0 )
         CB_TRY( v->masks.ensure( (size_t)( 128.0 * (double)n ) + ( 1u << 20 ) ) );
+    // One host wait per build, and it is off the GPU's critical path: when the list of a
+    // previous build left a neighbour array behind (the steady state of a rebuild loop), the CSR
+    // fill pass is launched BEFORE the host has seen the new size -- the kernel itself checks
+    // that the masks did not overflow and that the list fits, and leaves without writing
+    // otherwise -- so the host wakes up while the fill pass is already running.  Only when the
+    // speculation fails (first build, list grew past the 5 % slack) does the fill pass start
+    // after the read-back, as the reference's processCounts does (:507-562).
+    if ( !v->ev_stats )
+        CB_CUDA( cudaEventCreateWithFlags( &v->ev_stats, cudaEventDisableTiming ) );
+    bool filled = false;
     for ( int attempt = 0;; ++attempt )
     {
         a.masks = v->masks.as<uint4>();
@@ -669,11 +686,32 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
                                   cudaMemcpyDeviceToHost, stream ) );
         CB_CUDA( cudaMemcpyAsync( stats_h + 4, v->chunk_off.as<int>() + rec_capacity,
                                   sizeof( int ), cudaMemcpyDeviceToHost, stream ) );
+        if ( n_dev )
+            CB_CUDA( cudaMemcpyAsync( stats_h + 5, n_dev, sizeof( long long ),
+                                      cudaMemcpyDeviceToHost, stream ) );
         v->mark( 4, stream );
-        CB_CUDA( cudaStreamSynchronize( stream ) ); // sizes the allocation (:518-528)
+        CB_CUDA( cudaEventRecord( v->ev_stats, stream ) );
+        const char* spec_env = getenv( "CB_VERLET_SPECULATE" );
+        const bool speculate = csr && attempt == 0 && n > 0 &&
+                               v->neighbors.capacity >= sizeof( int ) &&
+                               !( spec_env && spec_env[0] == '0' );
+        if ( speculate )
+        {
+            a.neighbors = v->neighbors.as<int>();
+            a.width = 0;
+            a.spec_total = stats_dev + 1;
+            a.spec_capacity = (long long)( v->neighbors.capacity / sizeof( int ) );
+            a.spec_failed = reinterpret_cast<int*>( v->ctrl.as<char>() + 32 );
+            CB_TRY( tile_fill_pass( a, true, stream ) );
+            a.spec_total = nullptr;
+        }
+        CB_CUDA( cudaEventSynchronize( v->ev_stats ) ); // sizes the allocation (:518-528)
         const int overflowed = (int)( stats_h[3] & 0xffffffffll );
         if ( !overflowed )
+        {
+            filled = speculate && stats_h[1] <= (long long)( v->neighbors.capacity / sizeof( int ) );
             break;
+        }
         if ( attempt >= 1 )
             return fail( CB_ERR_NOMEM, "cb_verlet_build: mask buffer kept overflowing" );
         const long long chunks = (long long)( stats_h[4] & 0xffffffffll );
@@ -683,12 +721,15 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
     v->max_n = stats_h[0];
     v->total = stats_h[1];
     v->extent = v->total;
+    if ( n_dev )
+        v->n = stats_h[5] < n ? stats_h[5] : n;
     if ( csr )
     {
         if ( v->total > 2147483647ll )
             return fail( CB_ERR_OVERFLOW, "cb_verlet_build: total neighbours exceed INT_MAX" );
-        CB_TRY( v->neighbors.ensure( sizeof( int ) * (size_t)( v->total > 0 ? v->total : 1 ),
-                                     1.05 ) );
+        if ( !filled )
+            CB_TRY( v->neighbors.ensure( sizeof( int ) * (size_t)( v->total > 0 ? v->total : 1 ),
+                                         1.05 ) );
         a.offsets = v->offsets.as<int>();
         a.width = 0;
     }
@@ -712,7 +753,7 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
         a.width = v->width;
     }
     a.neighbors = v->neighbors.as<int>();
-    if ( n > 0 && v->total > 0 )
+    if ( !filled && n > 0 && v->total > 0 )
         CB_TRY( tile_fill_pass( a, csr, stream ) );
     v->mark( 5, stream );
     v->built = true;
@@ -725,7 +766,27 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
                                 int64_t max_neigh, int algorithm, int layout,
                                 int build_op, cb_stream_t stream_ )
 {
+    return cb::verlet_build_devcount( v, x, begin, end, radius, cell_size_ratio, grid_min,
+                                      grid_max, max_neigh, algorithm, layout, build_op, stream_,
+                                      nullptr );
+}
+
+bool cb::verlet_devcount_supported()
+{
+    const char* impl_env = getenv( "CB_VERLET_IMPL" );
+    return !( impl_env && ( strcmp( impl_env, "v0" ) == 0 || strcmp( impl_env, "v1" ) == 0 ) );
+}
+
+int cb::verlet_build_devcount( cb_verlet* v, const cb_positions* x, long long begin,
+                               long long end, double radius, double cell_size_ratio,
+                               const double* grid_min, const double* grid_max,
+                               long long max_neigh, int algorithm, int layout, int build_op,
+                               void* stream_, const long long* n_dev )
+{
     ScopedRegion region( "Cabana::VerletList::build" );
+    if ( n_dev && !verlet_devcount_supported() )
+        return fail( CB_ERR_UNSUPPORTED,
+                     "cb_verlet_build: a device-side particle count needs the v2 kernels" );
     if ( !v || !x || !grid_min || !grid_max )
         return fail( CB_ERR_INVALID, "cb_verlet_build: null argument" );
     // asserts of the reference (:1381-1382)
@@ -783,7 +844,7 @@ extern "C" int cb_verlet_build( cb_verlet* v, const cb_positions* x, int64_t beg
         v->width = 0;
         v->refilled = 0;
         return build_tile( v, x, begin, end, radius, grid, cell_range, grid_min, grid_max,
-                           max_neigh, algorithm, layout, stream, nullptr );
+                           max_neigh, algorithm, layout, stream, nullptr, n_dev );
     }
     int refine = 1;
     if ( !use_v0 )

@@ -233,8 +233,10 @@ constexpr int kBinBatch = 4; // particles per thread and round: their loads are 
 
 __global__ void __launch_bounds__( 256 )
     k_tbin_count( PosAccess x, Grid g, long long n, int* __restrict__ counts,
-                  uint2* __restrict__ cellslot )
+                  uint2* __restrict__ cellslot, const long long* __restrict__ n_dev )
 {
+    if ( n_dev )
+        n = min( n, *n_dev );
     const unsigned lane = lane_id();
     const unsigned lt = lanemask_lt();
     for ( long long p0 = (long long)blockIdx.x * ( 256 * kBinBatch ); p0 < n;
@@ -320,8 +322,11 @@ __global__ void __launch_bounds__( 256 )
 __global__ void __launch_bounds__( 256 )
     k_tbin_scatter( PosAccess x, long long n, const uint2* __restrict__ cellslot,
                     const unsigned* __restrict__ cell_off, float4* __restrict__ q,
-                    unsigned* __restrict__ permute, double ox, double oy, double oz )
+                    unsigned* __restrict__ permute, double ox, double oy, double oz,
+                    const long long* __restrict__ n_dev )
 {
+    if ( n_dev )
+        n = min( n, *n_dev );
     for ( long long p0 = (long long)blockIdx.x * ( 256 * kBinBatch ); p0 < n;
           p0 += (long long)gridDim.x * ( 256 * kBinBatch ) )
     {
@@ -1042,6 +1047,12 @@ __global__ void __launch_bounds__( kBlockT, 4 )
     const int wib = threadIdx.x >> 5;
     FillSmem& S = reinterpret_cast<FillSmem*>( s_dyn )[wib];
     const int g = (int)( lane >> 2 ), t = (int)( lane & 3u );
+    if ( a.spec_total && ( *a.spec_total > a.spec_capacity || *a.overflow != 0 ) )
+    {
+        if ( blockIdx.x == 0 && threadIdx.x == 0 )
+            *a.spec_failed = 1; // the host sizes the buffers and launches the pass again
+        return;
+    }
     const int ntiles = *a.ntiles_dev;
 
     // The kernel is bound by the latency of dependent global loads, so everything a tile needs
@@ -1405,14 +1416,14 @@ double tile_filter_bound( const TileGrid& tg, double radius, int nzc )
 
 int tile_bin( const TileGrid& tg, const cb_positions& x, int* cell_counts, unsigned* cell_off,
               uint2* cellslot, unsigned char* pads, float4* q, unsigned* permute,
-              DeviceBuffer& scan_scratch, cudaStream_t stream )
+              DeviceBuffer& scan_scratch, cudaStream_t stream, const long long* n_dev )
 {
     const long long n = x.n;
     CB_CUDA( cudaMemsetAsync( cell_counts, 0, sizeof( int ) * (size_t)tg.ncells, stream ) );
     if ( n > 0 )
     {
         k_tbin_count<<<launch_grid_for( n, 256 * kBinBatch ), 256, 0, stream>>>(
-            make_access( x ), to_grid( tg.g ), n, cell_counts, cellslot );
+            make_access( x ), to_grid( tg.g ), n, cell_counts, cellslot, n_dev );
         CB_CHECK_LAUNCH();
     }
     k_tbin_pad<<<launch_grid_for( tg.ncols * 32, 256 ), 256, 0, stream>>>( cell_counts, tg.ncols,
@@ -1424,7 +1435,7 @@ int tile_bin( const TileGrid& tg, const cb_positions& x, int* cell_counts, unsig
     {
         k_tbin_scatter<<<launch_grid_for( n, 256 * kBinBatch ), 256, 0, stream>>>(
             make_access( x ), n, cellslot, cell_off, q, permute, tg.g.min[0], tg.g.min[1],
-            tg.g.min[2] );
+            tg.g.min[2], n_dev );
         CB_CHECK_LAUNCH();
     }
     k_tbin_sentinels<<<launch_grid_for( tg.ncols + 1, 256 ), 256, 0, stream>>>(

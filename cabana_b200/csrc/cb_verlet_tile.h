@@ -61,6 +61,11 @@ struct TileArgs
     const int* offsets; // CSR row starts (fill pass); nullptr for 2D
     int* neighbors;
     long long width;    // 2D row width
+    // speculative fill (launched before the host has seen the list size): the kernel leaves
+    // without writing when the mask buffer overflowed or the list does not fit
+    const long long* spec_total; // device: total stored neighbours (nullptr: not speculative)
+    long long spec_capacity;     // ints the neighbour array holds
+    int* spec_failed;            // set when the kernel left early
     // diagnostics (cb_verlet_filter_selftest): [0] max |c_mma - c_exact| as float bits,
     // [1] number of values that missed the bound
     unsigned* diag_maxerr;
@@ -75,11 +80,14 @@ double tile_filter_bound( const TileGrid& tg, double radius, int nzc );
 
 // Fused binning on the internal grid: cell_off[ncells+1] (every column padded to a multiple
 // of 8 slots plus 8), q / permute in cell-sorted order (pad slots hold far-away sentinels and
-// id -1).  The sorted arrays need sorted_capacity(tg, n) + 8 slots.
+// id -1).  The sorted arrays need sorted_capacity(tg, n) + 8 slots.  n_dev (optional, device):
+// the particle count when the host only knows the bound x.n (ghost counts that never left the
+// GPU, cb_slab_step).
 inline long long sorted_capacity( const TileGrid& tg, long long n ) { return n + 16 * tg.ncols; }
 int tile_bin( const TileGrid& tg, const cb_positions& x, int* cell_counts, unsigned* cell_off,
               uint2* cellslot, unsigned char* pads, float4* q, unsigned* permute,
-              DeviceBuffer& scan_scratch, cudaStream_t stream );
+              DeviceBuffer& scan_scratch, cudaStream_t stream,
+              const long long* n_dev = nullptr );
 
 // Tile records + mask chunk offsets.  block_tiles/tile_base: [nblocks+1] ints;
 // recs: capacity n/16 + nblocks + 1; chunk_off: same + 1.

@@ -445,6 +445,9 @@ int cb_p2p_window_create(cb_p2p_window** out, int64_t capacity_tuples, int64_t t
 int cb_p2p_window_destroy(cb_p2p_window* w);
 int cb_p2p_window_get_handle(const cb_p2p_window* w, void* handle_h /* 64 bytes */);
 int cb_p2p_window_open(const void* handle_h, void** peer_base);   /* in the PEER process */
+/* The window's base address for a pusher in the SAME process (several slabs driven by one
+ * process): pass it as peer_lo / peer_hi; never cb_p2p_window_close it. */
+int cb_p2p_window_local_base(const cb_p2p_window* w, void** base);
 int cb_p2p_window_close(void* peer_base);
 /* Fused plan + pack into the neighbours' windows (peer_lo / peer_hi from cb_p2p_window_open,
  * NULL when there is no neighbour on that side).  steer_scratch holds 2*num_local ids.
@@ -460,12 +463,17 @@ int cb_slab_halo_wait(cb_p2p_window* from_lo, cb_p2p_window* from_hi, uint64_t s
                       int64_t* counts_h /* [2] */, const void** data_lo, const void** data_hi,
                       cb_stream_t stream);
 
-/* The whole sharded step in one host call (bench.py, N > 1): cb_slab_halo_push +
- * cb_slab_halo_wait + cb_comm_unpack (lower neighbour's ghosts first) + cb_verlet_build with
- * begin = 0, end = num_local on x_all (whose n is its CAPACITY: owned + room for ghosts; the
- * fields must have the same capacity).  counts_h[0..1] = ghosts received from the lower / upper
- * neighbour.  Replaces Halo construction + gather (impl/Cabana_Halo_Mpi.hpp:41-125) followed
- * by VerletList::build (Cabana_VerletList.hpp:1351-1392). */
+/* The whole sharded step in one host call (bench.py, N > 1): ghost selection + push into the
+ * neighbours' windows, then ONE kernel that waits for their pushes and unpacks both ghost layers
+ * behind the owned particles (lower neighbour's first), then cb_verlet_build with begin = 0,
+ * end = num_local on x_all (whose n is its CAPACITY: owned + room for ghosts; the fields must
+ * have the same capacity).  The ghost counts stay on the device -- the build reads the particle
+ * count there -- and reach the host with the build's single read-back, so the step has no host
+ * synchronisation before the list size is known (CB_SLAB_SYNC=1 selects the older
+ * push / cb_slab_halo_wait / cb_comm_unpack / cb_verlet_build sequence with a read-back of the
+ * counts; same result).  counts_h[0..1] = ghosts received from the lower / upper neighbour.
+ * Replaces Halo construction + gather (impl/Cabana_Halo_Mpi.hpp:41-125) followed by
+ * VerletList::build (Cabana_VerletList.hpp:1351-1392). */
 int cb_slab_step(cb_verlet* list, const cb_positions* x_all, const cb_field* fields_h,
                  int num_fields, int64_t num_local, double lo_thresh, double hi_thresh,
                  void* peer_lo, void* peer_hi, cb_p2p_window* from_lo, cb_p2p_window* from_hi,

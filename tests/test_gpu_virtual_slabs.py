@@ -199,3 +199,117 @@ def test_slab_step_entry_single_rank(orc):
     ret = mgr.dict()
     mp.spawn(_single_rank_step, args=(port, ret), nprocs=1, join=True)
     assert ret[0] is True, ret[0]
+
+
+def _two_slab_step_lists(cb, ps, algo, reps):
+    """Two virtual ranks in ONE process drive cb_slab_step with its device-side ghost counts: each
+    rank's windows live on the same GPU and the neighbour pushes through their local base address.
+    The pushes of both ranks are issued first (cb_slab_halo_push), so the step's own wait finds them
+    -- its second push of the same sequence rewrites identical bytes."""
+    import ctypes as C
+
+    from cabana_b200 import capi
+
+    L = capi.lib()
+    P = 2
+    Lx = ps.grid_max[0]
+    bounds = [Lx * g / P for g in range(P + 1)]
+    hw = ps.radius * (1.0 + 2.0**-40)
+    owner = np.minimum(np.searchsorted(np.asarray(bounds[1:-1]), ps.xyz[:, 0], side="right"), P - 1)
+    mine = [np.nonzero(owner == g)[0] for g in range(P)]
+    capw = max(int(len(m) * 1.5 * hw / (bounds[1] - bounds[0])) + 1024 for m in mine)
+    xs, gids, nloc = [], [], []
+    for g in range(P):
+        cap = len(mine[g]) + capw
+        buf = np.zeros((cap, 3))
+        buf[: len(mine[g])] = ps.xyz[mine[g]]
+        xs.append(cb.slice_from_array(buf, vlen=32))
+        gi = np.full((cap, 1), -1, dtype=np.int32)
+        gi[: len(mine[g]), 0] = mine[g]
+        gids.append(cb.view_from_array(gi))
+        nloc.append(len(mine[g]))
+    fields = [[xs[g], gids[g]] for g in range(P)]
+    farr = [(capi.Field * 2)(*[f.field_desc() for f in fields[g]]) for g in range(P)]
+    tb = int(L.cb_comm_tuple_bytes(farr[0], 2))
+    # rank 0 receives from its upper neighbour, rank 1 from its lower one
+    win = [C.c_void_p(), C.c_void_p()]
+    base = [C.c_void_p(), C.c_void_p()]
+    for g in range(P):
+        capi.check(L.cb_p2p_window_create(C.byref(win[g]), C.c_int64(capw), C.c_int64(tb)))
+        capi.check(L.cb_p2p_window_local_base(win[g], C.byref(base[g])))
+    steer = [torch.empty(2 * nloc[g], dtype=torch.int32, device="cuda") for g in range(P)]
+    lsts = [cb.VerletList(algorithm=algo, layout=cb.CSR) for _ in range(P)]
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def args(g):
+        peer_lo = base[0] if g == 1 else C.c_void_p()
+        peer_hi = base[1] if g == 0 else C.c_void_p()
+        from_lo = win[1] if g == 1 else None
+        from_hi = win[0] if g == 0 else None
+        return peer_lo, peer_hi, from_lo, from_hi
+
+    out = []
+    try:
+        for seq in range(1, reps + 1):
+            for g in range(P):
+                peer_lo, peer_hi, _, _ = args(g)
+                d = xs[g].positions_desc()
+                d.n = nloc[g]
+                capi.check(L.cb_slab_halo_push(
+                    C.byref(d), farr[g], 2, C.c_int64(nloc[g]), C.c_double(bounds[g] + hw),
+                    C.c_double(bounds[g + 1] - hw), peer_lo, peer_hi, C.c_int64(capw),
+                    C.c_uint64(seq), C.c_void_p(steer[g].data_ptr()), st))
+            rows = {}
+            for g in range(P):
+                peer_lo, peer_hi, from_lo, from_hi = args(g)
+                lmin = (bounds[g] - hw if g > 0 else bounds[g], ps.grid_min[1], ps.grid_min[2])
+                lmax = (bounds[g + 1] + hw if g < P - 1 else bounds[g + 1], ps.grid_max[1], ps.grid_max[2])
+                d = xs[g].positions_desc()
+                counts = (C.c_int64 * 2)()
+                capi.check(L.cb_slab_step(
+                    lsts[g]._h, C.byref(d), farr[g], 2, C.c_int64(nloc[g]),
+                    C.c_double(bounds[g] + hw), C.c_double(bounds[g + 1] - hw), peer_lo, peer_hi,
+                    from_lo, from_hi, C.c_int64(capw), C.c_uint64(seq),
+                    C.c_void_p(steer[g].data_ptr()), C.c_double(ps.radius), C.c_double(1.0),
+                    capi.d3(lmin), capi.d3(lmax), C.c_int64(0), C.c_int(algo), C.c_int(cb.CSR),
+                    C.c_int(lsts[g].build_tag), counts, st))
+                lsts[g]._refresh()
+                nghost = int(counts[0]) + int(counts[1])
+                assert nghost > 0
+                ntot = nloc[g] + nghost
+                assert lsts[g]._data.counts.numel() == ntot, "list size = owned + ghosts"
+                cnt = lsts[g]._data.counts.cpu().numpy()
+                off = lsts[g]._data.offsets.cpu().numpy()
+                nb = lsts[g]._data.neighbors.cpu().numpy()
+                gid = gids[g].to_array().cpu().numpy()[:ntot, 0]
+                assert (gid >= 0).all()
+                assert cnt[nloc[g]:].sum() == 0
+                for i in range(nloc[g]):
+                    rows[int(gid[i])] = sorted(int(gid[j]) for j in nb[off[i]: off[i] + cnt[i]])
+            out.append(rows)
+    finally:
+        torch.cuda.synchronize()
+        for g in range(P):
+            L.cb_p2p_window_destroy(win[g])
+    return out
+
+
+@pytest.mark.parametrize("algo_name", ["full", "half"])
+def test_slab_step_device_side_ghost_counts(orc, cb, algo_name, monkeypatch):
+    """The sync-free step (k_halo_wait_unpack + a build that reads the particle count on the device
+    + the speculative fill of the rebuild) on one GPU: union of the two owner-local lists equals the
+    oracle's list of the whole box, on the first build and on two rebuilds; the older path
+    (CB_SLAB_SYNC=1) gives the same lists."""
+    ps = datasets.uniform_box(30_000, 20240177, radius=3.0)
+    algo = cb.FULL if algo_name == "full" else cb.HALF
+    ref = orc.verlet_build(orc.view_from_xyz(ps.xyz), 0, ps.n, ps.radius, 1.0, ps.grid_min,
+                           ps.grid_max, algo=orc.FULL if algo_name == "full" else orc.HALF)
+    want = [sorted(int(v) for v in ref.row(i)) for i in range(ps.n)]
+    for rows in _two_slab_step_lists(cb, ps, algo, reps=3):
+        assert len(rows) == ps.n
+        for i in range(ps.n):
+            assert rows[i] == want[i], f"particle {i}"
+    monkeypatch.setenv("CB_SLAB_SYNC", "1")
+    rows = _two_slab_step_lists(cb, ps, algo, reps=1)[0]
+    for i in range(ps.n):
+        assert rows[i] == want[i], f"particle {i} (sync path)"
