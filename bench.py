@@ -529,7 +529,10 @@ def run_ours(args):
     sync_all()
 
     # ---- timed region: device events on the launching stream, barrier+sync both sides
-    phase_sum = np.zeros(6)
+    # (per-phase times: the library records CUDA events around every phase of every timed build
+    # and averages them; they are read ONCE after the region -- a read per step would make the host
+    # wait for each build to finish before it may launch the next one)
+    capi.check(L.cb_verlet_set_profiling(lst._h, 1))
     launches0 = L.cb_kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
@@ -537,12 +540,12 @@ def run_ours(args):
     ev0.record()
     for _ in range(args.steps):
         local_total = step()
-        ph = (C.c_double * 6)()
-        capi.check(L.cb_verlet_get_phase_times(lst._h, ph))
-        phase_sum += np.array(list(ph))
     ev1.record()
     sync_all()
     sampler.mark_end()
+    ph = (C.c_double * 6)()
+    capi.check(L.cb_verlet_get_phase_times(lst._h, ph))
+    phase_sum = np.array(list(ph)) * args.steps
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = L.cb_kernel_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None

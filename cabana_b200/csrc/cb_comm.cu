@@ -191,11 +191,15 @@ __global__ void __launch_bounds__( kBlock )
 // kernel (decoupled look-back over a packed (lo,hi) pair of counters), so a plan costs one
 // launch and one 16-byte read-back instead of ten launches and two syncs.
 constexpr int kHaloThreads = 256;
-constexpr int kHaloItems = 4;
+constexpr int kHaloItems = 16; // per thread: few, fat tiles keep the look-back chain short
 constexpr int kHaloTile = kHaloThreads * kHaloItems;
 
 using ull = unsigned long long;
 
+// A warp owns 32 * kHaloItems consecutive particles; item e of lane l is particle
+// warp_base + 32 e + l, so every load instruction reads 256 contiguous bytes of an AoSoA and the
+// stable order inside the warp is e-major: a ballot per item gives each lane its place (no
+// shuffle scans), and the ballots themselves are all a thread has to keep between the two sweeps.
 __global__ void __launch_bounds__( kHaloThreads )
     k_halo_compact( PosAccess x, long long n, double lo_thresh, double hi_thresh, int has_lo,
                     int has_hi, unsigned* __restrict__ steer_lo,
@@ -210,35 +214,29 @@ __global__ void __launch_bounds__( kHaloThreads )
         s_tile = atomicAdd( tile_counter, 1u );
     __syncthreads();
     const unsigned tile = s_tile;
-    const long long base = (long long)tile * kHaloTile + (long long)t * kHaloItems;
-    bool flo[kHaloItems], fhi[kHaloItems];
+    const long long wbase = (long long)tile * kHaloTile + (long long)warp * ( 32 * kHaloItems );
+    double px[kHaloItems];
+#pragma unroll
+    for ( int e = 0; e < kHaloItems; ++e )
+    {
+        const long long p = wbase + 32 * e + lane;
+        px[e] = p < n ? x.base[x.offset( p )] : 0.0;
+    }
+    unsigned blo[kHaloItems], bhi[kHaloItems];
     unsigned clo = 0, chi = 0;
 #pragma unroll
     for ( int e = 0; e < kHaloItems; ++e )
     {
-        flo[e] = false;
-        fhi[e] = false;
-        if ( base + e < n )
-        {
-            const double px = x.base[x.offset( base + e )];
-            flo[e] = has_lo && px < lo_thresh;
-            fhi[e] = has_hi && px >= hi_thresh;
-        }
-        clo += flo[e] ? 1u : 0u;
-        chi += fhi[e] ? 1u : 0u;
+        const bool in = wbase + 32 * e + lane < n;
+        blo[e] = __ballot_sync( kFullMask, in && has_lo && px[e] < lo_thresh );
+        bhi[e] = __ballot_sync( kFullMask, in && has_hi && px[e] >= hi_thresh );
+        clo += (unsigned)__popc( blo[e] );
+        chi += (unsigned)__popc( bhi[e] );
     }
-    // packed sums: lo in bits 0..30, hi in bits 31..61 (n < 2^31)
+    // packed sums: lo in bits 0..30, hi in bits 31..61 (n < 2^31); clo / chi are warp totals
     const ull mine = (ull)clo | ( (ull)chi << 31 );
-    ull incl = mine;
-#pragma unroll
-    for ( int o = 1; o < 32; o <<= 1 )
-    {
-        const ull y = __shfl_up_sync( kFullMask, incl, o );
-        if ( lane >= o )
-            incl += y;
-    }
-    if ( lane == 31 )
-        s_warp[warp] = incl;
+    if ( lane == 0 )
+        s_warp[warp] = mine;
     __syncthreads();
     if ( warp == 0 )
     {
@@ -309,16 +307,20 @@ __global__ void __launch_bounds__( kHaloThreads )
         }
     }
     __syncthreads();
-    const ull excl = s_prefix + s_warp[warp] + ( incl - mine );
+    const ull excl = s_prefix + s_warp[warp];
     unsigned plo = (unsigned)( excl & 0x7fffffffull );
     unsigned phi = (unsigned)( ( excl >> 31 ) & 0x7fffffffull );
+    const unsigned lt = ( 1u << lane ) - 1u;
 #pragma unroll
     for ( int e = 0; e < kHaloItems; ++e )
     {
-        if ( flo[e] )
-            steer_lo[plo++] = (unsigned)( base + e );
-        if ( fhi[e] )
-            steer_hi[phi++] = (unsigned)( base + e );
+        const unsigned id = (unsigned)( wbase + 32 * e + lane );
+        if ( ( blo[e] >> lane ) & 1u )
+            steer_lo[plo + (unsigned)__popc( blo[e] & lt )] = id;
+        if ( ( bhi[e] >> lane ) & 1u )
+            steer_hi[phi + (unsigned)__popc( bhi[e] & lt )] = id;
+        plo += (unsigned)__popc( blo[e] );
+        phi += (unsigned)__popc( bhi[e] );
     }
 }
 

@@ -456,18 +456,36 @@ struct cb_verlet
     DeviceBuffer host_stage; // device copy of host positions (build_host)
     PinnedScalars pinned;
     cudaEvent_t ev_stats = nullptr; // "sizes are on the host" (the build's one host wait)
-    // optional phase timing
+    // optional phase timing: a ring of event sets, one per build, so a caller can time many
+    // builds back to back and read the averages once at the end (no host wait per build)
+    static constexpr int kProfRing = 32;
     bool profiling = false;
-    cudaEvent_t ev[CB_VERLET_NUM_PHASES + 1] = {};
-    bool ev_valid[CB_VERLET_NUM_PHASES + 1] = {};
+    cudaEvent_t ev[kProfRing][CB_VERLET_NUM_PHASES + 1] = {};
+    bool ev_valid[kProfRing][CB_VERLET_NUM_PHASES + 1] = {};
     bool have_events = false;
+    int prof_slot = 0;
     ~cb_verlet()
     {
         if ( have_events )
-            for ( auto& e : ev )
-                cudaEventDestroy( e );
+            for ( auto& set : ev )
+                for ( auto& e : set )
+                    cudaEventDestroy( e );
         if ( ev_stats )
             cudaEventDestroy( ev_stats );
+    }
+    void reset_profile()
+    {
+        for ( auto& set : ev_valid )
+            for ( auto& f : set )
+                f = false;
+        prof_slot = 0;
+    }
+    // a build starts: take the next event set of the ring
+    void begin_profile()
+    {
+        prof_slot = ( prof_slot + 1 ) % kProfRing;
+        for ( auto& f : ev_valid[prof_slot] )
+            f = false;
     }
     // mark(i): boundary i on the stream -- 0 start, 1 after binning, 2 after gather,
     // 3 after count, 4 after scan, 5 after fill.
@@ -475,8 +493,8 @@ struct cb_verlet
     {
         if ( profiling && have_events )
         {
-            cudaEventRecord( ev[i], s );
-            ev_valid[i] = true;
+            cudaEventRecord( ev[prof_slot][i], s );
+            ev_valid[prof_slot][i] = true;
         }
     }
 };
@@ -547,8 +565,7 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
     CB_TRY( v->tile_chunks.ensure( sizeof( int ) * (size_t)rec_capacity, 1.1 ) );
     CB_TRY( v->chunk_off.ensure( sizeof( int ) * (size_t)( rec_capacity + 1 ), 1.1 ) );
 
-    for ( auto& f : v->ev_valid )
-        f = false;
+    v->begin_profile();
     v->mark( 0, stream );
     CB_CUDA( cudaMemsetAsync( v->counts.ptr, 0, sizeof( int ) * na, stream ) ); // :215-216
 
@@ -908,8 +925,7 @@ int cb::verlet_build_devcount( cb_verlet* v, const cb_positions* x, long long be
     v->width = 0;
     v->refilled = 0;
 
-    for ( auto& f : v->ev_valid )
-        f = false;
+    v->begin_profile();
     v->mark( 0, stream );
 
     // counts zero-initialised (:215-216)
@@ -1278,8 +1294,7 @@ extern "C" int cb_verlet_build_radii( cb_verlet* v, const cb_positions* x,
     v->n = n;
     v->total = v->max_n = v->width = 0;
     v->refilled = 0;
-    for ( auto& f : v->ev_valid )
-        f = false;
+    v->begin_profile();
 
     CB_CUDA( cudaMemsetAsync( v->counts.ptr, 0, sizeof( int ) * na, stream ) );
     CB_CUDA( cudaMemsetAsync( v->row_cursor.ptr, 0, sizeof( int ) * na, stream ) );
@@ -1383,11 +1398,13 @@ extern "C" int cb_verlet_set_profiling( cb_verlet* v, int enable )
         return fail( CB_ERR_INVALID, "cb_verlet_set_profiling: null argument" );
     if ( enable && !v->have_events )
     {
-        for ( auto& e : v->ev )
-            CB_CUDA( cudaEventCreate( &e ) );
+        for ( auto& set : v->ev )
+            for ( auto& e : set )
+                CB_CUDA( cudaEventCreate( &e ) );
         v->have_events = true;
     }
     v->profiling = enable != 0;
+    v->reset_profile(); // the averages of cb_verlet_get_phase_times start here
     return CB_OK;
 }
 
@@ -1395,19 +1412,31 @@ extern "C" int cb_verlet_get_phase_times( const cb_verlet* v, double* ms )
 {
     if ( !v || !ms )
         return fail( CB_ERR_INVALID, "cb_verlet_get_phase_times: null argument" );
-    if ( !v->profiling || !v->have_events || !v->ev_valid[0] || !v->ev_valid[5] )
+    const int last = v->prof_slot;
+    if ( !v->profiling || !v->have_events || !v->ev_valid[last][0] || !v->ev_valid[last][5] )
         return fail( CB_ERR_INVALID, "cb_verlet_get_phase_times: no profiled build" );
-    CB_CUDA( cudaEventSynchronize( v->ev[5] ) );
-    for ( int i = 0; i < 5; ++i )
+    CB_CUDA( cudaEventSynchronize( v->ev[last][5] ) );
+    // average over the (up to kProfRing) most recent builds since profiling was switched on
+    double sum[CB_VERLET_NUM_PHASES] = { 0.0 };
+    int sets = 0;
+    for ( int r = 0; r < cb_verlet::kProfRing; ++r )
     {
+        if ( !v->ev_valid[r][0] || !v->ev_valid[r][5] )
+            continue;
+        for ( int i = 0; i < 5; ++i )
+        {
+            float t = 0.f;
+            if ( v->ev_valid[r][i] && v->ev_valid[r][i + 1] )
+                CB_CUDA( cudaEventElapsedTime( &t, v->ev[r][i], v->ev[r][i + 1] ) );
+            sum[i] += t;
+        }
         float t = 0.f;
-        if ( v->ev_valid[i] && v->ev_valid[i + 1] )
-            CB_CUDA( cudaEventElapsedTime( &t, v->ev[i], v->ev[i + 1] ) );
-        ms[i] = t;
+        CB_CUDA( cudaEventElapsedTime( &t, v->ev[r][0], v->ev[r][5] ) );
+        sum[5] += t;
+        ++sets;
     }
-    float t = 0.f;
-    CB_CUDA( cudaEventElapsedTime( &t, v->ev[0], v->ev[5] ) );
-    ms[5] = t;
+    for ( int i = 0; i < CB_VERLET_NUM_PHASES; ++i )
+        ms[i] = sum[i] / (double)sets;
     return CB_OK;
 }
 

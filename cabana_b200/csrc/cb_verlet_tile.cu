@@ -1028,6 +1028,19 @@ CB_D void expand_word( unsigned mm, const unsigned* ids2, int* rows, int& w )
         out += 4u;
     }
 }
+// (same loop with the table and the output given as shared-window addresses)
+CB_D void expand_word_at( unsigned mm, unsigned tab, unsigned out )
+{
+    while ( mm )
+    {
+        const unsigned p = top_bit( mm );
+        asm( "xor.b32 %0, %0, %1;" : "+r"( mm ) : "r"( 1u << p ) );
+        unsigned v;
+        asm volatile( "ld.shared.u32 %0, [%1];" : "=r"( v ) : "r"( tab + ( p << 5 ) ) );
+        asm volatile( "st.shared.u32 [%0], %1;" ::"r"( out ), "r"( v ) : "memory" );
+        out += 4u;
+    }
+}
 CB_D void expand_word_global( unsigned mm, const unsigned* ids2, int*& out )
 {
     while ( mm )
@@ -1211,12 +1224,47 @@ __global__ void __launch_bounds__( kBlockT, 4 )
                     const unsigned* ids2 = S.ids + 2 * t;
                     if ( !direct )
                     {
-                        int w_g = cur_g + ( pk & 0xffff ) - pg;
-                        int w_g8 = cur_g8 + ( pk >> 16 ) - pg8;
-                        expand_word( m.x, ids2, S.rows, w_g );
-                        expand_word( m.y, ids2 + 1, S.rows, w_g );
-                        expand_word( m.z, ids2, S.rows, w_g8 );
-                        expand_word( m.w, ids2 + 1, S.rows, w_g8 );
+                        // The four words of a lane are expanded by four loops the whole warp
+                        // walks together, each as long as its busiest lane.  Every word knows
+                        // where its ids go, so a lane may take them in any order: sorted by
+                        // population (largest first), the first loop is the only long one.
+                        const int w_g = cur_g + ( pk & 0xffff ) - pg;
+                        const int w_g8 = cur_g8 + ( pk >> 16 ) - pg8;
+                        const unsigned rows_a = smem_u32( S.rows );
+                        const unsigned tab0 = smem_u32( ids2 );
+                        unsigned wm[4] = { m.x, m.y, m.z, m.w };
+                        unsigned wo[4] = { rows_a + 4u * (unsigned)w_g,
+                                           rows_a + 4u * (unsigned)( w_g + __popc( m.x ) ),
+                                           rows_a + 4u * (unsigned)w_g8,
+                                           rows_a + 4u * (unsigned)( w_g8 + __popc( m.z ) ) };
+                        unsigned wt[4] = { tab0, tab0 + 4u, tab0, tab0 + 4u };
+                        int wc[4] = { __popc( m.x ), __popc( m.y ), __popc( m.z ), __popc( m.w ) };
+                        auto cswap = [&]( int i, int j )
+                        {
+                            const bool sw = wc[i] < wc[j];
+                            const unsigned tm = sw ? wm[j] : wm[i], to = sw ? wo[j] : wo[i],
+                                           tt = sw ? wt[j] : wt[i];
+                            const int tc = sw ? wc[j] : wc[i];
+                            wm[j] = sw ? wm[i] : wm[j];
+                            wo[j] = sw ? wo[i] : wo[j];
+                            wt[j] = sw ? wt[i] : wt[j];
+                            wc[j] = sw ? wc[i] : wc[j];
+                            wm[i] = tm;
+                            wo[i] = to;
+                            wt[i] = tt;
+                            wc[i] = tc;
+                        };
+                        if ( a.fill_sort )
+                        {
+                            cswap( 0, 1 );
+                            cswap( 2, 3 );
+                            cswap( 0, 2 );
+                            cswap( 1, 3 );
+                            cswap( 1, 2 );
+                        }
+#pragma unroll
+                        for ( int k = 0; k < 4; ++k )
+                            expand_word_at( wm[k], wt[k], wo[k] );
                         cur_g += qt & 0xffff;
                         cur_g8 += qt >> 16;
                     }
@@ -1505,8 +1553,11 @@ int tile_sorted_dst( const TileArgs& a, long long ncells, long long ns_cap, int*
     return CB_OK;
 }
 
-int tile_fill_pass( const TileArgs& a, bool csr, cudaStream_t stream )
+int tile_fill_pass( const TileArgs& a_, bool csr, cudaStream_t stream )
 {
+    TileArgs a = a_;
+    const char* sort_env = getenv( "CB_FILL_SORT" );
+    a.fill_sort = !( sort_env && sort_env[0] == '0' );
     const int smem = (int)sizeof( FillSmem ) * kWarpsT;
     return csr ? launch_persistent( k_tile_fill<true>, smem, a, stream )
                : launch_persistent( k_tile_fill<false>, smem, a, stream );

@@ -66,6 +66,7 @@ struct TileArgs
     const long long* spec_total; // device: total stored neighbours (nullptr: not speculative)
     long long spec_capacity;     // ints the neighbour array holds
     int* spec_failed;            // set when the kernel left early
+    int fill_sort;               // fill pass: expand a lane's mask words largest first
     // diagnostics (cb_verlet_filter_selftest): [0] max |c_mma - c_exact| as float bits,
     // [1] number of values that missed the bound
     unsigned* diag_maxerr;

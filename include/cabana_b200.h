@@ -257,9 +257,12 @@ int cb_verlet_set_neighbor(cb_verlet* list, int64_t particle_index,
                            cb_stream_t stream);
 int cb_verlet_destroy(cb_verlet* list);
 
-/* Optional per-phase device timing (CUDA events on the caller's stream) of the LAST build:
- * ms_h[0..5] = binning, gather-permute, count pass, offsets scan + max/sum, fill pass,
- * whole build.  Used by bench.py for the per-kernel roofline; off by default. */
+/* Optional per-phase device timing (CUDA events on the caller's stream):
+ * ms_h[0..5] = binning, gather-permute / tile plan, count pass, offsets scan + max/sum, fill
+ * pass, whole build -- AVERAGED over the builds (the 32 most recent at most) since the last
+ * cb_verlet_set_profiling(list, 1), so a rebuild loop is timed without a host wait per build;
+ * cb_verlet_get_phase_times waits for the last one.  Used by bench.py for the per-kernel
+ * roofline; off by default. */
 #define CB_VERLET_NUM_PHASES 6
 int cb_verlet_set_profiling(cb_verlet* list, int enable);
 int cb_verlet_get_phase_times(const cb_verlet* list, double* ms_h);

@@ -26,14 +26,15 @@ for zdiv in zdivs:
     for zb in zbs:
         os.environ["CB_TILE_ZDIV"] = str(zdiv)
         os.environ["CB_TILE_ZB"] = str(zb)
-        acc = np.zeros(6)
         reps = 6
-        for it in range(reps + 2):
+        for it in range(2):
             lst.build(x, 0, n, bench.RADIUS, 1.0, (0.0, 0.0, 0.0), gmax)
-            torch.cuda.synchronize()
-            ph = (C.c_double * 6)()
-            capi.check(L.cb_verlet_get_phase_times(lst._h, ph))
-            if it >= 2:
-                acc += np.array(list(ph))
+        torch.cuda.synchronize()
+        capi.check(L.cb_verlet_set_profiling(lst._h, 1))   # the averages start here
+        for it in range(reps):
+            lst.build(x, 0, n, bench.RADIUS, 1.0, (0.0, 0.0, 0.0), gmax)
+        torch.cuda.synchronize()
+        ph = (C.c_double * 6)()
+        capi.check(L.cb_verlet_get_phase_times(lst._h, ph))
         print("zdiv %4.1f zb %3d total %d : bin %.3f plan %.3f count %.3f scan %.3f fill %.3f | step %.3f ms"
-              % ((zdiv, zb, lst.total) + tuple(acc / reps)), flush=True)
+              % ((zdiv, zb, lst.total) + tuple(ph)), flush=True)
