@@ -540,6 +540,11 @@ static int build_tile( cb_verlet* v, const cb_positions* x, long long begin, lon
 
     TileGrid tg;
     make_tile_grid( tg, grid_min, grid_max, radius, n );
+    if ( getenv( "CB_TILE_DEBUG" ) )
+        fprintf( stderr,
+                 "[cb] pencil grid %d x %d x %d, dx %.6f %.6f %.6f, x in [%.6f, %.6f], kz %d\n",
+                 tg.ncx, tg.ncy, tg.nz, tg.g.dx[0], tg.g.dx[1], tg.g.dx[2], tg.g.min[0],
+                 tg.g.max[0], tg.kz );
     const long long ns_cap = sorted_capacity( tg, n ); // sorted slots incl. column pads
     const long long rec_capacity = ns_cap / kTileHomes + tg.nblocks + 2;
 
