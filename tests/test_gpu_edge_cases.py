@@ -112,6 +112,26 @@ def test_handle_reuse_across_regimes(orc, cb):
         assert np.array_equal(got, ref.sorted_rows_flat()[0])
 
 
+def test_speculative_fill_paths(orc, cb, monkeypatch):
+    """Rebuilds on one handle launch the CSR fill pass before the host has seen the list size: the
+    list that grows past the array of the previous build (guard fails, pass re-launched after the
+    allocation), the one that fits (speculation holds), the one that shrinks, and the switch
+    CB_VERLET_SPECULATE=0 must all give the oracle's list."""
+    ps = datasets.uniform_box(12_000, 20240811, radius=3.0)
+    x = cb.slice_from_array(ps.xyz, vlen=32)
+    ox = orc.view_from_xyz(ps.xyz)
+    lst = cb.VerletList(algorithm=cb.HALF, layout=cb.CSR)
+    for r, spec in ((1.5, "1"), (3.0, "1"), (3.0, "1"), (2.2, "1"), (3.0, "0"), (2.9, "1")):
+        monkeypatch.setenv("CB_VERLET_SPECULATE", spec)
+        lst.build(x, 0, ps.n, r, 1.0, ps.grid_min, ps.grid_max)
+        ref = orc.verlet_build(ox, 0, ps.n, r, 1.0, ps.grid_min, ps.grid_max, algo=orc.HALF)
+        counts = lst._data.counts.cpu().numpy()
+        assert lst.total == ref.total and np.array_equal(counts, ref.counts), r
+        got, _ = orc.sorted_rows_flat(orc.CSR, counts, lst._data.offsets.cpu().numpy(),
+                                      lst._data.neighbors.cpu().numpy(), 0)
+        assert np.array_equal(got, ref.sorted_rows_flat()[0]), r
+
+
 # ---------------------------------------------------------------- kernel generations (VERDICT r1 1d)
 @pytest.fixture
 def verlet_impl():
