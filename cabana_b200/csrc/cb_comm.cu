@@ -15,6 +15,8 @@
 #include <new>
 #include <string.h>
 
+#include <vector>
+
 #include "cb_common.cuh"
 #include "cb_internal.h"
 
@@ -94,24 +96,91 @@ __global__ void __launch_bounds__( kBlock )
             atomicAdd( &counts[r], (unsigned long long)s_hist[r] );
 }
 
-__global__ void __launch_bounds__( kBlock )
-    k_flag_rank( const int* __restrict__ export_ranks, long long n, int rank,
-                 int* __restrict__ flags )
+// Stable partition of the exports by destination in ONE pass over them per 5 bits of the
+// (dense) destination index -- one pass for up to 32 destinations that actually receive
+// something, two up to 1024 -- instead of a flag / scan / scatter sweep per destination.
+// Least-significant-digit radix sort of (dense destination, export index): a tile of 256 exports
+// per CTA; inside a warp __match_any groups equal digits (rank = peers below me), per-warp digit
+// counts in shared memory order the warps of a tile, and a scan of the digit-major table of tile
+// histograms orders the tiles.  Dropped exports (rank -1) leave in the first pass.
+constexpr int kSteerDigits = 32;
+constexpr int kSteerTile = 256;
+
+struct SteerKey
 {
-    for ( long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n;
-          i += (long long)gridDim.x * kBlock )
-        flags[i] = export_ranks[i] == rank ? 1 : 0;
+    bool valid;
+    unsigned src;
+    int digit;
+};
+template <bool FIRST>
+CB_D SteerKey steer_key( const int* __restrict__ export_ranks,
+                         const unsigned* __restrict__ idx_in, long long count,
+                         const int* __restrict__ dense_of, int shift )
+{
+    SteerKey k;
+    const long long i = (long long)blockIdx.x * kSteerTile + threadIdx.x;
+    k.valid = i < count;
+    k.src = 0u;
+    k.digit = 0;
+    if ( k.valid )
+    {
+        k.src = FIRST ? (unsigned)i : idx_in[i];
+        const int r = export_ranks[k.src];
+        const int d = r >= 0 ? dense_of[r] : -1;
+        k.valid = d >= 0;
+        k.digit = ( d >> shift ) & ( kSteerDigits - 1 );
+    }
+    return k;
 }
 
-__global__ void __launch_bounds__( kBlock )
-    k_steer_scatter( const int* __restrict__ export_ranks, long long n, int rank,
-                     const int* __restrict__ slot, const unsigned* __restrict__ export_ids,
-                     unsigned* __restrict__ steering_block )
+template <bool FIRST>
+__global__ void __launch_bounds__( kSteerTile )
+    k_steer_digit_hist( const int* __restrict__ export_ranks,
+                        const unsigned* __restrict__ idx_in, long long count,
+                        const int* __restrict__ dense_of, int shift, int* __restrict__ hist,
+                        long long num_tiles )
 {
-    for ( long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n;
-          i += (long long)gridDim.x * kBlock )
-        if ( export_ranks[i] == rank )
-            steering_block[slot[i]] = export_ids ? export_ids[i] : (unsigned)i;
+    __shared__ int s_cnt[kSteerDigits];
+    if ( threadIdx.x < kSteerDigits )
+        s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const SteerKey k = steer_key<FIRST>( export_ranks, idx_in, count, dense_of, shift );
+    const unsigned lane = lane_id();
+    const unsigned peers =
+        __match_any_sync( kFullMask, k.valid ? k.digit : kSteerDigits + (int)lane );
+    if ( k.valid && (int)lane == __ffs( (int)peers ) - 1 )
+        atomicAdd( &s_cnt[k.digit], __popc( peers ) );
+    __syncthreads();
+    if ( threadIdx.x < kSteerDigits )
+        hist[(long long)threadIdx.x * num_tiles + blockIdx.x] = s_cnt[threadIdx.x];
+}
+
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__( kSteerTile )
+    k_steer_digit_scatter( const int* __restrict__ export_ranks,
+                           const unsigned* __restrict__ idx_in, long long count,
+                           const int* __restrict__ dense_of, int shift,
+                           const int* __restrict__ base, long long num_tiles,
+                           const unsigned* __restrict__ export_ids, unsigned* __restrict__ out )
+{
+    __shared__ int s_w[kSteerTile / 32][kSteerDigits];
+    const unsigned lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    s_w[warp][lane] = 0;
+    __syncthreads();
+    const SteerKey k = steer_key<FIRST>( export_ranks, idx_in, count, dense_of, shift );
+    const unsigned peers =
+        __match_any_sync( kFullMask, k.valid ? k.digit : kSteerDigits + (int)lane );
+    const int rank_in_warp = __popc( peers & lanemask_lt() );
+    if ( k.valid && rank_in_warp == 0 )
+        s_w[warp][k.digit] = __popc( peers );
+    __syncthreads();
+    if ( !k.valid )
+        return;
+    int pos = base[(long long)k.digit * num_tiles + blockIdx.x] + rank_in_warp;
+    for ( int w = 0; w < warp; ++w )
+        pos += s_w[w][k.digit];
+    out[pos] = LAST ? ( export_ids ? export_ids[k.src] : k.src ) : k.src;
 }
 
 struct FieldSet
@@ -353,7 +422,7 @@ int make_field_set( const cb_field* fields, int num_fields, FieldSet& fs )
 // Scratch shared by the plan kernels (one caller thread per process, cabana_b200.h).
 struct CommScratch
 {
-    DeviceBuffer counts, flags, slots, scan;
+    DeviceBuffer counts, flags, slots, scan, dense, idx_a;
     PinnedScalars pinned;
 };
 CommScratch& scratch()
@@ -462,21 +531,52 @@ extern "C" int cb_comm_count_and_steer( const int32_t* export_ranks, int64_t num
 
     if ( num_export > 0 && run > 0 )
     {
-        CB_TRY( s.flags.ensure( sizeof( int ) * (size_t)num_export, 1.1 ) );
-        CB_TRY( s.slots.ensure( sizeof( int ) * (size_t)( num_export + 1 ), 1.1 ) );
-        const int grid = launch_grid_for( num_export, kBlock );
+        // dense index of the destinations that receive something, in ascending rank order
+        std::vector<int> dense( (size_t)num_ranks, -1 );
+        int k = 0;
         for ( int r = 0; r < num_ranks; ++r )
+            if ( counts_h[r] > 0 )
+                dense[(size_t)r] = k++;
+        const long long tiles0 = ( num_export + kSteerTile - 1 ) / kSteerTile;
+        CB_TRY( s.dense.ensure( sizeof( int ) * (size_t)kMaxRanks ) );
+        CB_TRY( s.flags.ensure( sizeof( int ) * (size_t)( kSteerDigits * tiles0 ), 1.1 ) );
+        CB_TRY( s.slots.ensure( sizeof( int ) * (size_t)( kSteerDigits * tiles0 + 1 ), 1.1 ) );
+        CB_CUDA( cudaMemcpyAsync( s.dense.ptr, dense.data(), sizeof( int ) * (size_t)num_ranks,
+                                  cudaMemcpyHostToDevice, stream ) );
+        CB_CUDA( cudaStreamSynchronize( stream ) ); // (dense is a stack-lifetime host buffer)
+        const int* dense_d = s.dense.as<int>();
+        int* hist = s.flags.as<int>();
+        int* base = s.slots.as<int>();
+        const bool two = k > kSteerDigits;
+        if ( two )
+            CB_TRY( s.idx_a.ensure( sizeof( unsigned ) * (size_t)run, 1.1 ) );
+        // pass over the low 5 bits (the only one for <= 32 destinations)
+        k_steer_digit_hist<true><<<(unsigned)tiles0, kSteerTile, 0, stream>>>(
+            export_ranks, nullptr, num_export, dense_d, 0, hist, tiles0 );
+        CB_CHECK_LAUNCH();
+        CB_TRY( exclusive_scan_i32( hist, base, kSteerDigits * tiles0, false, nullptr, s.scan,
+                                    stream ) );
+        if ( !two )
+            k_steer_digit_scatter<true, true><<<(unsigned)tiles0, kSteerTile, 0, stream>>>(
+                export_ranks, nullptr, num_export, dense_d, 0, base, tiles0, export_ids,
+                steering );
+        else
+            k_steer_digit_scatter<true, false><<<(unsigned)tiles0, kSteerTile, 0, stream>>>(
+                export_ranks, nullptr, num_export, dense_d, 0, base, tiles0, nullptr,
+                s.idx_a.as<unsigned>() );
+        CB_CHECK_LAUNCH();
+        if ( two )
         {
-            if ( counts_h[r] == 0 )
-                continue;
-            k_flag_rank<<<grid, kBlock, 0, stream>>>( export_ranks, num_export, r,
-                                                      s.flags.as<int>() );
+            // pass over the high 5 bits of what the first pass kept (stable: LSD radix)
+            const long long tiles1 = ( run + kSteerTile - 1 ) / kSteerTile;
+            k_steer_digit_hist<false><<<(unsigned)tiles1, kSteerTile, 0, stream>>>(
+                export_ranks, s.idx_a.as<unsigned>(), run, dense_d, 5, hist, tiles1 );
             CB_CHECK_LAUNCH();
-            CB_TRY( exclusive_scan_i32( s.flags.as<int>(), s.slots.as<int>(), num_export,
-                                        false, nullptr, s.scan, stream ) );
-            k_steer_scatter<<<grid, kBlock, 0, stream>>>(
-                export_ranks, num_export, r, s.slots.as<int>(), export_ids,
-                steering + offsets_h[r] );
+            CB_TRY( exclusive_scan_i32( hist, base, kSteerDigits * tiles1, false, nullptr,
+                                        s.scan, stream ) );
+            k_steer_digit_scatter<false, true><<<(unsigned)tiles1, kSteerTile, 0, stream>>>(
+                export_ranks, s.idx_a.as<unsigned>(), run, dense_d, 5, base, tiles1, export_ids,
+                steering );
             CB_CHECK_LAUNCH();
         }
     }

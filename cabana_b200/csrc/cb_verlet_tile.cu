@@ -1012,23 +1012,8 @@ CB_D unsigned top_bit( unsigned m )
     return p;
 }
 // The expansion loop is the hot spot of the fill pass (one iteration per stored neighbour and
-// lane): 32-bit shared-window addresses keep it at FLO, LEA, LDS, SHF, LOP3, STS, IADD, BRA.
-CB_D void expand_word( unsigned mm, const unsigned* ids2, int* rows, int& w )
-{
-    unsigned out = smem_u32( rows + w );
-    const unsigned tab = smem_u32( ids2 );
-    w += __popc( mm );
-    while ( mm )
-    {
-        const unsigned p = top_bit( mm );
-        asm( "xor.b32 %0, %0, %1;" : "+r"( mm ) : "r"( 1u << p ) ); // (in place: no copy per trip)
-        unsigned v;
-        asm volatile( "ld.shared.u32 %0, [%1];" : "=r"( v ) : "r"( tab + ( p << 5 ) ) );
-        asm volatile( "st.shared.u32 [%0], %1;" ::"r"( out ), "r"( v ) : "memory" );
-        out += 4u;
-    }
-}
-// (same loop with the table and the output given as shared-window addresses)
+// lane): 32-bit shared-window addresses keep it at FLO, LEA, LDS, SHF, LOP3, STS, IADD, BRA;
+// the table and the output are given as shared-window addresses.
 CB_D void expand_word_at( unsigned mm, unsigned tab, unsigned out )
 {
     while ( mm )

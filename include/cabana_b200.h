@@ -396,8 +396,9 @@ int cb_slab_migrate_destinations(const cb_positions* x, int64_t num_local,
  * steering[offsets_h[r] + s] = export_ids[k] (k itself when export_ids is NULL) for the
  * s-th export with destination r: ascending rank, ascending k inside a rank
  * (deterministic; the reference's order inside a block is not). num_ranks <= 1024.
- * Cost: one histogram pass + one flag/scan/scatter pass per destination rank that actually
- * receives something (<= 27 for a Cartesian halo), not per rank of the communicator. */
+ * Cost: one histogram pass, then a stable radix partition of the exports by destination --
+ * ONE histogram / scan / scatter sweep when at most 32 destinations receive something (any
+ * Cartesian halo or migration), two up to 1024 -- independent of the communicator's size. */
 int cb_comm_count_and_steer(const int32_t* export_ranks, int64_t num_export,
                             int num_ranks, int64_t* counts_h, int64_t* offsets_h,
                             uint32_t* steering, const uint32_t* export_ids,

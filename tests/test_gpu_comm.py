@@ -49,6 +49,33 @@ def test_count_and_steer_matches_reference_semantics(mods):
                           np.concatenate([np.nonzero(ranks == r)[0] for r in range(nr)]))
 
 
+@pytest.mark.parametrize("n,nr,used", [(70_000, 3, None), (100_001, 32, None), (65_536, 33, None),
+                                       (200_000, 1024, None), (50_000, 1024, [5, 6, 700, 1023]),
+                                       (1, 4, [2]), (300, 64, [])])
+def test_count_and_steer_radix_partition(mods, n, nr, used):
+    """The stable radix partition behind cb_comm_count_and_steer: one 5-bit pass up to 32 receiving
+    destinations, two beyond; ascending rank blocks, ascending export index inside a block, dropped
+    exports (-1) nowhere -- for tile remainders, sparse destinations and no destination at all."""
+    cb, comm = mods
+    k = comm.CudaCommKernels()
+    rng = np.random.default_rng(n + nr)
+    if used is None:
+        ranks = rng.integers(-1, nr, n).astype(np.int32)
+    elif len(used) == 0:
+        ranks = np.full(n, -1, dtype=np.int32)
+    else:
+        ranks = np.asarray(used, dtype=np.int32)[rng.integers(0, len(used), n)]
+        ranks[rng.random(n) < 0.2] = -1
+    ids = rng.integers(0, 1 << 30, n).astype(np.int32)
+    counts, offsets, steering = k.count_and_steer(torch.from_numpy(ranks).cuda(),
+                                                  torch.from_numpy(ids).cuda(), nr)
+    steering = steering.cpu().numpy()
+    assert counts == [int((ranks == r).sum()) for r in range(nr)]
+    assert offsets[-1] == int((ranks >= 0).sum())
+    order = np.argsort(np.where(ranks >= 0, ranks, nr), kind="stable")[: offsets[-1]]
+    assert np.array_equal(steering[: offsets[-1]], ids[order])
+
+
 @pytest.mark.parametrize("layout", ["view", "slice"])
 def test_pack_unpack_scatter(mods, layout):
     cb, comm = mods
