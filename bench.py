@@ -588,6 +588,11 @@ def run_ours(args):
                 tj = json.load(f)
         except Exception:
             tj = {}
+    if world != 1 or args.workload != "cfg3":
+        # the capture is of the single-GPU cfg3 build: it says nothing per launch about a slab or
+        # another workload -- report null rather than a number that does not belong to this run
+        tj = {"source": "none for this configuration (the committed ncu capture is the 1-GPU cfg3 build: "
+                        "profiles/r02_traffic.json)"}
     per_kernel = {}
     for i, nm in enumerate(names):
         ms_k = float(phases[i])
