@@ -574,6 +574,12 @@ class PeerHalo:
         self.slab = slab
         L = capi.lib()
         self.capacity = int(capacity)
+        if slab.world > 1:
+            # a pusher addresses the neighbour's window with ITS OWN idea of the layout, so every
+            # rank must use the same capacity: the largest one asked for
+            t = torch.tensor([self.capacity], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=slab.group)
+            self.capacity = int(t.item())
         arr = (capi.Field * len(fields))(*[f.field_desc() for f in fields])
         self.tuple_bytes = int(L.cb_comm_tuple_bytes(arr, len(fields)))
         self._win = [C.c_void_p(), C.c_void_p()]      # from_lo, from_hi

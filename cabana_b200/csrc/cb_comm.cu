@@ -957,6 +957,10 @@ extern "C" int cb_p2p_window_create( cb_p2p_window** out, int64_t capacity_tuple
     cudaError_t e = cudaMalloc( (void**)&w->base, bytes ); // plain cudaMalloc: IPC-exportable
     if ( e == cudaSuccess )
         e = cudaMemset( w->base, 0, bytes );
+    // (cudaMemset returns before the legacy stream has run it, and a caller on a non-blocking
+    // stream is not ordered behind that stream: the headers must be zero before a handle leaves)
+    if ( e == cudaSuccess )
+        e = cudaDeviceSynchronize();
     if ( e != cudaSuccess )
     {
         delete w;

@@ -873,6 +873,20 @@ class VerletList
 
     const cb_verlet_view& view() const { return _view; }
 
+    //! Hook for fused steps that build this list through another C entry of the library
+    //! (Cabana::SlabPeerHalo::step -> cb_slab_step): fn( cb_verlet*, algorithm, layout, build_op )
+    //! does the build, then the public data is refreshed as after build().
+    template <class BuildFunction>
+    void buildThrough( BuildFunction&& fn )
+    {
+        static_assert( NumSpaceDim == 3, "fused builds are three-dimensional" );
+        ensure_handle();
+        fn( _h.get(), Impl::algorithm_enum<AlgorithmTag>::value, Impl::layout_enum<LayoutTag>::value,
+            Impl::op_enum<BuildTag>::value );
+        Impl::check( cb_verlet_get( _h.get(), &_view ), "cb_verlet_get" );
+        fill_data( _data );
+    }
+
     using device_view_type = VerletListView<MemorySpace, AlgorithmTag, LayoutTag>;
     device_view_type deviceView() const { return device_view_type{ _data }; }
 

@@ -576,6 +576,205 @@ std::size_t migrate_in_place( const DistributorType& distributor, const std::siz
     return distributor.totalNumImport();
 }
 
+//---------------------------------------------------------------------------//
+// SlabPeerHalo: the sharded step of a 1-D x-slab decomposition from host C++.  Replaces, for the
+// slab topology, Halo construction + gather( halo, x ) + VerletList::build( x, 0, num_local, ... )
+// (Cabana_Halo.hpp:107-115, impl/Cabana_Halo_Mpi.hpp:41-125, Cabana_VerletList.hpp:1351-1392)
+// by ONE call: ghosts are packed straight into the neighbours' HBM windows (CUDA IPC over
+// NVLink), waited for and unpacked on the device, and the owner-local list is built with the
+// ghost counts never visiting the host (cb_slab_step).  NCCL is used once, to exchange the
+// window handles.  One process per GPU of one node.
+//---------------------------------------------------------------------------//
+class SlabPeerHalo
+{
+  public:
+    //! bounds: size()+1 ascending slab faces; halo_width: the cutoff the ghosts must cover;
+    //! capacity_tuples: room per face; tuple_bytes: cb_comm_tuple_bytes of the slices that travel.
+    SlabPeerHalo( const NcclCommunicator& comm, const std::vector<double>& bounds,
+                  const double halo_width, const std::size_t capacity_tuples,
+                  const std::size_t tuple_bytes )
+        : _comm( comm )
+        , _capacity( capacity_tuples )
+        , _tuple_bytes( tuple_bytes )
+    {
+        const int size = comm.size(), rank = comm.rank();
+        if ( (int)bounds.size() != size + 1 )
+            throw std::runtime_error( "Cabana::SlabPeerHalo: need size + 1 slab faces" );
+        _lo = bounds[rank];
+        _hi = bounds[rank + 1];
+        _hw = halo_width * ( 1.0 + 0x1p-40 );
+        _lo_rank = rank > 0 ? rank - 1 : -1;
+        _hi_rank = rank < size - 1 ? rank + 1 : -1;
+        for ( int g = 0; g < size; ++g )
+            if ( size > 1 && bounds[g + 1] - bounds[g] < _hw )
+                throw std::runtime_error( "Cabana::SlabPeerHalo: a slab is thinner than the halo" );
+        // A pusher addresses the neighbour's window with ITS OWN idea of the layout, so every
+        // rank must use the same capacity: the largest one asked for.
+        if ( size > 1 )
+        {
+            auto d = Impl::device_alloc<long long>( 1 );
+            const long long mine_cap = (long long)_capacity;
+            long long agreed = mine_cap;
+            cudaStream_t st = comm.stream();
+            Impl::cudaCheck( cudaMemcpyAsync( d.get(), &mine_cap, sizeof( long long ),
+                                              cudaMemcpyHostToDevice, st ),
+                             "SlabPeerHalo: capacity" );
+            Impl::ncclCheck( ncclAllReduce( d.get(), d.get(), 1, ncclInt64, ncclMax, comm.comm(), st ),
+                             "SlabPeerHalo: capacity" );
+            Impl::cudaCheck( cudaMemcpyAsync( &agreed, d.get(), sizeof( long long ),
+                                              cudaMemcpyDeviceToHost, st ),
+                             "SlabPeerHalo: capacity" );
+            Impl::cudaCheck( cudaStreamSynchronize( st ), "SlabPeerHalo: capacity" );
+            _capacity = (std::size_t)agreed;
+        }
+        // my receive windows; handles travel as 2 x 64 bytes per rank: [from_lo | from_hi]
+        unsigned char mine[2 * CB_IPC_HANDLE_BYTES] = { 0 };
+        if ( _lo_rank >= 0 )
+        {
+            Impl::check( cb_p2p_window_create( &_from_lo, (int64_t)_capacity, (int64_t)_tuple_bytes ),
+                         "Cabana::SlabPeerHalo: window" );
+            Impl::check( cb_p2p_window_get_handle( _from_lo, mine ), "cb_p2p_window_get_handle" );
+        }
+        if ( _hi_rank >= 0 )
+        {
+            Impl::check( cb_p2p_window_create( &_from_hi, (int64_t)_capacity, (int64_t)_tuple_bytes ),
+                         "Cabana::SlabPeerHalo: window" );
+            Impl::check( cb_p2p_window_get_handle( _from_hi, mine + CB_IPC_HANDLE_BYTES ),
+                         "cb_p2p_window_get_handle" );
+        }
+        std::vector<unsigned char> all( (std::size_t)size * sizeof( mine ) );
+        if ( size > 1 )
+        {
+            auto d_send = Impl::device_alloc<unsigned char>( sizeof( mine ) );
+            auto d_recv = Impl::device_alloc<unsigned char>( all.size() );
+            cudaStream_t st = comm.stream();
+            Impl::cudaCheck( cudaMemcpyAsync( d_send.get(), mine, sizeof( mine ),
+                                              cudaMemcpyHostToDevice, st ),
+                             "SlabPeerHalo: handle upload" );
+            Impl::ncclCheck( ncclAllGather( d_send.get(), d_recv.get(), sizeof( mine ), ncclChar,
+                                            comm.comm(), st ),
+                             "SlabPeerHalo: ncclAllGather" );
+            Impl::cudaCheck( cudaMemcpyAsync( all.data(), d_recv.get(), all.size(),
+                                              cudaMemcpyDeviceToHost, st ),
+                             "SlabPeerHalo: handle download" );
+            Impl::cudaCheck( cudaStreamSynchronize( st ), "SlabPeerHalo: sync" );
+            // my low-face layer lands in the lower neighbour's "from_hi" window and vice versa
+            if ( _lo_rank >= 0 )
+                Impl::check( cb_p2p_window_open( all.data() + (std::size_t)_lo_rank * sizeof( mine ) +
+                                                     CB_IPC_HANDLE_BYTES,
+                                                 &_peer_lo ),
+                             "Cabana::SlabPeerHalo: cannot map the lower neighbour's window" );
+            if ( _hi_rank >= 0 )
+                Impl::check( cb_p2p_window_open( all.data() + (std::size_t)_hi_rank * sizeof( mine ),
+                                                 &_peer_hi ),
+                             "Cabana::SlabPeerHalo: cannot map the upper neighbour's window" );
+            barrier(); // every window is mapped before anyone pushes
+        }
+    }
+    SlabPeerHalo( const SlabPeerHalo& ) = delete;
+    SlabPeerHalo& operator=( const SlabPeerHalo& ) = delete;
+    //! Collective: no neighbour may still be pushing when the windows go away.
+    void close()
+    {
+        if ( _closed )
+            return;
+        cudaStreamSynchronize( _comm.stream() );
+        if ( _comm.size() > 1 )
+            barrier();
+        if ( _peer_lo )
+            cb_p2p_window_close( _peer_lo );
+        if ( _peer_hi )
+            cb_p2p_window_close( _peer_hi );
+        if ( _from_lo )
+            cb_p2p_window_destroy( _from_lo );
+        if ( _from_hi )
+            cb_p2p_window_destroy( _from_hi );
+        _peer_lo = _peer_hi = nullptr;
+        _from_lo = _from_hi = nullptr;
+        _closed = true;
+    }
+    ~SlabPeerHalo()
+    {
+        // (not collective: call close() on every rank before the object dies)
+        if ( !_closed )
+        {
+            cudaStreamSynchronize( _comm.stream() );
+            if ( _peer_lo )
+                cb_p2p_window_close( _peer_lo );
+            if ( _peer_hi )
+                cb_p2p_window_close( _peer_hi );
+            if ( _from_lo )
+                cb_p2p_window_destroy( _from_lo );
+            if ( _from_hi )
+                cb_p2p_window_destroy( _from_hi );
+        }
+    }
+
+    //! The local grid of this rank along x: the slab widened by the halo on its interior faces.
+    double localGridMinX() const { return _lo_rank >= 0 ? _lo - _hw : _lo; }
+    double localGridMaxX() const { return _hi_rank >= 0 ? _hi + _hw : _hi; }
+
+    //! One step: gather the ghosts of `members` (the first must be the positions `x_all`; all hold
+    //! room for owned + ghost elements) and build `list` over x_all[0 : num_local + ghosts) with
+    //! begin = 0, end = num_local.  Returns { ghosts from the lower, from the upper neighbour }.
+    template <class VerletListType, class PositionSlice, class ArrayType, class... Slices>
+    std::pair<std::size_t, std::size_t>
+    step( VerletListType& list, const PositionSlice& x_all, const std::size_t num_local,
+          const double neighborhood_radius, const double cell_size_ratio,
+          const ArrayType& grid_min, const ArrayType& grid_max, const Slices&... more_members )
+    {
+        auto fields = Impl::fields_of( x_all, more_members... );
+        const int nf = (int)fields.size();
+        if ( (std::size_t)cb_comm_tuple_bytes( fields.data(), nf ) != _tuple_bytes )
+            throw std::runtime_error( "Cabana::SlabPeerHalo::step: members do not match the windows" );
+        const std::size_t need = 2 * ( num_local ? num_local : 1 );
+        if ( _steer_n < need )
+        {
+            _steer = Impl::device_alloc<std::uint32_t>( need + need / 8 );
+            _steer_n = need + need / 8;
+        }
+        ++_seq;
+        const cb_positions xd = x_all.positions();
+        const double mn[3] = { (double)grid_min[0], (double)grid_min[1], (double)grid_min[2] };
+        const double mx[3] = { (double)grid_max[0], (double)grid_max[1], (double)grid_max[2] };
+        int64_t counts[2] = { 0, 0 };
+        list.buildThrough(
+            [&]( cb_verlet* h, int algorithm, int layout, int build_op )
+            {
+                Impl::check( cb_slab_step( h, &xd, fields.data(), nf, (int64_t)num_local, _lo + _hw,
+                                           _hi - _hw, _peer_lo, _peer_hi, _from_lo, _from_hi,
+                                           (int64_t)_capacity, _seq, _steer.get(),
+                                           neighborhood_radius, cell_size_ratio, mn, mx, 0,
+                                           algorithm, layout, build_op, counts, _comm.stream() ),
+                             "Cabana::SlabPeerHalo::step" );
+            } );
+        return { (std::size_t)counts[0], (std::size_t)counts[1] };
+    }
+
+  private:
+    void barrier()
+    {
+        auto d = Impl::device_alloc<int>( 1 );
+        cudaStream_t st = _comm.stream();
+        Impl::cudaCheck( cudaMemsetAsync( d.get(), 0, sizeof( int ), st ), "SlabPeerHalo: barrier" );
+        Impl::ncclCheck( ncclAllReduce( d.get(), d.get(), 1, ncclInt, ncclSum, _comm.comm(), st ),
+                         "SlabPeerHalo: barrier" );
+        Impl::cudaCheck( cudaStreamSynchronize( st ), "SlabPeerHalo: barrier" );
+    }
+    NcclCommunicator _comm;
+    std::size_t _capacity, _tuple_bytes;
+    double _lo = 0.0, _hi = 0.0, _hw = 0.0;
+    int _lo_rank = -1, _hi_rank = -1;
+    cb_p2p_window* _from_lo = nullptr;
+    cb_p2p_window* _from_hi = nullptr;
+    void* _peer_lo = nullptr;
+    void* _peer_hi = nullptr;
+    std::shared_ptr<std::uint32_t> _steer;
+    std::size_t _steer_n = 0;
+    std::uint64_t _seq = 0;
+    bool _closed = false;
+};
+
 } // namespace Cabana
 
 #endif // CABANA_B200_COMM_HPP

@@ -445,6 +445,9 @@ int64_t cb_comm_tuple_bytes(const cb_field* fields_h, int num_fields);
 typedef struct cb_p2p_window cb_p2p_window;
 #define CB_IPC_HANDLE_BYTES 64
 /* capacity_tuples per buffer; tuple_bytes from cb_comm_tuple_bytes */
+/* (capacity_tuples and tuple_bytes must be the same on both sides of a face: the pusher computes
+ * the offsets inside the neighbour's window from the values IT passes to cb_slab_halo_push /
+ * cb_slab_step.) */
 int cb_p2p_window_create(cb_p2p_window** out, int64_t capacity_tuples, int64_t tuple_bytes);
 int cb_p2p_window_destroy(cb_p2p_window* w);
 int cb_p2p_window_get_handle(const cb_p2p_window* w, void* handle_h /* 64 bytes */);

@@ -6,6 +6,7 @@
 //   test_cabana_comm.bin <rank> <world> <id-file>
 // rank 0 writes the ncclUniqueId to <id-file>; the other ranks wait for it.  world = 1 runs the
 // same cases with this rank as its only neighbour (a one-GPU box).
+#include <algorithm>
 #include <array>
 #include <chrono>
 #include <cstdio>
@@ -292,6 +293,104 @@ static void testDistributorAllToAll( const Cabana::NcclCommunicator& comm, bool 
     EXPECT_TRUE( ok );
 }
 
+// ---- SlabPeerHalo::step: ghosts through peer-memory windows + owner-local VerletList ----------
+// Every rank draws the same pseudo-random particles, owns those of its x slab, and the union of
+// the owner-local lists (ghost ids mapped back through a global-id member that travels with the
+// positions) must be the brute-force neighbour list of the whole box.
+static void testSlabPeerStep( const Cabana::NcclCommunicator& comm )
+{
+    const int size = comm.size(), rank = comm.rank();
+    const double r = 3.0, slab = 12.0, L = slab * size, Lyz = 18.0;
+    const int n_all = 3000 * size;
+    std::vector<double> X( 3 * (std::size_t)n_all );
+    unsigned long long sd = 12345ull;
+    auto rnd = [&]()
+    {
+        sd = sd * 6364136223846793005ull + 1442695040888963407ull;
+        return (double)( sd >> 11 ) / 9007199254740992.0;
+    };
+    for ( int i = 0; i < n_all; ++i )
+    {
+        X[3 * i] = rnd() * L;
+        X[3 * i + 1] = rnd() * Lyz;
+        X[3 * i + 2] = rnd() * Lyz;
+    }
+    std::vector<double> bounds( size + 1 );
+    for ( int g = 0; g <= size; ++g )
+        bounds[g] = slab * g;
+    std::vector<int> own;
+    for ( int i = 0; i < n_all; ++i )
+    {
+        int g = (int)( X[3 * i] / slab );
+        g = g > size - 1 ? size - 1 : g;
+        if ( g == rank )
+            own.push_back( i );
+    }
+    const std::size_t nl = own.size(), cap_face = nl + 16, cap = nl + 2 * cap_face;
+    std::vector<double> hx( 3 * cap, 0.0 );
+    std::vector<int> hg( cap, -1 );
+    for ( std::size_t k = 0; k < nl; ++k )
+    {
+        for ( int d = 0; d < 3; ++d )
+            hx[3 * k + d] = X[3 * own[k] + d];
+        hg[k] = own[k];
+    }
+    DeviceArray<double> dx( hx );
+    DeviceArray<int> dg( hg );
+    Cabana::View2D<double, 3> x_all( dx.p, cap );
+    IntView gid( dg.p, cap );
+    cb_field f[2] = { x_all.field(), gid.field() };
+    const std::size_t tb = (std::size_t)cb_comm_tuple_bytes( f, 2 );
+    Cabana::SlabPeerHalo halo( comm, bounds, r, cap_face, tb );
+    using ListT = Cabana::VerletList<Cabana::DeviceSpace, Cabana::FullNeighborTag,
+                                     Cabana::VerletLayoutCSR, Cabana::TeamOpTag>;
+    ListT list;
+    const double gmin[3] = { halo.localGridMinX(), 0.0, 0.0 };
+    const double gmax[3] = { halo.localGridMaxX(), Lyz, Lyz };
+    for ( int rep = 0; rep < 3; ++rep ) // (rebuilds take the speculative fill pass)
+    {
+        const auto ng = halo.step( list, x_all, nl, r, 1.0, gmin, gmax, gid );
+        cudaStreamSynchronize( comm.stream() );
+        const std::size_t ntot = nl + ng.first + ng.second;
+        EXPECT_EQ( list._data.num_particles, ntot );
+        if ( size > 1 )
+            EXPECT_TRUE( ng.first + ng.second > 0 );
+        else
+            EXPECT_EQ( ng.first + ng.second, (std::size_t)0 );
+        std::vector<int> counts( ntot ), offsets( ntot ), nb( list._data.total ? list._data.total : 1 );
+        cudaMemcpy( counts.data(), list._data.counts, sizeof( int ) * ntot, cudaMemcpyDeviceToHost );
+        cudaMemcpy( offsets.data(), list._data.offsets, sizeof( int ) * ntot, cudaMemcpyDeviceToHost );
+        cudaMemcpy( nb.data(), list._data.neighbors, sizeof( int ) * list._data.total,
+                    cudaMemcpyDeviceToHost );
+        const auto g_all = dg.host();
+        int bad = 0;
+        for ( std::size_t k = nl; k < ntot; ++k )
+            bad += counts[k] != 0; // ghost rows stay empty
+        for ( std::size_t k = 0; k < nl && bad == 0; ++k )
+        {
+            const int i = own[k];
+            std::vector<int> want, got;
+            for ( int j = 0; j < n_all; ++j )
+            {
+                if ( j == i )
+                    continue;
+                const double ddx = X[3 * i] - X[3 * j], ddy = X[3 * i + 1] - X[3 * j + 1],
+                             ddz = X[3 * i + 2] - X[3 * j + 2];
+                volatile double sx = ddx * ddx, sy = ddy * ddy, sz = ddz * ddz; // (no contraction)
+                if ( ( sx + sy ) + sz <= r * r )
+                    want.push_back( j );
+            }
+            for ( int c = 0; c < counts[k]; ++c )
+                got.push_back( g_all[nb[offsets[k] + c]] );
+            std::sort( got.begin(), got.end() );
+            if ( got != want )
+                ++bad;
+        }
+        EXPECT_EQ( bad, 0 );
+    }
+    halo.close();
+}
+
 int main( int argc, char** argv )
 {
     if ( argc < 4 )
@@ -352,6 +451,7 @@ int main( int argc, char** argv )
             testDistributorStay( comm, topo != 0 );
             testDistributorAllToAll( comm, topo != 0 );
         }
+        testSlabPeerStep( comm );
     }
     catch ( const std::exception& e )
     {

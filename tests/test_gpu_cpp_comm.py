@@ -31,8 +31,9 @@ def _run_world(world):
                     q.kill()
                 raise
             outs.append((p.returncode, out))
+    everything = "\n".join(f"--- rank {r} rc={rc}\n{out}" for r, (rc, out) in enumerate(outs))
     for r, (rc, out) in enumerate(outs):
-        assert rc == 0, f"rank {r} rc={rc}\n{out}"
+        assert rc == 0, f"rank {r} rc={rc}\n{everything}"
         assert f"rank {r}/{world}: ALL CABANA COMM TESTS PASSED" in out, out
 
 
